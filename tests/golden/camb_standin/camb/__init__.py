@@ -1,0 +1,72 @@
+"""Test-side stand-in for the (absent) `camb` package.
+
+TEST INFRASTRUCTURE ONLY.  It exists so that the *unmodified* reference
+(`/root/reference/hmvec`) can be imported in the build container to generate golden
+vectors (tests/golden/make_golden.py).  It is never imported by the product package
+`hmvec_b200` and must never shadow a real camb: make_golden.py only prepends this
+directory to sys.path after checking that `import camb` fails.
+
+It provides the handful of calls the reference makes at
+cosmology.py:164-179 (set_params / get_background) and cosmology.py:83-130
+(hubble_parameter, h_of_z, comoving_radial_distance, angular_diameter_distance,
+get_Omega) with flat-LCDM closed forms:
+    H(z)  = H0 sqrt(Om (1+z)^3 + 1 - Om),   Om = (ombh2+omch2)/h^2
+    chi(z)= c * int_0^z dz'/H(z')           (128-node Gauss-Legendre)
+    D_A   = chi/(1+z)
+"""
+import numpy as np
+from . import model  # noqa: F401  (reference does `from camb import model`)
+
+_C_KMS = 299792.458
+_GL_X, _GL_W = np.polynomial.legendre.leggauss(128)
+
+
+class _Pars(object):
+    def __init__(self, **kw):
+        self.kw = dict(kw)
+        self.YHe = kw.get("YHe", None)
+        if self.YHe is None:
+            self.YHe = 0.24
+        self.WantTransfer = False
+        self.WantTensors = False
+        self.H0 = kw["H0"]
+        self.ombh2 = kw["ombh2"]
+        self.omch2 = kw["omch2"]
+
+
+class _Background(object):
+    def __init__(self, pars):
+        self.H0 = float(pars.H0)
+        h = self.H0 / 100.0
+        self.om = (pars.ombh2 + pars.omch2) / h ** 2
+
+    def hubble_parameter(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        return self.H0 * np.sqrt(self.om * (1.0 + z) ** 3 + (1.0 - self.om))
+
+    def h_of_z(self, z):
+        return self.hubble_parameter(z) / _C_KMS
+
+    def comoving_radial_distance(self, z):
+        zz = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        # nodes on [0, z] for every z at once
+        t = 0.5 * zz[:, None] * (_GL_X[None, :] + 1.0)
+        f = _C_KMS / self.hubble_parameter(t)
+        chi = 0.5 * zz * np.sum(f * _GL_W[None, :], axis=1)
+        if np.ndim(z) == 0:
+            return float(chi[0])
+        return chi.reshape(np.shape(z))
+
+    def angular_diameter_distance(self, z):
+        return self.comoving_radial_distance(z) / (1.0 + np.asarray(z, dtype=np.float64))
+
+    def get_Omega(self, what):
+        return 0.0
+
+
+def set_params(**kw):
+    return _Pars(**kw)
+
+
+def get_background(pars):
+    return _Background(pars)

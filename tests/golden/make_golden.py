@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; never at test/bench time):
+
+    python tests/golden/make_golden.py [case ...]
+
+The reference (simonsobs/hmvec) is imported from /root/reference with `camb` replaced by the
+test-side stand-in in tests/golden/camb_standin (flat-LCDM closed forms) and accuracy='low', which
+routes both Pzk (hmvec.py:98-99) and the sigma^2 spectrum (cosmology.py:259-260) through the
+reference's own EH98 P_lin_approx (cosmology.py:391-402).  With that the reference's own files
+hmvec.py / fft.py / utils.py / params.py / cosmology.py execute the whole hot path.
+`limber_integral` cannot run under SciPy>=1.14 (interp2d / dfitpack.bispeu were removed), so
+`scipy.interpolate.interp2d` and `dfitpack.bispeu` are shimmed for the duration of this script
+with RectBivariateSpline(kx=ky=1) -- SciPy's documented bug-for-bug replacement; the reference's
+own limber_integral body (cosmology.py:867-904) is what executes.
+"""
+import os
+import sys
+import time
+import types
+import warnings
+
+import numpy as np
+import scipy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+warnings.filterwarnings("ignore")
+
+
+def _import_reference():
+    try:
+        import camb  # noqa: F401
+        raise SystemExit("a real camb is installed; the stand-in must not shadow it")
+    except ImportError:
+        pass
+    sys.path.insert(0, os.path.join(HERE, "camb_standin"))
+    sys.path.insert(0, REF)
+    # --- shims for SciPy>=1.14 (see module docstring) -------------------------------------
+    import hmvec  # noqa
+    import hmvec.cosmology as hcosm
+    import scipy.interpolate._fitpack as _fp
+    from scipy.interpolate import RectBivariateSpline
+
+    class _Interp2d(object):
+        """interp2d(ks, zs, Pzks[nz,nk]) for a regular grid == FITPACK regrid with kx=ky=1, s=0."""
+
+        def __init__(self, x, y, z, bounds_error=False, **kw):
+            tx, ty, c = RectBivariateSpline(np.asarray(x), np.asarray(y), np.asarray(z).T, kx=1, ky=1, s=0).tck
+            self.tck = (tx, ty, c, 1, 1)
+
+    hcosm.interp2d = _Interp2d
+    # reference: si.dfitpack.bispeu(tx,ty,c,kx,ky,x,y)[0]  ->  same FITPACK routine, new home
+    hcosm.si = types.SimpleNamespace(dfitpack=types.SimpleNamespace(bispeu=_fp.bispeu))
+    return hmvec
+
+
+def _meta():
+    return dict(numpy_version=np.__version__, scipy_version=scipy.__version__,
+                generated=time.strftime("%Y-%m-%d"), reference="simonsobs/hmvec @ /root/reference")
+
+
+SPECTRA = [("mm", "nfw", "nfw"), ("ee", "electron", "electron"), ("me", "nfw", "electron"),
+           ("gg", "g", "g"), ("gm", "g", "nfw"), ("ge", "g", "electron")]
+
+
+def _common(h, out):
+    out.update(zs=h.zs, ks=h.ks, ms=h.ms, Pzk=h.Pzk, sigma2=h.sigma2, nzm=h.nzm, bh=h.bh,
+               hubble=h.hubble_parameter(h.zs), h_of_z=h.h_of_z(h.zs), chi=h.comoving_radial_distance(h.zs),
+               rho_crit=h.rho_critical_z(h.zs), rho_m0=h.rho_matter_z(0.), deltav=h.deltav(h.zs),
+               cs=h.concentration(), rvirs=h.rvir(h.ms[None, :], h.zs[:, None]))
+
+
+def _hod(h, name, out, tag=None):
+    tag = tag or name
+    for k in ("Nc", "Ns", "NsNsm1", "NcNs", "ngal", "bg", "log10mthresh"):
+        out["hod_%s_%s" % (tag, k)] = np.asarray(h.hods[name][k])
+
+
+def case_readme(hm):
+    """C1-C3 of SURVEY 8(d) on the README grid (README.rst:55-84)."""
+    zs = np.linspace(0., 3., 20)
+    ms = np.geomspace(2e10, 1e17, 200)
+    ks = np.geomspace(1e-4, 100, 1001)
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+    out = {}
+    _common(h, out)
+    out["sPzk_sub"] = h.sPzk[:, ::10]
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    # cubes are 32 MB each: keep a strided sample (every 8th mass, every 4th k) + two full halos
+    out["uk_nfw_sub"] = h.uk_profiles["nfw"][:, ::8, ::4]
+    out["uk_e_sub"] = h.uk_profiles["electron"][:, ::8, ::4]
+    out["uk_nfw_rows"] = h.uk_profiles["nfw"][[0, 7, 19]][:, [0, 100, 199]]
+    out["uk_e_rows"] = h.uk_profiles["electron"][[0, 7, 19]][:, [0, 100, 199]]
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    h.add_hod("g2", ngal=np.geomspace(1e-3, 1e-5, zs.size))
+    out["g2_ngal_target"] = np.geomspace(1e-3, 1e-5, zs.size)
+    _hod(h, "g", out)
+    _hod(h, "g2", out)
+    for tag, a, b in SPECTRA + [("g2g2", "g2", "g2"), ("g2e", "g2", "electron")]:
+        out["P1h_" + tag] = h.get_power_1halo(a, b)
+        out["P2h_" + tag] = h.get_power_2halo(a, b)
+    return out
+
+
+MINI_ZS = np.array([0.01, 0.4, 0.8, 0.81, 1.6, 3.0])
+MINI_MS = np.geomspace(1e11, 1e16, 64)
+MINI_KS = np.geomspace(1e-3, 50, 257)
+
+
+def case_mini(hm):
+    """Full-resolution small grid exercising every branch of the path incl. pressure and Limber."""
+    zs, ms, ks = MINI_ZS, MINI_MS, MINI_KS
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+    out = {}
+    _common(h, out)
+    out["sPzk_sub"] = h.sPzk[:, ::10]
+    # mass conversion as used inside add_battaglia_profile (hmvec.py:216-225)
+    rhoc = h.rho_critical_z(zs)
+    m200 = hm.mdelta_from_mdelta(ms, h.concentration(), rhoc * h.deltav(zs), 200. * rhoc)
+    out["m200c"] = m200
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    h.add_battaglia_profile("electron_sh", family="SH", xmax=10, nxs=2000)
+    h.add_battaglia_profile("electron_ov", family="AGN", xmax=20, nxs=5000,
+                            param_override={"battaglia_gas_gamma": -0.3, "rho0_A0": 3000., "alpha_alphaz": 0.25,
+                                            "not_a_key": 1.0})
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    h.add_nfw_profile("nfwnum", numeric=True, nxs=8000, xmax=100)
+    out["uk_nfw"] = h.uk_profiles["nfw"]
+    out["uk_e"] = h.uk_profiles["electron"]
+    out["uk_e_sh"] = h.uk_profiles["electron_sh"]
+    out["uk_e_ov"] = h.uk_profiles["electron_ov"]
+    out["uk_nfwnum"] = h.uk_profiles["nfwnum"]
+    out["pk_y"] = h.pk_profiles["y"]
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    ngt = np.geomspace(2e-3, 3e-5, zs.size)
+    h.add_hod("g2", ngal=ngt)
+    h.add_hod("gmin", mthresh=10 ** (10.2 + 0.1 * zs), corr="min")
+    h.add_hod("gcen", mthresh=10 ** 10.8 + zs * 0., central_profile_name="electron", satellite_profile_name="nfwnum")
+    h.add_hod("gov", mthresh=10 ** 10.5 + zs * 0.,
+              param_override={"hod_sig_log_mstellar": 0.3, "hod_alphasat": 1.1, "hod_Bsat": 8.0, "hod_betacut": 0.5})
+    out["g2_ngal_target"] = ngt
+    for n in ("g", "g2", "gmin", "gcen", "gov"):
+        _hod(h, n, out)
+    pairs = SPECTRA + [("g2g2", "g2", "g2"), ("g2e", "g2", "electron"), ("gming", "gmin", "gmin"),
+                       ("gminm", "gmin", "nfw"), ("gcengcen", "gcen", "gcen"), ("gcene", "gcen", "electron"),
+                       ("gg2", "g", "g2"), ("govgov", "gov", "gov"), ("yy", "y", "y"), ("ym", "y", "nfw"),
+                       ("yg", "y", "g"), ("nn", "nfwnum", "nfwnum"), ("shsh", "electron_sh", "electron_sh"),
+                       ("ovm", "electron_ov", "nfw"), ("eg", "electron", "g")]
+    for tag, a, b in pairs:
+        out["P1h_" + tag] = h.get_power_1halo(a, b)
+        out["P2h_" + tag] = h.get_power_2halo(a, b)
+    b1 = np.linspace(1.2, 2.0, zs.size)
+    b2 = np.linspace(0.9, 1.4, zs.size)
+    out["b1_in"], out["b2_in"] = b1, b2
+    out["P2h_ge_bin"] = h.get_power_2halo("g", "electron", b1_in=b1, b2_in=b2)
+    # Limber (cosmology.py:536-597, 867-904)
+    ells = np.geomspace(10, 1e4, 40)
+    out["ells"] = ells
+    Pmm = out["P1h_mm"] + out["P2h_mm"]
+    Pgm = out["P1h_gm"] + out["P2h_gm"]
+    Pgg = out["P1h_gg"] + out["P2h_gg"]
+    Pyy = out["P1h_yy"] + out["P2h_yy"]
+    out["lens_window_25"] = h.lensing_window(zs, 2.5)
+    out["C_kk"] = h.C_kk(ells, zs, ks, Pmm, lzs1=2.5, lzs2=2.5)
+    out["C_kg"] = h.C_kg(ells, zs, ks, Pgm, gzs=0.8, lzs=2.5)
+    out["C_yy"] = h.C_yy(ells, zs, ks, Pyy)
+    lz = np.linspace(0.2, 2.8, 30)
+    ldn = lz ** 2 * np.exp(-(lz / 0.9) ** 1.5)
+    out["lz"], out["ldndz"] = lz, ldn
+    out["lens_window_dndz"] = h.lensing_window(zs, lz, ldn)
+    out["C_kk_dndz"] = h.C_kk(ells, zs, ks, Pmm, lzs1=lz, ldndz1=ldn, lzs2=1.1)
+    gz = np.linspace(0.05, 2.5, 25)
+    gdn = gz * np.exp(-gz / 0.5)
+    out["gz"], out["gdndz"] = gz, gdn
+    out["C_kg_dndz"] = h.C_kg(ells, zs, ks, Pgm, gzs=gz, gdndz=gdn, lzs=1100.)
+    out["C_gg_dndz"] = h.C_gg(ells, zs, ks, Pgg, gzs=gz, gdndz=gdn)
+    return out
+
+
+def case_mini_mean(hm):
+    """mdef='mean' branch (hmvec.py:111-115,166-169,219-220)."""
+    zs, ms, ks = MINI_ZS, MINI_MS, MINI_KS
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low', mdef='mean',
+                     params={"omch2": 0.125, "H0": 70.0, "ns": 0.97, "st_a": 0.75, "kstar_damping": 0.02})
+    out = {}
+    _common(h, out)
+    h.add_battaglia_profile("electron", xmax=20, nxs=5000)
+    out["uk_nfw"] = h.uk_profiles["nfw"]
+    out["uk_e"] = h.uk_profiles["electron"]
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    _hod(h, "g", out)
+    for tag, a, b in SPECTRA:
+        out["P1h_" + tag] = h.get_power_1halo(a, b)
+        out["P2h_" + tag] = h.get_power_2halo(a, b)
+    return out
+
+
+def case_largeslab(hm):
+    """Two redshifts at the LARGE grid's M and k resolution (2000 M x 10000 k): only [nz,nk] outputs kept."""
+    zs = np.array([0.01, 3.0])
+    ms = np.geomspace(2e10, 1e17, 2000)
+    ks = np.geomspace(1e-4, 100, 10000)
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+    out = dict(zs=zs, ms=ms, ks=ks, sigma2=h.sigma2, nzm=h.nzm, bh=h.bh)
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    out["uk_nfw_rows"] = h.uk_profiles["nfw"][:, ::400]
+    out["uk_e_rows"] = h.uk_profiles["electron"][:, ::400]
+    for tag, a, b in SPECTRA:
+        out["P1h_" + tag] = h.get_power_1halo(a, b)
+        out["P2h_" + tag] = h.get_power_2halo(a, b)
+    return out
+
+
+def case_kat(hm):
+    """Known-answer pieces the reference's own code names."""
+    from hmvec import fft as rfft_mod, utils as rutils
+    out = {}
+    xs = np.linspace(0., 30., 6001)[1:]
+    kt, U = rfft_mod.fft_integral(xs, np.exp(-xs ** 2 / 2.))
+    out["gauss_xs"], out["gauss_kt"], out["gauss_U"] = xs, kt, U
+    out["gauss_analytic"] = rfft_mod.analytic_fft_integral(kt)
+    x = np.array([2., 4., 6.])
+    out["bisect_x"] = x
+    out["bisect_y"] = rutils.vectorized_bisection_search(x, lambda y: np.sqrt(y), (1, 40), 'increasing',
+                                                         rtol=1e-4, verbose=False)
+    return out
+
+
+CASES = dict(readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
+
+if __name__ == "__main__":
+    hm = _import_reference()
+    which = sys.argv[1:] or list(CASES)
+    for name in which:
+        t = time.time()
+        out = CASES[name](hm)
+        out = {k: np.asarray(v) for k, v in out.items()}
+        for k, v in _meta().items():
+            out["_meta_" + k] = np.asarray(v)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-10s %6.1fs  %7.2f MB  %d arrays" % (name, time.time() - t, os.path.getsize(path) / 1e6, len(out)))
