@@ -1,0 +1,177 @@
+// k_sigma2.cu -- K3: sigma^2(R,z) contraction, K3b: Sheth-Tormen mass function and bias.
+// Reference arithmetic: cosmology.py:30-38 (Wkr), :245-269 (get_sigma2_R), hmvec.py:133-185.
+#include "common.cuh"
+
+namespace hmv {
+
+// ---- W^2 table: W2T[k'][m] = W(ks[k'] R[m])^2, k' major so the contraction reads it coalesced in m ----
+__global__ void w2_table_kernel(int nm, int nks, const double* __restrict__ ks, const double* __restrict__ R,
+                                double taylor_switch, double* __restrict__ W2T) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nm * nks) return;
+  const int k = (int)(idx / nm), m = (int)(idx - (long long)k * nm);
+  const double x = ks[k] * R[m];
+  double w;
+  if (x < taylor_switch) {
+    const double xx = x * x;
+    w = 1.0 - 0.1 * xx + 0.00357142857143 * xx * xx;  // cosmology.py:30-32
+  } else {
+    double s, c;
+    sincos(x, &s, &c);
+    w = 3.0 * (s - x * c) / (x * x * x);  // cosmology.py:36
+  }
+  W2T[idx] = w * w;
+}
+
+// ---- contraction C[z][m] = sum_k (sPzk[z][k]*kw[k]) * W2T[k][m] ; register-tiled FP64 GEMM -------------
+constexpr int BM = 32, BN = 64, BK = 16, GT = 256;
+
+__global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks, int kchunk,
+                                                         const double* __restrict__ sPzk,
+                                                         const double* __restrict__ kw,
+                                                         const double* __restrict__ W2T, double* __restrict__ out,
+                                                         long long out_split_stride) {
+  __shared__ double As[BK][BM + 2];
+  __shared__ double Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, microtile 2(z) x 4(m)
+  const int z0 = blockIdx.y * BM, m0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(nks, kbeg + kchunk);
+  double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  // loader indices
+  const int az = tid >> 3, ak = (tid & 7) * 2;     // A: 32 z x 16 k, 2 k per thread
+  const int bk = tid >> 4, bm = (tid & 15) * 4;    // B: 16 k x 64 m, 4 m per thread
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int z = z0 + az, k = k0 + ak + i;
+      As[ak + i][az] = (z < nz && k < kend) ? sPzk[(long long)z * nks + k] * kw[k] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + bk, m = m0 + bm + i;
+      Bs[bk][bm + i] = (k < kend && m < nm) ? W2T[(long long)k * nm + m] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const double a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+      const double b0 = Bs[kk][tx * 4], b1 = Bs[kk][tx * 4 + 1], b2 = Bs[kk][tx * 4 + 2], b3 = Bs[kk][tx * 4 + 3];
+      acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+      acc[0][2] = fma(a0, b2, acc[0][2]); acc[0][3] = fma(a0, b3, acc[0][3]);
+      acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+      acc[1][2] = fma(a1, b2, acc[1][2]); acc[1][3] = fma(a1, b3, acc[1][3]);
+    }
+    __syncthreads();
+  }
+  double* o = out + (long long)blockIdx.z * out_split_stride;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int z = z0 + ty * 2 + i;
+    if (z >= nz) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + tx * 4 + j;
+      if (m < nm) o[(long long)z * nm + m] = acc[i][j];
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(long long n, int nsplit, const double* __restrict__ part,
+                                     double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int p = 0; p < nsplit; ++p) s += part[(long long)p * n + i];  // fixed order: deterministic
+  out[i] = s;
+}
+
+static int sigma2_splits(int nz, int nm, int nks) {
+  const long long tiles = (long long)cdiv(nm, BN) * cdiv(nz, BM);
+  long long s = (2 * 148 + tiles - 1) / tiles;
+  if (s < 1) s = 1;
+  if (s > 32) s = 32;
+  const long long maxs = (nks + BK - 1) / BK;
+  if (s > maxs) s = maxs;
+  return (int)s;
+}
+
+// ---- mass function and bias --------------------------------------------------------------------------
+__global__ void mass_function_kernel(int nz, int nm, const double* __restrict__ sigma2,
+                                     const double* __restrict__ ms, double rho_m0, double A, double a, double p,
+                                     double dc, double* __restrict__ nzm, double* __restrict__ bh) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nz * nm) return;
+  const int z = (int)(idx / nm), m = (int)(idx - (long long)z * nm);
+  const double* s2row = sigma2 + (long long)z * nm;
+  const double s2 = s2row[m];
+  // d ln(sigma^-1) / d ln M with numpy.gradient's stencil (hmvec.py:181-183)
+  const double f0 = -0.5 * log(s2), x0 = log(ms[m]);
+  double g;
+  if (m == 0) {
+    g = (-0.5 * log(s2row[1]) - f0) / (log(ms[1]) - x0);
+  } else if (m == nm - 1) {
+    g = (f0 + 0.5 * log(s2row[m - 1])) / (x0 - log(ms[m - 1]));
+  } else {
+    const double fm = -0.5 * log(s2row[m - 1]), fp = -0.5 * log(s2row[m + 1]);
+    const double hs = x0 - log(ms[m - 1]), hd = log(ms[m + 1]) - x0;
+    const double ca = -hd / (hs * (hd + hs)), cb = (hd - hs) / (hd * hs), cc = hs / (hd * (hd + hs));
+    g = ca * fm + cb * f0 + cc * fp;
+  }
+  const double sig = sqrt(s2);
+  const double nu2a = a * dc * dc / s2;
+  // hmvec.py:141
+  const double f = A * sqrt(2.0 * a / M_PI) * (1.0 + pow(s2 / a / (dc * dc), p)) * (dc / sig) * exp(-0.5 * nu2a);
+  // hmvec.py:156
+  const double b = 1.0 + (nu2a - 1.0) / dc + (2.0 * p / dc) / (1.0 + pow(nu2a, p));
+  const double M = ms[m];
+  nzm[idx] = rho_m0 * f * g / (M * M);
+  bh[idx] = b;
+}
+
+}  // namespace hmv
+
+using namespace hmv;
+
+extern "C" long long hmv_sigma2_ws_doubles(int nz, int nm, int nks) {
+  if (nz <= 0 || nm <= 0 || nks <= 0) return 0;
+  const int s = sigma2_splits(nz, nm, nks);
+  return (long long)nks * nm + (s > 1 ? (long long)s * nz * nm : 0);
+}
+
+extern "C" int hmv_sigma2(int nz, int nm, int nks, const double* sPzk_d, const double* kw_d, const double* ks_sig_d,
+                          const double* R_d, double taylor_switch, double* w2_ws_d, double* sigma2_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nm > 0 && nks > 0, "hmv_sigma2: sizes must be positive (nz=%d nm=%d nks=%d)", nz, nm, nks);
+  HMV_REQUIRE(sPzk_d && kw_d && ks_sig_d && R_d && w2_ws_d && sigma2_d, "hmv_sigma2: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nw = (long long)nm * nks;
+  w2_table_kernel<<<cdiv(nw, 256), 256, 0, st>>>(nm, nks, ks_sig_d, R_d, taylor_switch, w2_ws_d);
+  int rc = check_launch("w2_table_kernel");
+  if (rc) return rc;
+  const int splits = sigma2_splits(nz, nm, nks);
+  int kchunk = cdiv(nks, splits);
+  kchunk = cdiv(kchunk, BK) * BK;
+  dim3 grid(cdiv(nm, BN), cdiv(nz, BM), splits);
+  if (splits == 1) {
+    sigma2_gemm_kernel<<<grid, GT, 0, st>>>(nz, nm, nks, kchunk, sPzk_d, kw_d, w2_ws_d, sigma2_d, 0);
+    return check_launch("sigma2_gemm_kernel");
+  }
+  double* part = w2_ws_d + nw;
+  const long long n = (long long)nz * nm;
+  sigma2_gemm_kernel<<<grid, GT, 0, st>>>(nz, nm, nks, kchunk, sPzk_d, kw_d, w2_ws_d, part, n);
+  rc = check_launch("sigma2_gemm_kernel");
+  if (rc) return rc;
+  splitk_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, splits, part, sigma2_d);
+  return check_launch("splitk_reduce_kernel");
+}
+
+extern "C" int hmv_mass_function(int nz, int nm, const double* sigma2_d, const double* ms_d, double rho_m0,
+                                 double st_A, double st_a, double st_p, double st_deltac, double* nzm_d, double* bh_d,
+                                 void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_mass_function: need nz>0 and nm>=2 (numpy.gradient needs two samples)");
+  HMV_REQUIRE(sigma2_d && ms_d && nzm_d && bh_d, "hmv_mass_function: null pointer");
+  const long long n = (long long)nz * nm;
+  mass_function_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(nz, nm, sigma2_d, ms_d, rho_m0, st_A, st_a,
+                                                                        st_p, st_deltac, nzm_d, bh_d);
+  return check_launch("mass_function_kernel");
+}

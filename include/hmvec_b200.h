@@ -1,0 +1,153 @@
+/* hmvec_b200.h -- C ABI of the B200 (sm_100a) halo-model hot path.
+ *
+ * The reference (simonsobs/hmvec) has no FFI of its own: its boundary is the Python class API
+ * (HaloModel / Cosmology, hmvec/hmvec.py:75-572, hmvec/cosmology.py:506-597,867-904).  This header is
+ * the boundary a maintainer would bind underneath that API (ctypes stub in INTEGRATION.md); every
+ * entry point names the reference lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every `*_d` pointer is a DEVICE pointer to float64 (or int32 where typed so); the caller owns
+ *     every buffer, including workspaces; the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and asynchronous,
+ *     no hidden synchronisation (except hmv_bench_* which time themselves with events);
+ *   - return value 0 = ok, <0 = error (HMV_E_*); hmv_last_error() gives a thread-local message;
+ *   - cubes u(z,M,k) are laid out [nz][nm][ldk] with k fastest and ldk >= nk the padded row stride
+ *     (the Python facade uses ldk = nk rounded up to 16 doubles = 128 B so every row starts on a line);
+ *   - [nz,nm] arrays are row-major with M fastest.
+ */
+#ifndef HMVEC_B200_H
+#define HMVEC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMV_OK 0
+#define HMV_E_ARG (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define HMV_E_CUDA (-2)    /* CUDA launch / runtime error; text in hmv_last_error() */
+#define HMV_E_LIMIT (-3)   /* size exceeds a compiled-in limit (stated in the message) */
+
+int hmv_abi_version(void);
+const char* hmv_last_error(void);
+/* Device sanity: returns compute capability major*10+minor of `device` (100 on B200), <0 on error. */
+int hmv_device_cc(int device);
+
+/* ---- a1: sigma^2(R,z)  (cosmology.py:245-269, Wkr :30-38) -------------------------------------------
+ * sigma2[z,m] = sum_k' sPzk[z,k'] * kw[k'] * W^2(ks_sig[k'] * R[m]),  kw = simpson_weight * k'^2 / (2 pi^2)
+ * (the Simpson rule is linear in the integrand, so the host supplies one weight vector).
+ * w2_ws_d: workspace of hmv_sigma2_ws_doubles() doubles (the W^2 table, k' major, + split-k partials). */
+long long hmv_sigma2_ws_doubles(int nz, int nm, int nks);
+int hmv_sigma2(int nz, int nm, int nks, const double* sPzk_d, const double* kw_d, const double* ks_sig_d,
+               const double* R_d, double taylor_switch, double* w2_ws_d, double* sigma2_d, void* stream);
+
+/* ---- a2: Sheth-Tormen f(sigma), bias, n(M,z)  (hmvec.py:133-185) ------------------------------------
+ * nzm = rho_m0 * f * dln(sigma^-1)/dlnM / M^2 with numpy.gradient's non-uniform stencil along M. */
+int hmv_mass_function(int nz, int nm, const double* sigma2_d, const double* ms_d, double rho_m0, double st_A,
+                      double st_a, double st_p, double st_deltac, double* nzm_d, double* bh_d, void* stream);
+
+/* ---- a3: Duffy concentration and r_vir  (hmvec.py:68-73,111-115,163-176,627) ------------------------
+ * cs = A (h M/2e12)^alpha (1+z)^beta ; rvir = (3M/(4 pi drho1[z]))^(1/3), drho1 = Delta_vir rho_c or 200 rho_m. */
+int hmv_halo_geometry(int nz, int nm, const double* zs_d, const double* ms_d, const double* drho1_d, double duffy_A,
+                      double duffy_alpha, double duffy_beta, double h, double* cs_d, double* rvir_d, void* stream);
+
+/* ---- a5: mass-definition conversion  (hmvec.py:748-798) ---------------------------------------------
+ * Solves M1/mc(C1) = M2/mc(C2(M2)) for M2 by the secant method in ln M2 (start values as scipy.optimize.newton). */
+int hmv_mdelta(int nz, int nm, const double* ms_d, const double* cs_d, const double* drho1_d,
+               const double* drho2_d, double* m2_d, void* stream);
+
+/* ---- a4: analytic NFW u(k|M,z)  (hmvec.py:346-353) --------------------------------------------------*/
+int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, const double* cs_d,
+               const double* rvir_d, double* uk_d, void* stream);
+
+/* ---- a6: Battaglia GNFW per-halo shape parameters  (hmvec.py:215-249,278-316,800-802,856-860,918-927)
+ * The transform kernel evaluates  rho(x) = amp * (x/xc)^gamma * (1 + (x/xc)^alpha)^(-expo)  per halo.
+ * kind 0 (density): xc=1, alpha=fit, expo=(beta+gamma)/alpha, amp=1 (cancels against the mass norm),
+ *                   rs = r200c/2, outscale = 1.
+ * kind 1 (pressure): xc=fit, alpha=pres_alpha, expo=beta, amp = eFrac (omb/omm) 200 m200c G rho_c /(2 r200c) P0,
+ *                   rs = r200c, outscale = 4 pi sigmaT/(me c^2) r200c^3 (1+z)^2 / H(z)   (const passed in `pref`).
+ * fit[9] = (A0, alpha_m, alpha_z) x 3 in the order (rho0|P0, alpha|xc, beta).
+ * Outputs are [nz,nm]: rs, cmax = rvir/rs, xc, alpha, expo, amp, outscale. */
+int hmv_gnfw_params(int kind, int nz, int nm, const double* zs_d, const double* m200c_d, const double* rvir_d,
+                    const double* rhocrit_d, const double* hofz_d, const double* fit9_h, double gamma,
+                    double pres_alpha, double amp_const, double pref, double* rs_d, double* cmax_d, double* xc_d,
+                    double* alpha_d, double* expo_d, double* amp_d, double* outscale_d, void* stream);
+
+/* ---- a7+a8: numerical profile transform + interpolation  (fft.py:35-115) ----------------------------
+ * Per halo: samples x_n=(n+1) xmax/nxs, theta-cut at cmax, trapezoid mass norm, the rFFT-equivalent sine
+ * sums U_j = step sum_n x_n y_n sin(2 pi j n/N), u_j = U_j/kt_j/mnorm, kout_j = kt_j/rs/(1+z), then linear
+ * interpolation onto ks (hold u_1 below the first bin, 0 above the last).  The (z,M,x) cube is never stored.
+ * outscale_d may be NULL (=1).  do_mass_norm as in generic_profile_fft.  ks need not be sorted. */
+int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
+                          double kmax /* = max(ks): bounds the bins computed */, const double* rs_d, const double* cmax_d, const double* xc_d, const double* alpha_d,
+                          const double* expo_d, const double* amp_d, const double* outscale_d, double gamma,
+                          double xmax, int nxs, int do_mass_norm, double* uk_d, void* stream);
+
+/* ---- a9: HOD occupations and their mass integrals  (hmvec.py:634-731, 462-466, 936-957) -------------
+ * hodp[8] = (sig_log_mstellar, alphasat, Bsat, betasat, Bcut, betacut, Msat_override or <=0, Mcut_override or <=0)
+ * corr: 0 = "max", 1 = "min".  Outputs [nz,nm]: Nc, Ns, NsNsm1, NcNs; [nz]: ngal, bg. */
+int hmv_hod(int nz, int nm, const double* zs_d, const double* ms_d, const double* log10mthresh_d,
+            const double* hodp_h, int corr, const double* nzm_d, const double* bh_d, double* Nc_d, double* Ns_d,
+            double* NsNsm1_d, double* NcNs_d, double* ngal_d, double* bg_d, void* stream);
+
+/* ---- a10: mthresh <-> ngal bisection  (utils.py:9-42, hmvec.py:415-433) -----------------------------
+ * Reproduces the reference's all-z loop exactly: every z bisects independently for HMV_BISECT_MAXIT
+ * iterations recording its midpoint and whether |x/x_target - 1| <= rtol; the result is the midpoint of the
+ * first iteration at which ALL z pass.  ws_d: nz*(HMV_BISECT_MAXIT+2) doubles.  iters_d: int32[1], the
+ * iteration count (0 = never converged within HMV_BISECT_MAXIT).  log10mthresh_d [nz] = y * A_log10mthresh. */
+#define HMV_BISECT_MAXIT 64
+int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
+                  const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
+                  double A_log10mthresh, double* ws_d, double* log10mthresh_d, int* iters_d, void* stream);
+
+/* ---- a12-a14: 1-halo + 2-halo mass integrals  (hmvec.py:469-572) ------------------------------------
+ * A tracer leg t(z,M,k) = a[z,M]*UC + b[z,M]*US with UC = uc cube (or 1 when uc_d == NULL) and US = us cube:
+ *   kind 0 matter   : a=0,        b=M/rho_m0         (hmvec.py:488-492)   bias 1
+ *   kind 1 hod      : a=Nc/ngal,  b=Ns/ngal          (hmvec.py:481-486)   bias bg(z)
+ *   kind 2 pressure : a=0,        b=1                (hmvec.py:494-497)   bias 0, no consistency term
+ * Both legs hod   -> 1h integrand (2 UC US NcNs + NsNsm1 US^2)/ngal^2 of leg A     (hmvec.py:477-479,510-511)
+ * Both pressure   -> 1h integrand US_A^2                                          (hmvec.py:512-513)
+ * P1h = trapz_M(n * integrand) * (1-exp(-(k/kstar)^2)) ; P2h = Pzk (I_A + b_A - C_A)(I_B + b_B - C_B). */
+typedef struct {
+  int kind;              /* 0 matter, 1 hod, 2 pressure */
+  const double* us_d;    /* [nz][nm][ldk] */
+  const double* uc_d;    /* [nz][nm][ldk] or NULL */
+  const double* Nc_d;    /* hod only, [nz,nm] */
+  const double* Ns_d;
+  const double* NcNs_d;
+  const double* NsNsm1_d;
+  const double* ngal_d;  /* hod only, [nz] */
+  const double* bias_d;  /* [nz] override (b1_in/b2_in) or NULL: matter 1, hod bg, pressure 0 */
+} hmv_tracer;
+
+/* Workspace size (in doubles) for hmv_power. */
+long long hmv_power_ws_doubles(int nz, int nm);
+/* p1h_d / p2h_d: [nz][nk] dense outputs (either may be NULL). */
+int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d, const double* nzm_d,
+              const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, const hmv_tracer* A,
+              const hmv_tracer* B, double* ws_d, double* p1h_d, double* p2h_d, void* stream);
+
+/* Six spectra {mm, ee, me, gg, gm, ge} in ONE pass over two cubes (u_m = matter profile, also the HOD's
+ * satellite profile with u_c = 1; u_e = second matter-like profile).  Outputs p1h_d/p2h_d: [6][nz][nk]. */
+int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d, const double* nzm_d,
+                  const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, const double* um_d,
+                  const double* ue_d, const double* Nc_d, const double* Ns_d, const double* NcNs_d,
+                  const double* NsNsm1_d, const double* ngal_d, double* ws_d, double* p1h_d, double* p2h_d,
+                  void* stream);
+
+/* ---- a16: Limber integral  (cosmology.py:867-904) ---------------------------------------------------
+ * C_l = trapz_gz( pref[gz] * P(k=(l+1/2)/chi[gz], gz) )  (ngz>1) or pref*P (ngz==1); P by bilinear
+ * interpolation in linear (k,z) with out-of-range coordinates clamped to the table edge. pref = H W1 W2/chi^2. */
+int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const double* zs_d, const double* ks_d,
+               const double* P_d, int ngz, const double* gzs_d, const double* pref_d, const double* chis_d,
+               double* cl_d, void* stream);
+
+/* ---- measurement helpers (bench.py) -------------------------------------------------------------------
+ * hmv_bench_dfma: dependent-chain-free DFMA micro-benchmark; returns achieved FP64 TFLOP/s (2 flop per FMA)
+ * on the current device, timed with CUDA events.  hmv_bench_copy: device copy GB/s (read+write bytes). */
+double hmv_bench_dfma(int iters, void* stream);
+double hmv_bench_copy(const double* src_d, double* dst_d, long long n, int reps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMVEC_B200_H */

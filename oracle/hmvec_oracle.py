@@ -90,9 +90,12 @@ class Background(object):
         return self.hubble(z) / C_KMS
 
     def chi(self, z):
-        zz = np.atleast_1d(np.asarray(z, dtype=np.float64))
-        nodes = 0.5 * zz[:, None] * (self._x[None, :] + 1.0)
-        out = 0.5 * zz * np.sum(self._w[None, :] * C_KMS / self.hubble(nodes), axis=1)
+        zz = np.atleast_1d(np.asarray(z, dtype=np.float64)).reshape(-1)
+        out = np.zeros(zz.size)
+        for p in range(4):  # t = ln(1+z'), 4 panels x 128 nodes
+            lo, hi = np.log1p(zz) * (p / 4.0), np.log1p(zz) * ((p + 1) / 4.0)
+            t = lo[:, None] + 0.5 * (hi - lo)[:, None] * (self._x[None, :] + 1.0)
+            out += 0.5 * (hi - lo) * np.sum(self._w[None, :] * np.exp(t) * C_KMS / self.hubble(np.expm1(t)), axis=1)
         return out.reshape(np.shape(z)) if np.ndim(z) else float(out[0])
 
     # cosmology.py:239-243

@@ -11,7 +11,7 @@ cosmology.py:164-179 (set_params / get_background) and cosmology.py:83-130
 (hubble_parameter, h_of_z, comoving_radial_distance, angular_diameter_distance,
 get_Omega) with flat-LCDM closed forms:
     H(z)  = H0 sqrt(Om (1+z)^3 + 1 - Om),   Om = (ombh2+omch2)/h^2
-    chi(z)= c * int_0^z dz'/H(z')           (128-node Gauss-Legendre)
+    chi(z)= c * int_0^z dz'/H(z')           (Gauss-Legendre in ln(1+z), 4 panels x 128 nodes)
     D_A   = chi/(1+z)
 """
 import numpy as np
@@ -48,11 +48,15 @@ class _Background(object):
         return self.hubble_parameter(z) / _C_KMS
 
     def comoving_radial_distance(self, z):
-        zz = np.atleast_1d(np.asarray(z, dtype=np.float64))
-        # nodes on [0, z] for every z at once
-        t = 0.5 * zz[:, None] * (_GL_X[None, :] + 1.0)
-        f = _C_KMS / self.hubble_parameter(t)
-        chi = 0.5 * zz * np.sum(f * _GL_W[None, :], axis=1)
+        zz = np.atleast_1d(np.asarray(z, dtype=np.float64)).reshape(-1)
+        # substitute t = ln(1+z'): chi = c int_0^{ln(1+z)} e^t / H dt, 4 panels x 128 nodes (good to z ~ 1100)
+        chi = np.zeros(zz.size)
+        for p in range(4):
+            lo = np.log1p(zz) * (p / 4.0)
+            hi = np.log1p(zz) * ((p + 1) / 4.0)
+            t = lo[:, None] + 0.5 * (hi - lo)[:, None] * (_GL_X[None, :] + 1.0)
+            f = np.exp(t) * _C_KMS / self.hubble_parameter(np.expm1(t))
+            chi += 0.5 * (hi - lo) * np.sum(f * _GL_W[None, :], axis=1)
         if np.ndim(z) == 0:
             return float(chi[0])
         return chi.reshape(np.shape(z))
