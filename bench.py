@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- P(k,z) grid points per second for the hmvec hot path on B200 (BASELINE.json metric).
+
+A step = one pass of the whole path over the LARGE synthetic grid (BASELINE.json configs[3]+[4]):
+    zs=linspace(0.01,3,200), ms=geomspace(2e10,1e17,2000), ks=geomspace(1e-4,100,10000), EH98 linear power;
+    sigma^2 -> n(M,z), b -> u_NFW cube -> Battaglia-AGN electron cube (xmax=20, nxs=5000) -> ngal-solved HOD ->
+    {mm,ee,me,gg,gm,ge} 1h+2h spectra -> [all-gather over z] -> Limber C_kk, C_kg at 1000 ells.
+One "grid point" = one (z,k) of one spectrum with both its 1-halo and 2-halo terms: 6*nz*nk points per step.
+With N GPUs the z axis is sharded (nz/N redshifts per rank, total work fixed -> "strong" scaling).
+
+  value : device-resident inputs, CUDA events around K steps, max over ranks
+  e2e   : the same step through pinned HOST buffers (H2D of the linear power + background, D2H of the 12 spectra and
+          the two C_ell), copies inside the timed region
+  --impl reference : the reference algorithm on the host cores (oracle port of the numpy path, one z-slab per worker)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "P(k,z) grid pts/s, Battaglia+HOD 1h+2h"
+UNIT = "pts/s"
+
+
+def grids(a):
+    zs = np.linspace(0.01, 3., a.nz)
+    ms = np.geomspace(2e10, 1e17, a.nm)
+    ks = np.geomspace(1e-4, 100, a.nk)
+    ells = np.geomspace(10, 1e4, a.nl)
+    return zs, ms, ks, ells
+
+
+def workload_name(a):
+    return "C4+C5: zs=%d, ms=%d (2e10-1e17), ks=%d (1e-4-100), Battaglia AGN electron (xmax=20,nxs=5000) + ngal-HOD, " \
+           "six spectra 1h+2h, Limber C_kk/C_kg at %d ells" % (a.nz, a.nm, a.nk, a.nl)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's numpy path, one z-slab per worker process
+# ---------------------------------------------------------------------------------------------------------
+def _oracle_slab(job):
+    zs, ms, ks, ngal = job
+    import warnings
+    warnings.filterwarnings("ignore")
+    from oracle import hmvec_oracle as orc
+    t = time.perf_counter()
+    o = orc.OracleHaloModel(zs, ks, ms)
+    o.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    o.add_hod("g", ngal=ngal)
+    chk = 0.0
+    for a, b in (("nfw", "nfw"), ("electron", "electron"), ("nfw", "electron"), ("g", "g"), ("g", "nfw"),
+                 ("g", "electron")):
+        chk += float(np.sum(o.get_power_1halo(a, b)[:, ::97])) + float(np.sum(o.get_power_2halo(a, b)[:, ::97]))
+    return time.perf_counter() - t, chk
+
+
+def cpu_workers():
+    n = os.cpu_count() or 1
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available / 4e9)))   # ~3 GB peak RSS per 1-z slab
+    except Exception:
+        pass
+    return max(1, min(n, 64))
+
+
+def cpu_sample(a, nworkers, zper=1):
+    """Time `nworkers` concurrent slabs of `zper` redshifts each at full M,k resolution; returns (pts/s, seconds)."""
+    zs, ms, ks, _ = grids(a)
+    ngal = np.geomspace(1e-3, 1e-5, zs.size)
+    pick = np.linspace(0, zs.size - 1, nworkers * zper).round().astype(int)
+    jobs = [(zs[pick[i * zper:(i + 1) * zper]], ms, ks, ngal[pick[i * zper:(i + 1) * zper]]) for i in range(nworkers)]
+    t = time.perf_counter()
+    if nworkers == 1:
+        _oracle_slab(jobs[0])
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(nworkers) as pool:
+            pool.map(_oracle_slab, jobs)
+    dt = time.perf_counter() - t
+    return 6.0 * nworkers * zper * ks.size / dt, dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P = cpu_workers()
+    for _ in range(a.warmup if a.warmup < 1 else 1):      # one warm-up step is enough to page numpy/scipy in
+        cpu_sample(a, P)
+    vals, secs = [], []
+    for _ in range(a.steps):
+        v, dt = cpu_sample(a, P)
+        vals.append(v)
+        secs.append(dt)
+    total_pts = 6.0 * P * a.nk * a.steps
+    value = total_pts / sum(secs)
+    sample = "%d concurrent 1-redshift slabs (of %d z) at full %d M x %d k resolution per step, whole path except " \
+             "Limber" % (P, a.nz, a.nm, a.nk)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * sum(secs) / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": workload_name(a), "parallelism": "host processes x%d" % P},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """Polls SM clock and throttle reasons through NVML from a thread while the timed region runs."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80))
+
+    def __init__(self, index, period=0.01):
+        import threading
+        self.sm, self.bits, self.mx, self.power = [], 0, None, []
+        self._stop = threading.Event()
+        self._ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self._ok = True
+        except Exception:
+            return
+        self.period = period
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0}
+        if not self._ok:
+            return out
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), samples=len(self.sm),
+                       power_w_max=float(np.max(self.power)) if self.power else None)
+        out["reasons"] = [n for n, b in self.REASONS if self.bits & b]
+        return out
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from hmvec_b200 import _capi as capi, pipeline, zshard
+
+    zs, ms, ks, ells = grids(a)
+    inp = pipeline.make_inputs(zs, ms, ks, ells=ells)
+    zc = zshard.ZComm(a.nz, None) if world > 1 else None
+    sl = zc.slab if zc is not None else slice(0, a.nz)
+    g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs)
+    g.upload()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms_):
+        if world == 1:
+            return ms_
+        t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(a.warmup, 3)):
+        g.run()
+    barrier()
+
+    # ---- device-resident timing, stage boundaries marked with events on the launching stream -------------------
+    nst = len(g.STAGES) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(nst)] for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0.record()
+    for s in range(a.steps):
+        g.run(events=evs[s])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler is not None else None
+    stage_ms = np.array([[evs[s][i].elapsed_time(evs[s][i + 1]) for i in range(nst - 1)] for s in range(a.steps)])
+    stage_ms = stage_ms.mean(axis=0)
+
+    # ---- end to end through pinned host buffers -----------------------------------------------------------------
+    for _ in range(2):
+        g.upload(); g.run(); g.download()
+    barrier()
+    e0.record()
+    for s in range(a.steps):
+        g.upload()
+        g.run()
+        g.download()
+        torch.cuda.current_stream().synchronize()     # the step's results are on the host before the next one starts
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pts_per_step = 6.0 * a.nz * a.nk
+    value = pts_per_step * a.steps / (ms_total * 1e-3)
+    e2e = pts_per_step * a.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline per stage (algorithmic bytes per launch of the stage's main kernel; this rank's slab) ------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    nzl, nm, nk = g.nz, g.nm, g.nk
+    alg_bytes = {
+        "uk_nfw": 8.0 * nzl * nm * nk,                                  # store of the cube (K2; FP64-pipe bound)
+        "uk_electron": 8.0 * nzl * nm * nk,                             # store of the cube (K1; FP64-pipe bound)
+        "power_six": nzl * nk * (16.0 * nm + 96.0 + 8.0),               # read 2 cubes once, write 12 spectra, read Pzk
+        "sigma2": 8.0 * (nzl * g.nks + 2.0 * g.nks * nm + nzl * nm),    # sPzk + W2 table write/read + sigma2 out
+    }
+    kernels = {}
+    for name, ms_ in zip(g.STAGES, stage_ms):
+        k = {"ms": float(ms_)}
+        if name in alg_bytes:
+            gbs = alg_bytes[name] / (ms_ * 1e-3) / 1e9
+            k.update(alg_bytes=alg_bytes[name], gbs=gbs, frac_hbm=gbs / hbm_peak)
+        kernels[name] = k
+    dom = max(alg_bytes, key=lambda n: kernels[n]["ms"])
+    fp64_tf = float(capi.lib.hmv_bench_dfma(20000, capi.stream()))
+    roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
+            "frac": kernels[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+            "ms_per_launch": kernels[dom]["ms"], "alg_bytes_per_launch": alg_bytes[dom],
+            "fp64_dfma_peak_tflops_measured": fp64_tf}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": "z-sharded x%d" % world,
+                       "l2": "inputs exceed L2 (two %.1f GB cubes per rank)" % (8e-9 * nzl * nm * g.ldk)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": g.h2d_bytes() * world,
+                    "d2h_bytes_per_step": g.d2h_bytes() * world, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(g.launches_per_run * a.steps), "clocks": clocks, "roofline": roof, "kernels": kernels}
+
+    if world == 1 and not a.no_cpu:
+        v, dt = cpu_sample(a, 1, zper=a.cpu_nz)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+                                "sample": "%d of %d redshifts at full %d M x %d k resolution, whole path except "
+                                          "Limber, single numpy thread" % (a.cpu_nz, a.nz, a.nm, a.nk)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nz", type=int, default=200)
+    ap.add_argument("--nm", type=int, default=2000)
+    ap.add_argument("--nk", type=int, default=10000)
+    ap.add_argument("--nl", type=int, default=1000)
+    ap.add_argument("--cpu-nz", type=int, default=2, help="redshifts in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

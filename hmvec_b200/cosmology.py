@@ -96,12 +96,20 @@ class Cosmology(object):
         self.p = dict(params) if params is not None else {}
         for key, val in default_params.items():
             self.p.setdefault(key, val)
-        self.device = torch.device(device) if device is not None else _default_device()
+        self._device = torch.device(device) if device is not None else None
         self._init_cosmology(self.p, halofit)
 
     # ------------------------------------------------------------------ device plumbing
+    @property
+    def device(self):
+        """CUDA device of this object; resolved on first use so that the host-side producers (background, P_lin,
+        windows) work on a machine without a GPU while every device op still fails loudly there."""
+        if self._device is None:
+            self._device = _default_device()
+        return self._device
+
     def _dev(self, a):
-        return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=self.device)
+        return torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=self.device)
 
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=self.device)
@@ -392,7 +400,7 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
     with np.errstate(all="ignore"):
         pref = hzs * np.array(Wz1s, dtype=np.float64).reshape(-1) * np.array(Wz2s, dtype=np.float64).reshape(-1) / chis ** 2.
     pref = np.broadcast_to(pref, gzs.shape)
-    dev = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+    dev = lambda a: torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=device)
     if isinstance(Pzks, torch.Tensor):
         P_d = Pzks.to(device=device, dtype=torch.float64).contiguous()
     else:
@@ -403,6 +411,6 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
     # keep every temporary alive until the launch has been issued (the caching allocator may otherwise recycle it)
     ells_d, zs_d, ks_d, gzs_d, pref_d, chis_d = dev(ells), dev(zs), dev(ks), dev(gzs), dev(pref), dev(chis)
     capi.check(capi.lib.hmv_limber(ells.size, capi.ptr(ells_d), zs.size, ks.size, ks.size, capi.ptr(zs_d),
-                                   capi.ptr(ks_d), capi.ptr(P_d), gzs.size, capi.ptr(gzs_d), capi.ptr(pref_d),
+                                   capi.ptr(ks_d), capi.ptr(P_d), None, gzs.size, capi.ptr(gzs_d), capi.ptr(pref_d),
                                    capi.ptr(chis_d), capi.ptr(out), capi.stream()), "hmv_limber")
     return out.cpu().numpy()

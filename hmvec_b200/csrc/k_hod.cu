@@ -151,9 +151,9 @@ __global__ void __launch_bounds__(HT) hod_bisect_kernel(int nm, const double* __
   if (threadIdx.x == 0) pass[z] = mask;
 }
 
-__global__ void hod_bisect_pick_kernel(int nz, const double* __restrict__ ys,
-                                       const unsigned long long* __restrict__ pass, double A,
-                                       double* __restrict__ lth_out, int* __restrict__ iters) {
+// AND of the per-z pass masks of this device's redshifts -> mask[0] (bit it = every local z passes at iteration it)
+__global__ void hod_mask_reduce_kernel(int nz, const unsigned long long* __restrict__ pass,
+                                       unsigned long long* __restrict__ mask) {
   __shared__ unsigned long long all;
   if (threadIdx.x == 0) all = ~0ull;
   __syncthreads();
@@ -161,11 +161,18 @@ __global__ void hod_bisect_pick_kernel(int nz, const double* __restrict__ ys,
   for (int z = threadIdx.x; z < nz; z += blockDim.x) mine &= pass[z];
   atomicAnd(&all, mine);
   __syncthreads();
-  const unsigned long long a = all;
-  const int T = a ? (__ffsll((long long)a) - 1) : -1;       // first iteration at which every z passes
-  if (threadIdx.x == 0) *iters = T + 1;
+  if (threadIdx.x == 0) mask[0] = all;
+}
+
+// mask[0] is the AND over ALL redshifts (all ranks when z is sharded): pick the first iteration every z passes
+__global__ void hod_bisect_pick_kernel(int nz, const double* __restrict__ ys,
+                                       const unsigned long long* __restrict__ mask, double A,
+                                       double* __restrict__ lth_out, int* __restrict__ iters) {
+  const unsigned long long a = mask[0];
+  const int T = a ? (__ffsll((long long)a) - 1) : -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *iters = T + 1;
   const int use = T >= 0 ? T : HMV_BISECT_MAXIT - 1;
-  for (int z = threadIdx.x; z < nz; z += blockDim.x)
+  for (int z = blockIdx.x * blockDim.x + threadIdx.x; z < nz; z += gridDim.x * blockDim.x)
     lth_out[z] = ys[(long long)z * HMV_BISECT_MAXIT + use] * A;  // hmvec.py:433
 }
 
@@ -203,12 +210,11 @@ extern "C" int hmv_hod(int nz, int nm, const double* zs_d, const double* ms_d, c
   return check_launch("hod_kernel");
 }
 
-extern "C" int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
-                             const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
-                             double A_log10mthresh, double* ws_d, double* log10mthresh_d, int* iters_d, void* stream) {
-  HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_hod_solve: need nz>0, nm>=2");
-  HMV_REQUIRE(zs_d && ms_d && nzm_d && ngal_target_d && hodp_h && ws_d && log10mthresh_d && iters_d,
-              "hmv_hod_solve: null pointer");
+extern "C" int hmv_hod_bisect(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
+                              const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
+                              double* ws_d, unsigned long long* mask_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_hod_bisect: need nz>0, nm>=2");
+  HMV_REQUIRE(zs_d && ms_d && nzm_d && ngal_target_d && hodp_h && ws_d && mask_d, "hmv_hod_bisect: null pointer");
   size_t smem;
   int rc = hod_smem(nm, &smem);
   if (rc) return rc;
@@ -221,6 +227,25 @@ extern "C" int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* m
                                           pass);
   rc = check_launch("hod_bisect_kernel");
   if (rc) return rc;
-  hod_bisect_pick_kernel<<<1, 256, 0, st>>>(nz, ys, pass, A_log10mthresh, log10mthresh_d, iters_d);
+  hod_mask_reduce_kernel<<<1, 256, 0, st>>>(nz, pass, mask_d);
+  return check_launch("hod_mask_reduce_kernel");
+}
+
+extern "C" int hmv_hod_pick(int nz, const double* ws_d, const unsigned long long* mask_d, double A_log10mthresh,
+                            double* log10mthresh_d, int* iters_d, void* stream) {
+  HMV_REQUIRE(nz > 0, "hmv_hod_pick: need nz>0");
+  HMV_REQUIRE(ws_d && mask_d && log10mthresh_d && iters_d, "hmv_hod_pick: null pointer");
+  hod_bisect_pick_kernel<<<cdiv(nz, 256), 256, 0, (cudaStream_t)stream>>>(nz, ws_d, mask_d, A_log10mthresh,
+                                                                         log10mthresh_d, iters_d);
   return check_launch("hod_bisect_pick_kernel");
+}
+
+extern "C" int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
+                             const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
+                             double A_log10mthresh, double* ws_d, double* log10mthresh_d, int* iters_d, void* stream) {
+  HMV_REQUIRE(ws_d != nullptr, "hmv_hod_solve: null workspace");
+  unsigned long long* mask = (unsigned long long*)(ws_d + (size_t)nz * (HMV_BISECT_MAXIT + 1));
+  int rc = hmv_hod_bisect(nz, nm, zs_d, ms_d, nzm_d, ngal_target_d, hodp_h, ylo, yhi, rtol, ws_d, mask, stream);
+  if (rc) return rc;
+  return hmv_hod_pick(nz, ws_d, mask, A_log10mthresh, log10mthresh_d, iters_d, stream);
 }

@@ -18,7 +18,8 @@ __device__ __forceinline__ int interval(const double* __restrict__ x, int n, dou
 
 __global__ void limber_kernel(int nl, const double* __restrict__ ells, int nzp, int nk, int ldp,
                               const double* __restrict__ zs, const double* __restrict__ ks,
-                              const double* __restrict__ P, int ngz, const double* __restrict__ gzs,
+                              const double* __restrict__ P, const double* __restrict__ P2, int ngz,
+                              const double* __restrict__ gzs,
                               const double* __restrict__ pref, const double* __restrict__ chis,
                               double* __restrict__ cl) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -35,13 +36,16 @@ __global__ void limber_kernel(int nl, const double* __restrict__ ells, int nzp, 
       const double zq = fmin(fmax(gzs[g], zs[0]), zs[nzp - 1]);
       const int iz = interval(zs, nzp, zq);
       const double tz = (zq - zs[iz]) / (zs[iz + 1] - zs[iz]);
-      const double* r0 = P + (long long)iz * ldp;
-      const double* r1 = r0 + ldp;
-      const double v0 = fma(tk, r0[ik + 1] - r0[ik], r0[ik]);
-      const double v1 = fma(tk, r1[ik + 1] - r1[ik], r1[ik]);
+      const long long o0 = (long long)iz * ldp + ik, o1 = o0 + ldp;
+      double a0 = P[o0], a1 = P[o0 + 1], b0 = P[o1], b1 = P[o1 + 1];
+      if (P2) { a0 += P2[o0]; a1 += P2[o0 + 1]; b0 += P2[o1]; b1 += P2[o1 + 1]; }   // P = P1h + P2h
+      const double v0 = fma(tk, a1 - a0, a0);
+      const double v1 = fma(tk, b1 - b0, b0);
       val = fma(tz, v1 - v0, v0);
     } else {
-      val = fma(tk, P[ik + 1] - P[ik], P[ik]);
+      double a0 = P[ik], a1 = P[ik + 1];
+      if (P2) { a0 += P2[ik]; a1 += P2[ik + 1]; }
+      val = fma(tk, a1 - a0, a0);
     }
     const double w = (ngz > 1) ? trapz_weight(gzs, g, ngz) : 1.0;   // cosmology.py:902-903
     acc = fma(w, val * pref[g], acc);
@@ -72,13 +76,13 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ s
 using namespace hmv;
 
 extern "C" int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const double* zs_d,
-                          const double* ks_d, const double* P_d, int ngz, const double* gzs_d, const double* pref_d,
-                          const double* chis_d, double* cl_d, void* stream) {
+                          const double* ks_d, const double* P_d, const double* P2_d, int ngz, const double* gzs_d,
+                          const double* pref_d, const double* chis_d, double* cl_d, void* stream) {
   HMV_REQUIRE(nl > 0 && nzp > 0 && nk >= 2 && ldp >= nk && ngz > 0, "hmv_limber: bad sizes");
   HMV_REQUIRE(ells_d && zs_d && ks_d && P_d && gzs_d && pref_d && chis_d && cl_d, "hmv_limber: null pointer");
   const int wpb = 4;  // warps per block
-  limber_kernel<<<cdiv(nl, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, P_d, ngz,
-                                                                      gzs_d, pref_d, chis_d, cl_d);
+  limber_kernel<<<cdiv(nl, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, P_d, P2_d,
+                                                                      ngz, gzs_d, pref_d, chis_d, cl_d);
   return check_launch("limber_kernel");
 }
 

@@ -1,0 +1,527 @@
+"""HaloModel: drop-in for `hmvec.hmvec.HaloModel` (reference hmvec/hmvec.py:75-572) on one B200.
+
+Same constructor and method signatures, same attributes (`zs, ks, ms, p, params, h, omm0, Pzk, sigma2, nzm, bh,
+uk_profiles, pk_profiles, hods`), same numpy float64 return types -- but nothing on the path is computed by numpy.
+The host side prepares O(nz)+O(nk) inputs (background scalars, linear P(k), Simpson weights), uploads them once and
+every [nz,nm] / [nz,nm,nk] quantity is produced by the sm_100a kernels behind the C ABI (include/hmvec_b200.h):
+
+    init_mass_function   -> hmv_sigma2, hmv_mass_function, hmv_halo_geometry
+    add_nfw_profile      -> hmv_uk_nfw                      (numeric=True -> hmv_profile_transform)
+    add_battaglia_*      -> hmv_mdelta, hmv_gnfw_params, hmv_profile_transform
+    add_hod              -> hmv_hod_bisect/hmv_hod_pick (ngal given), hmv_hod
+    get_power_1halo/2halo/get_power/get_power_six -> hmv_power / hmv_power_six
+
+Data layout in HBM: cubes are [nz][nm][ldk] float64, k fastest, ldk = nk rounded up to 16 doubles.  The cubes stay
+resident on the device; `uk_profiles[name]` / `pk_profiles[name]` download a numpy copy on access (at the LARGE grid
+one cube is 32 GB, which is why they are not mirrored eagerly).  There is no CPU fallback.
+"""
+from collections.abc import MutableMapping
+import ctypes as C
+
+import numpy as np
+import torch
+from scipy import constants
+
+from . import _capi as capi
+from . import utils  # noqa: F401  (reference exports `utils` through `from .hmvec import *`)
+from .cosmology import Cosmology, limber_integral, Wkr, a2z, _trapz  # noqa: F401
+from .params import default_params, battaglia_defaults
+
+_KIND_MATTER, _KIND_HOD, _KIND_PRESSURE = 0, 1, 2
+
+
+def duffy_concentration(m, z, A=None, alpha=None, beta=None, h=None):
+    """Host helper with the reference's defaults (hmvec.py:68-73); the device path is hmv_halo_geometry."""
+    A = default_params['duffy_A_mean'] if A is None else A
+    alpha = default_params['duffy_alpha_mean'] if alpha is None else alpha
+    beta = default_params['duffy_beta_mean'] if beta is None else beta
+    h = default_params['H0'] / 100. if h is None else h
+    return A * ((h * m / 2.e12) ** alpha) * (1 + z) ** beta
+
+
+def R_from_M(M, rho, delta):
+    """hmvec.py:627-628"""
+    return (3. * M / 4. / np.pi / delta / rho) ** (1. / 3.)
+
+
+class DeviceCubes(MutableMapping):
+    """name -> u(z,M,k) cube resident in HBM ([nz][nm][ldk] float64).  Reading an item returns a numpy
+    [nz,nm,nk] copy (what reference callers index); assigning a numpy/torch [nz,nm,nk] array uploads it."""
+
+    def __init__(self, owner):
+        self._owner = owner
+        self._t = {}
+
+    def device(self, name):
+        return self._t[name]
+
+    def __getitem__(self, name):
+        t = self._t[name]
+        return t[..., :self._owner._nk].cpu().numpy()
+
+    def __setitem__(self, name, value):
+        o = self._owner
+        if isinstance(value, torch.Tensor) and value.is_cuda and value.dim() == 3 and value.shape[-1] == o._ldk:
+            self._t[name] = value
+            return
+        arr = torch.as_tensor(np.asarray(value, dtype=np.float64))
+        if tuple(arr.shape) != (o._nz, o._nm, o._nk):
+            raise ValueError("profile cube must have shape (nz,nm,nk)=%s" % ((o._nz, o._nm, o._nk),))
+        t = o._cube()
+        t[..., :o._nk] = arr.to(o.device)
+        self._t[name] = t
+
+    def __delitem__(self, name):
+        del self._t[name]
+
+    def __iter__(self):
+        return iter(self._t)
+
+    def __len__(self):
+        return len(self._t)
+
+
+class HaloModel(Cosmology):
+    def __init__(self, zs, ks, ms=None, params={}, mass_function="sheth-torman", halofit=None, mdef='vir',
+                 nfw_numeric=False, skip_nfw=False, accuracy='medium', engine='camb', device=None, Pzk=None,
+                 sPzk=None, zcomm=None):
+        """Reference signature (hmvec.py:76-77) plus keyword-only extensions:
+        device -- CUDA device (default: current); Pzk [nz,nk], sPzk [nz,sigma2_numks] -- host-supplied linear power
+        on `ks` and on the sigma^2 grid (the CAMB products; skips the internal producer); zcomm -- a
+        `zshard.ZComm` when `zs` is this rank's slab of a redshift axis sharded over several GPUs."""
+        self.zs = np.asarray(zs, dtype=np.float64).reshape(-1)
+        self.ks = ks
+        self._ks64 = np.asarray(ks, dtype=np.float64).reshape(-1)
+        self._Pzk_in, self._sPzk_in = Pzk, sPzk
+        self._zcomm = zcomm
+        Cosmology.__init__(self, params, halofit, accuracy=accuracy, engine=engine, device=device)
+        if mdef not in ('vir', 'mean'):
+            raise ValueError("mdef must be 'vir' or 'mean'")
+        self.mdef = mdef
+        self.mode = mass_function
+        self.hods = {}
+        self._hod_d = {}
+        self._nz, self._nk = self.zs.size, self._ks64.size
+        self._ldk = ((self._nk + 15) // 16) * 16
+        self._zs_d = self._dev(self.zs)
+        self._ks_d = self._dev(self._ks64)
+        self._Pzk_d = self._dev(self.Pzk)
+        self._rho_m0 = float(np.atleast_1d(self.rho_matter_z(0.))[0])
+        self.uk_profiles = DeviceCubes(self)
+        self.pk_profiles = DeviceCubes(self)
+        if ms is not None:
+            self.ms = np.asarray(ms, dtype=np.float64).reshape(-1)
+            self.init_mass_function(self.ms)
+        if not skip_nfw:
+            self.add_nfw_profile("nfw", numeric=nfw_numeric)
+
+    # ------------------------------------------------------------------ host-side inputs
+    def _init_cosmology(self, params, halofit):
+        Cosmology._init_cosmology(self, params, halofit)
+        if self._Pzk_in is not None:
+            self.Pzk = np.array(self._Pzk_in, dtype=np.float64)
+            if self.Pzk.shape != (self.zs.size, self._ks64.size):
+                raise ValueError("Pzk must have shape (nz,nk)")
+        elif self.accuracy == 'low':
+            self.Pzk = self.P_lin_approx(self._ks64, self.zs)               # hmvec.py:98-99
+        else:
+            self.Pzk = self._get_matter_power(self.zs, self._ks64, nonlinear=False)
+        if halofit is not None and self._Pzk_in is None:
+            self.nPzk = self._get_matter_power(self.zs, self._ks64, nonlinear=True)
+
+    def _sigma2_inputs(self, zs, kmin=None, kmax=None, numks=None):
+        if self._sPzk_in is None:
+            return Cosmology._sigma2_inputs(self, zs, kmin, kmax, numks)
+        from .cosmology import simpson_weights
+        ks_sigma2 = np.geomspace(self.p['sigma2_kmin'] if kmin is None else kmin,
+                                 self.p['sigma2_kmax'] if kmax is None else kmax,
+                                 int(self.p['sigma2_numks'] if numks is None else numks))
+        self.sPzk = np.array(self._sPzk_in, dtype=np.float64)
+        if self.sPzk.shape != (np.size(zs), ks_sigma2.size):
+            raise ValueError("sPzk must have shape (nz, sigma2_numks)")
+        return ks_sigma2, simpson_weights(ks_sigma2) * ks_sigma2 ** 2. / 2. / np.pi ** 2.
+
+    def deltav(self, z):
+        """Bryan & Norman virial overdensity (hmvec.py:105-109)."""
+        x = self.omz(z) - 1.
+        return 18. * np.pi ** 2. + 82. * x - 39. * x ** 2.
+
+    def rvir(self, m, z):
+        if self.mdef == 'vir':
+            return R_from_M(m, self.rho_critical_z(z), delta=self.deltav(z))
+        return R_from_M(m, self.rho_matter_z(z), delta=200.)
+
+    def R_of_m(self, ms):
+        return R_from_M(ms, self.rho_matter_z(0), delta=1.)
+
+    def _delta_rhos1(self):
+        rhocritz = self.rho_critical_z(self.zs)
+        if self.mdef == 'vir':
+            return rhocritz * self.deltav(self.zs)
+        return self.rho_matter_z(self.zs) * 200.
+
+    # ------------------------------------------------------------------ device plumbing
+    def _cube(self):
+        return torch.zeros((self._nz, self._nm, self._ldk), dtype=torch.float64, device=self.device)
+
+    def _duffy(self):
+        tag = 'mean' if self.mdef == 'mean' else 'vir'
+        return self.p['duffy_A_' + tag], self.p['duffy_alpha_' + tag], self.p['duffy_beta_' + tag]
+
+    # ------------------------------------------------------------------ mass function (K3, K3b, geometry)
+    def get_sigma2(self):
+        return self._sigma2_d.cpu().numpy()
+
+    def init_mass_function(self, ms):
+        """sigma^2 -> n(M,z), b(M,z) and the per-halo geometry, all on the device (hmvec.py:127-185)."""
+        if self.mode != "sheth-torman":
+            raise NotImplementedError("mass_function=%r: only 'sheth-torman' is on the device path" % (self.mode,))
+        self.ms = np.asarray(ms, dtype=np.float64).reshape(-1)
+        self._nm = self.ms.size
+        self._ms_d = self._dev(self.ms)
+        ks_sig, kw = self._sigma2_inputs(self.zs)
+        R = np.asarray(self.R_of_m(self.ms), dtype=np.float64).reshape(-1)
+        self._sigma2_d = self._sigma2_device(self._dev(R), self._dev(self.sPzk), self._dev(ks_sig), self._dev(kw))
+        self._nzm_d, self._bh_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
+        p = self.p
+        capi.check(capi.lib.hmv_mass_function(self._nz, self._nm, capi.ptr(self._sigma2_d), capi.ptr(self._ms_d),
+                                              self._rho_m0, p['st_A'], p['st_a'], p['st_p'], p['st_deltac'],
+                                              capi.ptr(self._nzm_d), capi.ptr(self._bh_d), capi.stream()),
+                   "hmv_mass_function")
+        A, alpha, beta = self._duffy()
+        self._drho1_d = self._dev(self._delta_rhos1())
+        self._cs_d, self._rvir_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
+        capi.check(capi.lib.hmv_halo_geometry(self._nz, self._nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d),
+                                              capi.ptr(self._drho1_d), A, alpha, beta, self.h, capi.ptr(self._cs_d),
+                                              capi.ptr(self._rvir_d), capi.stream()), "hmv_halo_geometry")
+        self.sigma2 = self._sigma2_d.cpu().numpy()
+        self.nzm = self._nzm_d.cpu().numpy()
+        self.bh = self._bh_d.cpu().numpy()
+
+    def get_nzm(self):
+        return self._nzm_d.cpu().numpy()
+
+    def get_bh(self):
+        return self._bh_d.cpu().numpy()
+
+    def concentration(self, mode='duffy'):
+        if mode != 'duffy':
+            raise NotImplementedError
+        return self._cs_d.cpu().numpy()
+
+    # ------------------------------------------------------------------ profiles (K0, K1, K2)
+    def _m200c_device(self):
+        rhoc = np.asarray(self.rho_critical_z(self.zs), dtype=np.float64)
+        drho2_d = self._dev(200. * rhoc)
+        m200_d = self._empty(self._nz, self._nm)
+        capi.check(capi.lib.hmv_mdelta(self._nz, self._nm, capi.ptr(self._ms_d), capi.ptr(self._cs_d),
+                                       capi.ptr(self._drho1_d), capi.ptr(drho2_d), capi.ptr(m200_d), capi.stream()),
+                   "hmv_mdelta")
+        return m200_d, self._dev(rhoc)
+
+    def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm):
+        out = self._cube()
+        capi.check(capi.lib.hmv_profile_transform(
+            self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d), capi.ptr(self._ks_d),
+            float(np.max(self._ks64)), capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
+            capi.ptr(expo_d), capi.ptr(amp_d), capi.ptr(oscale_d), float(gamma), float(xmax), int(nxs),
+            int(bool(mass_norm)), capi.ptr(out), capi.stream()), "hmv_profile_transform")
+        return out
+
+    def _gnfw(self, kind, fit9, gamma, pres_alpha, amp_const, pref, xmax, nxs):
+        m200_d, rhoc_d = self._m200c_device()
+        hofz_d = self._dev(self.h_of_z(self.zs))
+        outs = [self._empty(self._nz, self._nm) for _ in range(7)]
+        capi.check(capi.lib.hmv_gnfw_params(kind, self._nz, self._nm, capi.ptr(self._zs_d), capi.ptr(m200_d),
+                                            capi.ptr(self._rvir_d), capi.ptr(rhoc_d), capi.ptr(hofz_d),
+                                            capi.darr(fit9), float(gamma), float(pres_alpha), float(amp_const),
+                                            float(pref), *[capi.ptr(o) for o in outs], capi.stream()),
+                   "hmv_gnfw_params")
+        rs, cmax, xc, alpha, expo, amp, oscale = outs
+        return self._transform(rs, cmax, xc, alpha, expo, amp, oscale, gamma, xmax, nxs, mass_norm=(kind == 0))
+
+    def add_battaglia_profile(self, name, family=None, param_override=None, nxs=None, xmax=None,
+                              ignore_existing=False):
+        """Battaglia-2016 GNFW electron density u(k|M,z) (hmvec.py:188-250 + fft.py:56-115), one fused kernel."""
+        if not ignore_existing:
+            assert name not in self.uk_profiles.keys(), "Profile name already exists."
+        assert name != 'nfw', "Name nfw is reserved."
+        if nxs is None:
+            nxs = self.p['electron_density_profile_integral_numxs']
+        if xmax is None:
+            xmax = self.p['electron_density_profile_integral_xmax']
+        if family is None:
+            family = self.p['battaglia_gas_family']
+        pparams = {'battaglia_gas_gamma': self.p['battaglia_gas_gamma']}
+        pparams.update(battaglia_defaults[family])
+        if param_override is not None:
+            print(param_override)                                           # hmvec.py:205
+            for key in param_override.keys():                               # unknown keys are ignored (:204-213)
+                if key == 'battaglia_gas_gamma' or key in battaglia_defaults[family]:
+                    pparams[key] = param_override[key]
+        fit9 = [pparams[q + s] for q in ('rho0', 'alpha', 'beta') for s in ('_A0', '_alpham', '_alphaz')]
+        self.uk_profiles[name] = self._gnfw(0, fit9, pparams['battaglia_gas_gamma'], 1.0, 1.0, 1.0, xmax, nxs)
+
+    def add_battaglia_pres_profile(self, name, family=None, param_override=None, nxs=None, xmax=None,
+                                   ignore_existing=False):
+        """Battaglia-2012 GNFW electron pressure -> Compton-y profile (hmvec.py:252-316, 906-927)."""
+        if not ignore_existing:
+            assert name not in self.pk_profiles.keys(), "Profile name already exists."
+        assert name != 'nfw', "Name nfw is reserved."
+        if nxs is None:
+            nxs = self.p['electron_pressure_profile_integral_numxs']
+        if xmax is None:
+            xmax = self.p['electron_pressure_profile_integral_xmax']
+        if family is None:
+            family = self.p['battaglia_pres_family']
+        pparams = {'battaglia_pres_gamma': self.p['battaglia_pres_gamma'],
+                   'battaglia_pres_alpha': self.p['battaglia_pres_alpha']}
+        pparams.update(battaglia_defaults[family])
+        if param_override is not None:
+            for key in param_override.keys():
+                if key in ('battaglia_pres_gamma', 'battaglia_pres_alpha') or key in battaglia_defaults[family]:
+                    pparams[key] = param_override[key]
+        fit9 = [pparams[q + s] for q in ('P0', 'xc', 'beta') for s in ('_A0', '_alpham', '_alphaz')]
+        XH = .76
+        eFrac = 2.0 * (XH + 1.0) / (5.0 * XH + 3.0)                         # hmvec.py:918-920
+        omb = self.p['ombh2'] / self.h ** 2.
+        G_newt = constants.G / (default_params['parsec'] * 1e6) ** 3 * default_params['mSun']
+        amp_const = eFrac * (omb / self.omm0) * 200 * G_newt                # x m200c rho_c /(2 r200c) P0 on device
+        sigmaT = constants.physical_constants['Thomson cross section'][0]
+        mElect = constants.physical_constants['electron mass'][0] / default_params['mSun']
+        pref = 4 * np.pi * (sigmaT / (mElect * constants.c ** 2))           # x r200c^3 (1+z)^2/H on device (:316)
+        self.pk_profiles[name] = self._gnfw(1, fit9, pparams['battaglia_pres_gamma'],
+                                            pparams['battaglia_pres_alpha'], amp_const, pref, xmax, nxs)
+
+    def add_nfw_profile(self, name, numeric=False, nxs=None, xmax=None, ignore_existing=False):
+        """Truncated-NFW u(k|M,z): analytic Si/Ci kernel, or the numerical transform (hmvec.py:318-355)."""
+        if not ignore_existing:
+            assert name not in self.uk_profiles.keys(), "Profile name already exists."
+        if nxs is None:
+            nxs = self.p['nfw_integral_numxs']
+        if xmax is None:
+            xmax = self.p['nfw_integral_xmax']
+        if numeric:
+            # rho_nfw_x = 1/x/(1+x)^2 is the GNFW form with gamma=-1, alpha=1, exponent 2; cmax = c, rs = rvir/c
+            one = torch.ones((self._nz, self._nm), dtype=torch.float64, device=self.device)
+            rs_d = self._rvir_d / self._cs_d
+            out = self._transform(rs_d, self._cs_d, one, one, 2.0 * one, one, one, -1.0, xmax, nxs, mass_norm=True)
+        else:
+            out = self._cube()
+            capi.check(capi.lib.hmv_uk_nfw(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d),
+                                           capi.ptr(self._ks_d), capi.ptr(self._cs_d), capi.ptr(self._rvir_d),
+                                           capi.ptr(out), capi.stream()), "hmv_uk_nfw")
+        self.uk_profiles[name] = out
+        return self.ks, LazyCube(self.uk_profiles, name)
+
+    # ------------------------------------------------------------------ HOD (K4, K4b)
+    def add_hod(self, name, mthresh=None, ngal=None, corr="max", satellite_profile_name='nfw',
+                central_profile_name=None, ignore_existing=False, param_override=None):
+        """Leauthaud-SHMR HOD from a stellar-mass threshold or a number density (hmvec.py:357-460)."""
+        if not ignore_existing:
+            assert name not in self.uk_profiles.keys(), "HOD name already used by profile."
+        assert satellite_profile_name in self.uk_profiles.keys(), "No matter profile by that name exists."
+        if central_profile_name is not None:
+            assert central_profile_name in self.uk_profiles.keys(), "No matter profile by that name exists."
+        if not ignore_existing:
+            assert name not in self.hods.keys(), "HOD with that name already exists."
+        if corr not in ("max", "min"):
+            raise ValueError("corr must be 'max' or 'min'")
+        hod_params = ['hod_sig_log_mstellar', 'hod_bisection_search_min_log10mthresh',
+                      'hod_bisection_search_max_log10mthresh', 'hod_bisection_search_rtol',
+                      'hod_bisection_search_warn_iter', 'hod_alphasat', 'hod_Bsat', 'hod_betasat', 'hod_Bcut',
+                      'hod_betacut', 'hod_A_log10mthresh']
+        pp = {k: self.p[k] for k in hod_params}
+        if param_override is not None:
+            for key in param_override.keys():
+                if key in hod_params:
+                    pp[key] = param_override[key]
+                else:
+                    raise ValueError("%r is not an HOD parameter" % (key,))
+        hodp = capi.darr([pp['hod_sig_log_mstellar'], pp['hod_alphasat'], pp['hod_Bsat'], pp['hod_betasat'],
+                          pp['hod_Bcut'], pp['hod_betacut'], 0.0, 0.0])
+        nz, nm = self._nz, self._nm
+        iters = 0
+        if ngal is not None:
+            ngal = np.asarray(ngal, dtype=np.float64)
+            if ngal.size != nz:
+                raise ValueError("ngal has to be a vector of size self.zs")
+            assert mthresh is None
+            l10_d, iters = self._solve_mthresh(self._dev(ngal.reshape(-1)), hodp, pp)
+            print("Bisection search converged in ", iters, " iterations.")   # utils.py:41
+        else:
+            mthresh = np.asarray(mthresh, dtype=np.float64)
+            if mthresh.size != nz:
+                raise ValueError("mthresh has to be a vector of size self.zs")
+            l10_d = self._dev(np.log10(mthresh.reshape(-1)))
+        d = {k: self._empty(nz, nm) for k in ('Nc', 'Ns', 'NsNsm1', 'NcNs')}
+        d['ngal'], d['bg'] = self._empty(nz), self._empty(nz)
+        capi.check(capi.lib.hmv_hod(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d), capi.ptr(l10_d), hodp,
+                                    0 if corr == "max" else 1, capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
+                                    capi.ptr(d['Nc']), capi.ptr(d['Ns']), capi.ptr(d['NsNsm1']), capi.ptr(d['NcNs']),
+                                    capi.ptr(d['ngal']), capi.ptr(d['bg']), capi.stream()), "hmv_hod")
+        self._hod_d[name] = d
+        h = {k: v.cpu().numpy() for k, v in d.items()}
+        h['satellite_profile'] = satellite_profile_name
+        h['central_profile'] = central_profile_name
+        h['log10mthresh'] = l10_d.cpu().numpy()[:, None]
+        h['iterations'] = iters
+        self.hods[name] = h
+
+    def _solve_mthresh(self, target_d, hodp, pp):
+        """All-z bisection (utils.py:9-42): every redshift bisects on the device and records, per iteration,
+        its midpoint and a pass bit; the answer is the midpoint of the first iteration at which EVERY redshift
+        passes -- across all ranks when the z axis is sharded (one 8-byte all-reduce)."""
+        nz, nm = self._nz, self._nm
+        ws = self._empty(nz * (capi.HMV_BISECT_MAXIT + 2))
+        mask_d = torch.empty(1, dtype=torch.int64, device=self.device)
+        capi.check(capi.lib.hmv_hod_bisect(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d), capi.ptr(self._nzm_d),
+                                           capi.ptr(target_d), hodp,
+                                           float(pp['hod_bisection_search_min_log10mthresh']),
+                                           float(pp['hod_bisection_search_max_log10mthresh']),
+                                           float(pp['hod_bisection_search_rtol']), capi.ptr(ws),
+                                           C.c_void_p(mask_d.data_ptr()), capi.stream()), "hmv_hod_bisect")
+        if self._zcomm is not None:
+            self._zcomm.all_reduce_and(mask_d)
+        l10_d = self._empty(nz)
+        iters_d = torch.zeros(1, dtype=torch.int32, device=self.device)
+        capi.check(capi.lib.hmv_hod_pick(nz, capi.ptr(ws), C.c_void_p(mask_d.data_ptr()),
+                                         float(pp['hod_A_log10mthresh']), capi.ptr(l10_d), capi.ptr(iters_d),
+                                         capi.stream()), "hmv_hod_pick")
+        iters = int(iters_d.item())
+        if iters == 0:
+            raise capi.HmvError("mthresh<->ngal bisection did not converge within %d iterations"
+                                % capi.HMV_BISECT_MAXIT)
+        return l10_d, iters
+
+    def get_ngal(self, Nc, Ns):
+        return _trapz(self.nzm * (Nc + Ns), self.ms, axis=-1)
+
+    def get_bg(self, Nc, Ns, ngal):
+        return _trapz(self.nzm * (Nc + Ns) * self.bh, self.ms, axis=-1) / ngal
+
+    # ------------------------------------------------------------------ spectra (K5)
+    def _kind(self, name, order):
+        for k in order:
+            if k == 'h' and name in self.hods:
+                return _KIND_HOD
+            if k == 'm' and name in self.uk_profiles:
+                return _KIND_MATTER
+            if k == 'p' and name in self.pk_profiles:
+                return _KIND_PRESSURE
+        raise ValueError("no profile or HOD named %r" % (name,))
+
+    def _tracer(self, name, kind, bias_d=None):
+        t = capi.Tracer()
+        t.kind = kind
+        keep = []
+        if kind == _KIND_HOD:
+            hod, d = self.hods[name], self._hod_d[name]
+            t.us_d = self.uk_profiles.device(hod['satellite_profile']).data_ptr()
+            cen = hod['central_profile']
+            t.uc_d = self.uk_profiles.device(cen).data_ptr() if cen is not None else None
+            t.Nc_d, t.Ns_d = d['Nc'].data_ptr(), d['Ns'].data_ptr()
+            t.NcNs_d, t.NsNsm1_d = d['NcNs'].data_ptr(), d['NsNsm1'].data_ptr()
+            t.ngal_d = d['ngal'].data_ptr()
+        elif kind == _KIND_MATTER:
+            t.us_d = self.uk_profiles.device(name).data_ptr()
+        else:
+            t.us_d = self.pk_profiles.device(name).data_ptr()
+        if bias_d is not None:
+            t.bias_d = bias_d.data_ptr()
+            keep.append(bias_d)
+        return t, keep
+
+    def _power(self, name, name2, want1, want2, b1_in=None, b2_in=None, kinds=None, to_host=True):
+        name2 = name if name2 is None else name2
+        kA, kB = kinds
+        bA = self._dev(np.asarray(b1_in, dtype=np.float64).reshape(-1)) if b1_in is not None else None
+        bB = self._dev(np.asarray(b2_in, dtype=np.float64).reshape(-1)) if b2_in is not None else None
+        for b in (bA, bB):
+            if b is not None and b.numel() != self._nz:
+                raise ValueError("b1_in/b2_in must have one value per redshift")
+        A, keepA = self._tracer(name, kA, bA)
+        B, keepB = self._tracer(name2, kB, bB)
+        ws = self._empty(int(capi.lib.hmv_power_ws_doubles(self._nz, self._nm)))
+        p1 = self._empty(self._nz, self._nk) if want1 else None
+        p2 = self._empty(self._nz, self._nk) if want2 else None
+        capi.check(capi.lib.hmv_power(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._ms_d),
+                                      capi.ptr(self._ks_d), capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
+                                      capi.ptr(self._Pzk_d), self._rho_m0, float(self.p['kstar_damping']),
+                                      C.byref(A), C.byref(B), capi.ptr(ws), capi.ptr(p1), capi.ptr(p2),
+                                      capi.stream()), "hmv_power")
+        if not to_host:
+            return p1, p2
+        return (p1.cpu().numpy() if want1 else None), (p2.cpu().numpy() if want2 else None)
+
+    # 1-halo looks names up as HOD first (hmvec.py:510-523); 2-halo as matter profile first (hmvec.py:536-550)
+    def _kinds_1h(self, name, name2):
+        return self._kind(name, 'hmp'), self._kind(name2, 'hmp')
+
+    def _kinds_2h(self, name, name2):
+        return self._kind(name, 'mph'), self._kind(name2, 'mph')
+
+    def get_power_1halo(self, name="nfw", name2=None):
+        name2 = name if name2 is None else name2
+        return self._power(name, name2, True, False, kinds=self._kinds_1h(name, name2))[0]
+
+    def get_power_2halo(self, name="nfw", name2=None, verbose=False, b1_in=None, b2_in=None):
+        name2 = name if name2 is None else name2
+        kinds = self._kinds_2h(name, name2)
+        if _KIND_PRESSURE in kinds:
+            print('Check the consistency relation for tSZ')                 # hmvec.py:544
+        return self._power(name, name2, False, True, b1_in, b2_in, kinds=kinds)[1]
+
+    def get_power(self, name, name2=None, verbose=False, b1=None, b2=None):
+        """P1h + P2h (hmvec.py:500-502); one pass over the cubes produces both terms."""
+        name2 = name if name2 is None else name2
+        k1, k2 = self._kinds_1h(name, name2), self._kinds_2h(name, name2)
+        if k1 == k2:
+            p1, p2 = self._power(name, name2, True, True, b1, b2, kinds=k1)
+            return p1 + p2
+        return self.get_power_1halo(name, name2) + self.get_power_2halo(name, name2, verbose, b1, b2)
+
+    def get_power_six(self, matter="nfw", electron="electron", hod="g", to_host=True):
+        """{mm, ee, me, gg, gm, ge} 1h and 2h spectra in ONE pass over the two cubes (hmv_power_six).
+
+        Requires the HOD's satellite profile to be `matter` and its central profile to be None.  Returns
+        (P1h, P2h), each a dict tag -> [nz,nk] (numpy, or CUDA tensors when to_host=False)."""
+        h = self.hods[hod]
+        if h['satellite_profile'] != matter or h['central_profile'] is not None:
+            raise ValueError("get_power_six needs satellite_profile == matter profile and no central profile")
+        d = self._hod_d[hod]
+        ws = self._empty(int(capi.lib.hmv_power_ws_doubles(self._nz, self._nm)))
+        p1, p2 = self._empty(6, self._nz, self._nk), self._empty(6, self._nz, self._nk)
+        capi.check(capi.lib.hmv_power_six(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._ms_d),
+                                          capi.ptr(self._ks_d), capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
+                                          capi.ptr(self._Pzk_d), self._rho_m0, float(self.p['kstar_damping']),
+                                          capi.ptr(self.uk_profiles.device(matter)),
+                                          capi.ptr(self.uk_profiles.device(electron)), capi.ptr(d['Nc']),
+                                          capi.ptr(d['Ns']), capi.ptr(d['NcNs']), capi.ptr(d['NsNsm1']),
+                                          capi.ptr(d['ngal']), capi.ptr(ws), capi.ptr(p1), capi.ptr(p2),
+                                          capi.stream()), "hmv_power_six")
+        tags = ("mm", "ee", "me", "gg", "gm", "ge")
+        if not to_host:
+            return {t: p1[i] for i, t in enumerate(tags)}, {t: p2[i] for i, t in enumerate(tags)}
+        h1, h2 = p1.cpu().numpy(), p2.cpu().numpy()
+        return {t: h1[i] for i, t in enumerate(tags)}, {t: h2[i] for i, t in enumerate(tags)}
+
+
+class LazyCube(object):
+    """Second return value of add_nfw_profile: behaves as the [nz,nm,nk] numpy array when converted or indexed,
+    without forcing a 32 GB device->host copy when the caller ignores it."""
+
+    def __init__(self, cubes, name):
+        self._cubes, self._name = cubes, name
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._cubes[self._name]
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, idx):
+        return self._cubes[self._name][idx]
+
+    @property
+    def shape(self):
+        o = self._cubes._owner
+        return (o._nz, o._nm, o._nk)

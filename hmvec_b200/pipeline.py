@@ -1,0 +1,262 @@
+"""GridSix: the whole hot path for one z-slab as a stream-ordered, allocation-free launch sequence.
+
+    sigma^2 -> n(M,z), b(M,z) -> halo geometry -> u_NFW cube -> M200c, GNFW parameters -> u_electron cube ->
+    HOD (mthresh<->ngal bisection + occupations) -> {mm,ee,me,gg,gm,ge} 1h+2h spectra -> [all-gather over z] ->
+    Limber C_kk, C_kg
+
+This is what `HaloModel(...)`, `add_battaglia_profile`, `add_hod(ngal=...)`, six `get_power` calls and
+`C_kk`/`C_kg` do in the reference (hmvec.py:76-572, cosmology.py:536-568,867-904), arranged B200-first: every buffer
+(two [nz][nm][ldk] cubes, ~20 [nz,nm] arrays, workspaces, outputs) is allocated once in __init__, `run()` only issues
+kernel launches through the C ABI on the current stream with no host synchronisation, host inputs arrive through
+pinned staging buffers (`upload`) and results leave through pinned buffers (`download`).  Host-side inputs (the CAMB
+products and O(nz) background scalars) are prepared by `make_inputs`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+from .cosmology import Cosmology, simpson_weights
+from .params import default_params, battaglia_defaults
+
+TAGS = ("mm", "ee", "me", "gg", "gm", "ge")
+
+# host inputs that change with the cosmology / redshift slab (uploaded every e2e step), name -> shape key
+_PER_STEP = ("Pzk", "sPzk", "drho1", "drho2", "rhocrit", "hofz", "ngal_target")
+
+
+def make_inputs(zs, ms, ks, params=None, mdef='vir', ngal=None, ells=None, lzs=2.5, gz=0.8, accuracy='low'):
+    """Host-side producers: linear power on `ks` and on the sigma^2 grid, Simpson weights, background scalars per z,
+    Limber prefactors.  Everything here is O(nz*nk) numpy work on inputs of the path (north_star: "Linear P(k) from
+    CAMB stays a host-side input")."""
+    zs = np.asarray(zs, dtype=np.float64).reshape(-1)
+    ms = np.asarray(ms, dtype=np.float64).reshape(-1)
+    ks = np.asarray(ks, dtype=np.float64).reshape(-1)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        c = Cosmology(dict(params or {}), accuracy=accuracy)
+    p = c.p
+    ks_sig = np.geomspace(p['sigma2_kmin'], p['sigma2_kmax'], int(p['sigma2_numks']))
+    rho_m0 = float(np.atleast_1d(c.rho_matter_z(0.))[0])
+    rhoc = np.asarray(c.rho_critical_z(zs), dtype=np.float64)
+    if mdef == 'vir':
+        x = c.omz(zs) - 1.
+        drho1 = rhoc * (18. * np.pi ** 2. + 82. * x - 39. * x ** 2.)
+    elif mdef == 'mean':
+        drho1 = c.rho_matter_z(zs) * 200.
+    else:
+        raise ValueError("mdef must be 'vir' or 'mean'")
+    inp = dict(zs=zs, ms=ms, ks=ks, ks_sig=ks_sig,
+               kw=simpson_weights(ks_sig) * ks_sig ** 2. / 2. / np.pi ** 2.,
+               R=(3. * ms / 4. / np.pi / rho_m0) ** (1. / 3.),
+               Pzk=c.P_lin_approx(ks, zs), sPzk=c.P_lin_approx(ks_sig, zs),
+               drho1=np.asarray(drho1, dtype=np.float64), drho2=200. * rhoc, rhocrit=rhoc,
+               hofz=np.asarray(c.h_of_z(zs), dtype=np.float64),
+               ngal_target=np.geomspace(1e-3, 1e-5, zs.size) if ngal is None else np.asarray(ngal, dtype=np.float64),
+               rho_m0=rho_m0, h=c.h, p=p, mdef=mdef)
+    if ells is not None:
+        chis = c.comoving_radial_distance(zs)
+        W = c.lensing_window(zs, lzs)
+        with np.errstate(all="ignore"):
+            inp["ells"] = np.asarray(ells, dtype=np.float64)
+            inp["chis"] = chis
+            inp["pref_kk"] = inp["hofz"] * W * W / chis ** 2.                  # cosmology.py:887 with C_kk's windows
+            chig = c.comoving_radial_distance(np.array([gz]))
+            inp["gz"] = np.array([gz])
+            inp["chig"] = chig
+            inp["pref_kg"] = c.h_of_z(np.array([gz])) * c.lensing_window(np.array([gz]), lzs) / chig ** 2.
+    return inp
+
+
+def slab_inputs(inp, sl):
+    """The rows of the per-redshift inputs owned by slab `sl` (everything else is replicated)."""
+    out = dict(inp)
+    for k in ("zs", "Pzk", "sPzk", "drho1", "drho2", "rhocrit", "hofz", "ngal_target"):
+        out[k] = np.ascontiguousarray(inp[k][sl])
+    return out
+
+
+class GridSix(object):
+    STAGES = ("sigma2", "massfn", "uk_nfw", "uk_electron", "hod", "power_six", "limber")
+
+    def __init__(self, inp, device=None, zcomm=None, family="AGN", xmax=None, nxs=None, nz_total_zs=None):
+        """inp: this rank's slab of `make_inputs` (see slab_inputs).  zcomm: zshard.ZComm for a sharded z axis;
+        nz_total_zs: the full redshift vector (needed for Limber after the all-gather)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("hmvec_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback.")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.zcomm = zcomm
+        p = self.p = inp["p"]
+        self.nz, self.nm, self.nk = inp["zs"].size, inp["ms"].size, inp["ks"].size
+        self.nks = inp["ks_sig"].size
+        self.ldk = ((self.nk + 15) // 16) * 16
+        self.rho_m0, self.h = inp["rho_m0"], inp["h"]
+        self.kmax = float(np.max(inp["ks"]))
+        self.xmax = float(p['electron_density_profile_integral_xmax'] if xmax is None else xmax)
+        self.nxs = int(p['electron_density_profile_integral_numxs'] if nxs is None else nxs)
+        tag = 'mean' if inp["mdef"] == 'mean' else 'vir'
+        self.duffy = (p['duffy_A_' + tag], p['duffy_alpha_' + tag], p['duffy_beta_' + tag])
+        fam = battaglia_defaults[family]
+        self.gamma = float(p['battaglia_gas_gamma'])
+        self.fit9 = capi.darr([fam[q + s] for q in ('rho0', 'alpha', 'beta') for s in ('_A0', '_alpham', '_alphaz')])
+        self.hodp = capi.darr([p['hod_sig_log_mstellar'], p['hod_alphasat'], p['hod_Bsat'], p['hod_betasat'],
+                               p['hod_Bcut'], p['hod_betacut'], 0.0, 0.0])
+        f64 = dict(dtype=torch.float64, device=self.device)
+        E = lambda *s: torch.empty(s, **f64)
+        nz, nm, nk = self.nz, self.nm, self.nk
+        # replicated inputs (uploaded once)
+        self.d = {k: torch.as_tensor(np.array(inp[k], dtype=np.float64), device=self.device)
+                  for k in ("zs", "ms", "ks", "ks_sig", "kw", "R")}
+        # per-step inputs: pinned host staging + device buffers
+        self.h_in = {k: torch.as_tensor(np.array(inp[k], dtype=np.float64)).pin_memory() for k in _PER_STEP}
+        for k in _PER_STEP:
+            self.d[k] = torch.empty_like(self.h_in[k], device=self.device)
+        # intermediates
+        for k in ("sigma2", "nzm", "bh", "cs", "rvir", "m200c", "rs", "cmax", "xc", "alpha", "expo", "amp", "oscale",
+                  "Nc", "Ns", "NsNsm1", "NcNs"):
+            self.d[k] = E(nz, nm)
+        self.d["ngal"], self.d["bg"], self.d["l10"] = E(nz), E(nz), E(nz)
+        self.d["sig_ws"] = E(int(capi.lib.hmv_sigma2_ws_doubles(nz, nm, self.nks)))
+        self.d["pow_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
+        self.d["bis_ws"] = E(nz * (capi.HMV_BISECT_MAXIT + 2))
+        self.mask = torch.empty(1, dtype=torch.int64, device=self.device)
+        self.iters = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # the two cubes: [nz][nm][ldk]; pad columns (if any) zeroed once, never written by the kernels
+        self.um = torch.empty((nz, nm, self.ldk), **f64)
+        self.ue = torch.empty((nz, nm, self.ldk), **f64)
+        if self.ldk > nk:
+            self.um[..., nk:] = 0.0
+            self.ue[..., nk:] = 0.0
+        self.p1 = E(6, nz, nk)
+        self.p2 = E(6, nz, nk)
+        self.h_p1 = torch.empty((6, nz, nk), dtype=torch.float64).pin_memory()
+        self.h_p2 = torch.empty((6, nz, nk), dtype=torch.float64).pin_memory()
+        # Limber (replicated on every rank after the all-gather)
+        self.has_limber = "ells" in inp
+        if self.has_limber:
+            self.zs_all = torch.as_tensor(np.array(inp["zs"] if nz_total_zs is None else nz_total_zs, dtype=np.float64),
+                                          device=self.device)
+            self.nl = inp["ells"].size
+            for k in ("ells", "chis", "pref_kk", "gz", "chig", "pref_kg"):
+                self.d[k] = torch.as_tensor(np.array(inp[k], dtype=np.float64), device=self.device)
+            self.cl = E(2, self.nl)
+            self.h_cl = torch.empty((2, self.nl), dtype=torch.float64).pin_memory()
+        self.launches_per_run = 0
+        self._ev = None
+
+    # ------------------------------------------------------------------ host <-> device
+    def h2d_bytes(self):
+        return int(sum(t.numel() * 8 for t in self.h_in.values()))
+
+    def d2h_bytes(self):
+        n = self.h_p1.numel() * 8 + self.h_p2.numel() * 8
+        return int(n + (self.h_cl.numel() * 8 if self.has_limber else 0))
+
+    def upload(self):
+        for k in _PER_STEP:
+            self.d[k].copy_(self.h_in[k], non_blocking=True)
+
+    def download(self):
+        self.h_p1.copy_(self.p1, non_blocking=True)
+        self.h_p2.copy_(self.p2, non_blocking=True)
+        if self.has_limber:
+            self.h_cl.copy_(self.cl, non_blocking=True)
+
+    # ------------------------------------------------------------------ the launch sequence
+    def _mark(self, i):
+        if self._ev is not None:
+            self._ev[i].record()
+
+    def run(self, events=None):
+        """Issue the whole path on the current stream.  `events`: optional list of len(STAGES)+1 CUDA events
+        recorded at the stage boundaries (per-kernel timing for the roofline report)."""
+        L, d, ptr, st = capi.lib, self.d, capi.ptr, capi.stream()
+        nz, nm, nk, ldk = self.nz, self.nm, self.nk, self.ldk
+        p = self.p
+        self._ev = events
+        n = 0
+        self._mark(0)
+        capi.check(L.hmv_sigma2(nz, nm, self.nks, ptr(d["sPzk"]), ptr(d["kw"]), ptr(d["ks_sig"]), ptr(d["R"]),
+                                float(p['Wkr_taylor_switch']), ptr(d["sig_ws"]), ptr(d["sigma2"]), st), "hmv_sigma2")
+        n += 3
+        self._mark(1)
+        capi.check(L.hmv_mass_function(nz, nm, ptr(d["sigma2"]), ptr(d["ms"]), self.rho_m0, p['st_A'], p['st_a'],
+                                       p['st_p'], p['st_deltac'], ptr(d["nzm"]), ptr(d["bh"]), st), "hmv_mass_function")
+        capi.check(L.hmv_halo_geometry(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["drho1"]), self.duffy[0], self.duffy[1],
+                                       self.duffy[2], self.h, ptr(d["cs"]), ptr(d["rvir"]), st), "hmv_halo_geometry")
+        n += 2
+        self._mark(2)
+        capi.check(L.hmv_uk_nfw(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), ptr(d["cs"]), ptr(d["rvir"]), ptr(self.um),
+                                st), "hmv_uk_nfw")
+        n += 1
+        self._mark(3)
+        capi.check(L.hmv_mdelta(nz, nm, ptr(d["ms"]), ptr(d["cs"]), ptr(d["drho1"]), ptr(d["drho2"]), ptr(d["m200c"]),
+                                st), "hmv_mdelta")
+        capi.check(L.hmv_gnfw_params(0, nz, nm, ptr(d["zs"]), ptr(d["m200c"]), ptr(d["rvir"]), ptr(d["rhocrit"]),
+                                     ptr(d["hofz"]), self.fit9, self.gamma, 1.0, 1.0, 1.0, ptr(d["rs"]), ptr(d["cmax"]),
+                                     ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]), ptr(d["oscale"]),
+                                     st), "hmv_gnfw_params")
+        capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["rs"]),
+                                           ptr(d["cmax"]), ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]),
+                                           ptr(d["oscale"]), self.gamma, self.xmax, self.nxs, 1, ptr(self.ue), st),
+                   "hmv_profile_transform")
+        n += 3
+        self._mark(4)
+        capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]), self.hodp,
+                                    float(p['hod_bisection_search_min_log10mthresh']),
+                                    float(p['hod_bisection_search_max_log10mthresh']),
+                                    float(p['hod_bisection_search_rtol']), ptr(d["bis_ws"]),
+                                    C.c_void_p(self.mask.data_ptr()), st), "hmv_hod_bisect")
+        if self.zcomm is not None:
+            self.zcomm.all_reduce_and(self.mask)
+        capi.check(L.hmv_hod_pick(nz, ptr(d["bis_ws"]), C.c_void_p(self.mask.data_ptr()),
+                                  float(p['hod_A_log10mthresh']), ptr(d["l10"]), ptr(self.iters), st), "hmv_hod_pick")
+        capi.check(L.hmv_hod(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["l10"]), self.hodp, 0, ptr(d["nzm"]), ptr(d["bh"]),
+                             ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NsNsm1"]), ptr(d["NcNs"]), ptr(d["ngal"]), ptr(d["bg"]),
+                             st), "hmv_hod")
+        n += 4
+        self._mark(5)
+        capi.check(L.hmv_power_six(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                   ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), ptr(self.um), ptr(self.ue),
+                                   ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NcNs"]), ptr(d["NsNsm1"]), ptr(d["ngal"]),
+                                   ptr(d["pow_ws"]), ptr(self.p1), ptr(self.p2), st), "hmv_power_six")
+        n += 2
+        self._mark(6)
+        if self.has_limber:
+            n += self._limber(st)
+        self._mark(7)
+        self.launches_per_run = n
+        self._ev = None
+
+    def _limber(self, st):
+        """P = P1h + P2h for mm and gm, all-gathered over z when sharded, then C_kk and C_kg (cosmology.py:536-568)."""
+        L, d, ptr = capi.lib, self.d, capi.ptr
+        if self.zcomm is not None:
+            # one all-gather of the four [nz_local,nk] slabs (P1h, P2h of mm and gm) -> [4, nz_total, nk]
+            P = self.zcomm.all_gather_z(torch.stack((self.p1[0], self.p2[0], self.p1[4], self.p2[4])))
+            mm1, mm2, gm1, gm2 = P[0], P[1], P[2], P[3]
+            self._Pfull = P
+        else:
+            mm1, mm2, gm1, gm2 = self.p1[0], self.p2[0], self.p1[4], self.p2[4]
+        nzt = mm1.shape[0]
+        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, self.nk, self.nk, ptr(self.zs_all), ptr(d["ks"]),
+                                ptr(mm1), ptr(mm2), nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
+                                ptr(self.cl[0]), st), "hmv_limber(kk)")
+        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, self.nk, self.nk, ptr(self.zs_all), ptr(d["ks"]),
+                                ptr(gm1), ptr(gm2), 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
+                                st), "hmv_limber(kg)")
+        return 2
+
+    def spectra(self):
+        """Download and return ({tag: P1h}, {tag: P2h}, C_kk, C_kg) as numpy (synchronises)."""
+        self.download()
+        torch.cuda.current_stream().synchronize()
+        p1, p2 = self.h_p1.numpy().copy(), self.h_p2.numpy().copy()
+        out1 = {t: p1[i] for i, t in enumerate(TAGS)}
+        out2 = {t: p2[i] for i, t in enumerate(TAGS)}
+        if self.has_limber:
+            cl = self.h_cl.numpy().copy()
+            return out1, out2, cl[0], cl[1]
+        return out1, out2, None, None

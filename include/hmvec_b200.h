@@ -91,10 +91,20 @@ int hmv_hod(int nz, int nm, const double* zs_d, const double* ms_d, const double
 
 /* ---- a10: mthresh <-> ngal bisection  (utils.py:9-42, hmvec.py:415-433) -----------------------------
  * Reproduces the reference's all-z loop exactly: every z bisects independently for HMV_BISECT_MAXIT
- * iterations recording its midpoint and whether |x/x_target - 1| <= rtol; the result is the midpoint of the
- * first iteration at which ALL z pass.  ws_d: nz*(HMV_BISECT_MAXIT+2) doubles.  iters_d: int32[1], the
- * iteration count (0 = never converged within HMV_BISECT_MAXIT).  log10mthresh_d [nz] = y * A_log10mthresh. */
+ * iterations recording its midpoint and whether |x/x_target - 1| <= rtol (bit `it` of its pass mask); the
+ * result is the midpoint of the first iteration at which ALL z pass.
+ *   hmv_hod_bisect : runs the iterations; ws_d = nz*(HMV_BISECT_MAXIT+2) doubles (midpoints + per-z masks);
+ *                    mask_d[0] (uint64, device) = AND of the masks of THIS call's redshifts.
+ *   (z-sharded runs AND-reduce mask_d over the ranks here -- the reference's loop condition is global in z.)
+ *   hmv_hod_pick   : log10mthresh_d[z] = midpoint(z, first set bit of mask_d[0]) * A_log10mthresh;
+ *                    iters_d: int32[1], the iteration count (0 = never converged within HMV_BISECT_MAXIT).
+ *   hmv_hod_solve  : both steps on one device. */
 #define HMV_BISECT_MAXIT 64
+int hmv_hod_bisect(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
+                   const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
+                   double* ws_d, unsigned long long* mask_d, void* stream);
+int hmv_hod_pick(int nz, const double* ws_d, const unsigned long long* mask_d, double A_log10mthresh,
+                 double* log10mthresh_d, int* iters_d, void* stream);
 int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
                   const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
                   double A_log10mthresh, double* ws_d, double* log10mthresh_d, int* iters_d, void* stream);
@@ -136,10 +146,14 @@ int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const dou
 
 /* ---- a16: Limber integral  (cosmology.py:867-904) ---------------------------------------------------
  * C_l = trapz_gz( pref[gz] * P(k=(l+1/2)/chi[gz], gz) )  (ngz>1) or pref*P (ngz==1); P by bilinear
- * interpolation in linear (k,z) with out-of-range coordinates clamped to the table edge. pref = H W1 W2/chi^2. */
+ * interpolation in linear (k,z) with out-of-range coordinates clamped to the table edge. pref = H W1 W2/chi^2.
+ * P2_d: optional second [nzp][ldp] table added to P_d at lookup (P = P1h + P2h without a temporary), or NULL. */
 int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const double* zs_d, const double* ks_d,
-               const double* P_d, int ngz, const double* gzs_d, const double* pref_d, const double* chis_d,
-               double* cl_d, void* stream);
+               const double* P_d, const double* P2_d, int ngz, const double* gzs_d, const double* pref_d,
+               const double* chis_d, double* cl_d, void* stream);
+
+/* ---- test hook: elementwise Si(x), Ci(x) of the device routine used by hmv_uk_nfw (x > 0) -----------*/
+int hmv_sici_test(int n, const double* x_d, double* si_d, double* ci_d, void* stream);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------------
  * hmv_bench_dfma: dependent-chain-free DFMA micro-benchmark; returns achieved FP64 TFLOP/s (2 flop per FMA)

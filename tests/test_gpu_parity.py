@@ -1,0 +1,227 @@
+"""Parity of the CUDA path (through the drop-in HaloModel / C ABI) against the golden vectors produced by the
+unmodified reference and against the CPU oracle.  Tolerance: rtol 1e-6 (FP64 kernels; BASELINE.json north_star) on
+every [nz,nk] spectrum and [nz,nm] weight; u(k) cubes, which oscillate through zero, add an absolute floor of
+1e-9 * max|cube| (u is O(1); the spectra built from them are still compared with pure rtol)."""
+import numpy as np
+import pytest
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+OSC = 1e-9
+# Occupations are 0.5*(1-erf(x)): where Nc < 1e-10 the result is a difference of two numbers that agree to 11+ digits,
+# so one ulp of erf (CUDA libm vs cephes) is a 1e-5 relative change of a 1e-12 value.  Floor: 1e-14 * max|array|.
+HOD_FLOOR = 1e-14
+SPECTRA = [("mm", "nfw", "nfw"), ("ee", "electron", "electron"), ("me", "nfw", "electron"),
+           ("gg", "g", "g"), ("gm", "g", "nfw"), ("ge", "g", "electron")]
+
+
+@pytest.fixture(scope="module")
+def hm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    import hmvec_b200
+    return hmvec_b200
+
+
+@pytest.fixture(scope="module")
+def mini(hm, golden_mini):
+    g = golden_mini
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + g["zs"] * 0.0)
+    return h
+
+
+def test_background_and_plin(mini, golden_mini):
+    g, h = golden_mini, mini
+    assert_close(h.hubble_parameter(g["zs"]), g["hubble"], 1e-12)
+    assert_close(h.comoving_radial_distance(g["zs"]), g["chi"], 1e-12)
+    assert_close(h.rho_critical_z(g["zs"]), g["rho_crit"], 1e-12)
+    assert_close(h.deltav(g["zs"]), g["deltav"], 1e-12)
+    assert_close(h.Pzk, g["Pzk"], 1e-9, name="Pzk")
+    assert_close(h.sPzk[:, ::10], g["sPzk_sub"], 1e-9, name="sPzk")
+
+
+def test_mass_function(mini, golden_mini):
+    g, h = golden_mini, mini
+    assert_close(h.sigma2, g["sigma2"], 1e-9, name="sigma2")
+    assert_close(h.nzm, g["nzm"], 1e-6, name="nzm")
+    assert_close(h.bh, g["bh"], 1e-9, name="bh")
+    assert_close(h.concentration(), g["cs"], 1e-12, name="cs")
+    assert_close(h._rvir_d.cpu().numpy(), g["rvirs"], 1e-12, name="rvir")
+    m200, _ = h._m200c_device()
+    assert_close(m200.cpu().numpy(), g["m200c"], 1e-9, name="m200c")
+
+
+def test_profiles(mini, golden_mini):
+    g, h = golden_mini, mini
+    assert_close(h.uk_profiles["nfw"], g["uk_nfw"], 1e-6, OSC, "uk_nfw")
+    assert_close(h.uk_profiles["electron"], g["uk_e"], 1e-6, OSC, "uk_e")
+    h.add_battaglia_profile("esh", family="SH", xmax=10, nxs=2000)
+    assert_close(h.uk_profiles["esh"], g["uk_e_sh"], 1e-6, OSC, "uk_e_sh")
+    h.add_battaglia_profile("eov", family="AGN", xmax=20, nxs=5000,
+                            param_override={"battaglia_gas_gamma": -0.3, "rho0_A0": 3000., "alpha_alphaz": 0.25,
+                                            "not_a_key": 1.0})
+    assert_close(h.uk_profiles["eov"], g["uk_e_ov"], 1e-6, OSC, "uk_e_ov")
+    h.add_nfw_profile("nfwnum", numeric=True, nxs=8000, xmax=100)
+    assert_close(h.uk_profiles["nfwnum"], g["uk_nfwnum"], 1e-6, OSC, "uk_nfwnum")
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    assert_close(h.pk_profiles["y"], g["pk_y"], 1e-6, OSC, "pk_y")
+    for tag, a, b in [("shsh", "esh", "esh"), ("ovm", "eov", "nfw")]:
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+
+
+def test_hod_and_spectra(mini, golden_mini):
+    g, h = golden_mini, mini
+    zs = g["zs"]
+    h.add_hod("g2", ngal=g["g2_ngal_target"])
+    h.add_hod("gmin", mthresh=10 ** (10.2 + 0.1 * zs), corr="min")
+    for n in ("g", "g2", "gmin"):
+        for k in ("Nc", "Ns", "NsNsm1", "NcNs", "ngal", "bg", "log10mthresh"):
+            assert_close(h.hods[n][k], g["hod_%s_%s" % (n, k)], 1e-6, HOD_FLOOR, name="%s.%s" % (n, k))
+    pairs = SPECTRA + [("g2g2", "g2", "g2"), ("g2e", "g2", "electron"), ("gming", "gmin", "gmin"),
+                       ("gminm", "gmin", "nfw"), ("gg2", "g", "g2"), ("eg", "electron", "g")]
+    for tag, a, b in pairs:
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+        assert_close(h.get_power(a, b), g["P1h_" + tag] + g["P2h_" + tag], 1e-6, name="P_" + tag)
+    assert_close(h.get_power_2halo("g", "electron", b1_in=g["b1_in"], b2_in=g["b2_in"]), g["P2h_ge_bin"], 1e-6)
+    p1, p2 = h.get_power_six("nfw", "electron", "g")
+    for tag, _, _ in SPECTRA:
+        assert_close(p1[tag], g["P1h_" + tag], 1e-6, name="six P1h_" + tag)
+        assert_close(p2[tag], g["P2h_" + tag], 1e-6, name="six P2h_" + tag)
+
+
+def test_central_profile_override_and_pressure_spectra(mini, golden_mini):
+    g, h = golden_mini, mini
+    zs = g["zs"]
+    if "nfwnum" not in h.uk_profiles:
+        h.add_nfw_profile("nfwnum", numeric=True, nxs=8000, xmax=100)
+    if "y" not in h.pk_profiles:
+        h.add_battaglia_pres_profile("y")
+    h.add_hod("gcen", mthresh=10 ** 10.8 + zs * 0., central_profile_name="electron", satellite_profile_name="nfwnum")
+    h.add_hod("gov", mthresh=10 ** 10.5 + zs * 0.,
+              param_override={"hod_sig_log_mstellar": 0.3, "hod_alphasat": 1.1, "hod_Bsat": 8.0, "hod_betacut": 0.5})
+    for n in ("gcen", "gov"):
+        for k in ("Nc", "Ns", "NsNsm1", "ngal", "bg"):
+            assert_close(h.hods[n][k], g["hod_%s_%s" % (n, k)], 1e-6, HOD_FLOOR, name="%s.%s" % (n, k))
+    for tag, a, b in [("gcengcen", "gcen", "gcen"), ("gcene", "gcen", "electron"), ("govgov", "gov", "gov"),
+                      ("yy", "y", "y"), ("ym", "y", "nfw"), ("yg", "y", "g"), ("nn", "nfwnum", "nfwnum")]:
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+
+
+def test_limber(mini, golden_mini):
+    g, h = golden_mini, mini
+    zs, ks, ells = g["zs"], g["ks"], g["ells"]
+    Pmm = g["P1h_mm"] + g["P2h_mm"]
+    Pgm = g["P1h_gm"] + g["P2h_gm"]
+    Pgg = g["P1h_gg"] + g["P2h_gg"]
+    Pyy = g["P1h_yy"] + g["P2h_yy"]
+    assert_close(h.lensing_window(zs, 2.5), g["lens_window_25"], 1e-9)
+    assert_close(h.lensing_window(zs, g["lz"], g["ldndz"]), g["lens_window_dndz"], 1e-9)
+    assert_close(h.C_kk(ells, zs, ks, Pmm, lzs1=2.5, lzs2=2.5), g["C_kk"], 1e-6)
+    assert_close(h.C_kg(ells, zs, ks, Pgm, gzs=0.8, lzs=2.5), g["C_kg"], 1e-6)
+    assert_close(h.C_yy(ells, zs, ks, Pyy), g["C_yy"], 1e-6)
+    assert_close(h.C_kk(ells, zs, ks, Pmm, lzs1=g["lz"], ldndz1=g["ldndz"], lzs2=1.1), g["C_kk_dndz"], 1e-6)
+    assert_close(h.C_kg(ells, zs, ks, Pgm, gzs=g["gz"], gdndz=g["gdndz"], lzs=1100.), g["C_kg_dndz"], 1e-6)
+    assert_close(h.C_gg(ells, zs, ks, Pgg, g["gz"], g["gdndz"]), g["C_gg_dndz"], 1e-6)
+
+
+def test_mean_mdef(hm, golden_mini_mean):
+    g = golden_mini_mean
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low', mdef='mean',
+                     params={"omch2": 0.125, "H0": 70.0, "ns": 0.97, "st_a": 0.75, "kstar_damping": 0.02})
+    h.add_battaglia_profile("electron", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + g["zs"] * 0.0)
+    assert_close(h.sigma2, g["sigma2"], 1e-9)
+    assert_close(h.nzm, g["nzm"], 1e-6)
+    assert_close(h.concentration(), g["cs"], 1e-12)
+    assert_close(h.uk_profiles["nfw"], g["uk_nfw"], 1e-6, OSC)
+    assert_close(h.uk_profiles["electron"], g["uk_e"], 1e-6, OSC)
+    for tag, a, b in SPECTRA:
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+
+
+def test_readme_grid(hm, golden_readme):
+    """C1-C3 (README.rst:55-84): zs[0]=0, 19-iteration ngal bisection."""
+    g = golden_readme
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    assert_close(h.sigma2, g["sigma2"], 1e-9)
+    assert_close(h.nzm, g["nzm"], 1e-6)
+    assert_close(h.bh, g["bh"], 1e-9)
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    assert_close(h.uk_profiles["nfw"][:, ::8, ::4], g["uk_nfw_sub"], 1e-6, OSC)
+    assert_close(h.uk_profiles["electron"][:, ::8, ::4], g["uk_e_sub"], 1e-6, OSC)
+    h.add_hod("g", mthresh=10 ** 10.5 + g["zs"] * 0.0)
+    h.add_hod("g2", ngal=g["g2_ngal_target"])
+    assert h.hods["g2"]["iterations"] == 19
+    for n in ("g", "g2"):
+        for k in ("Nc", "Ns", "NsNsm1", "NcNs", "ngal", "bg", "log10mthresh"):
+            assert_close(h.hods[n][k], g["hod_%s_%s" % (n, k)], 1e-6, HOD_FLOOR, name="%s.%s" % (n, k))
+    for tag, a, b in SPECTRA + [("g2g2", "g2", "g2"), ("g2e", "g2", "electron")]:
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+
+
+def test_large_slab(hm, golden_largeslab):
+    """Two redshifts at the LARGE grid's M and k resolution (2000 M x 10000 k)."""
+    g = golden_largeslab
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    assert_close(h.sigma2, g["sigma2"], 1e-9)
+    assert_close(h.nzm, g["nzm"], 1e-6)
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + g["zs"] * 0.0)
+    assert_close(h.uk_profiles["nfw"][:, ::400], g["uk_nfw_rows"], 1e-6, OSC)
+    assert_close(h.uk_profiles["electron"][:, ::400], g["uk_e_rows"], 1e-6, OSC)
+    p1, p2 = h.get_power_six("nfw", "electron", "g")
+    for tag, a, b in SPECTRA:
+        assert_close(p1[tag], g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(p2[tag], g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="pair P1h_" + tag)
+
+
+def test_known_answers(hm, golden_kat):
+    """Device Si/Ci against scipy, and structural invariants the reference's code implies."""
+    import torch
+    from scipy.special import sici
+    from hmvec_b200 import _capi as capi
+    x = np.concatenate([np.geomspace(1e-8, 4.0, 4000), np.linspace(4.0, 60.0, 4000), np.geomspace(60, 1e6, 2000)])
+    xd = torch.as_tensor(x, device="cuda")
+    si, ci = torch.empty_like(xd), torch.empty_like(xd)
+    capi.check(capi.lib.hmv_sici_test(x.size, capi.ptr(xd), capi.ptr(si), capi.ptr(ci), capi.stream()), "sici")
+    S, Cc = sici(x)
+    np.testing.assert_allclose(si.cpu().numpy(), S, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(ci.cpu().numpy(), Cc, rtol=1e-12, atol=3e-15)
+
+
+def test_two_halo_consistency_invariant(mini):
+    """P2h(k->0) -> b1 b2 P_lin by construction of the consistency term (hmvec.py:566-572): at the lowest k the
+    matter u(k) -> 1, so I - C -> 0 and P2h_mm -> Pzk."""
+    p2 = mini.get_power_2halo("nfw", "nfw")
+    np.testing.assert_allclose(p2[:, 0], mini.Pzk[:, 0], rtol=2e-3)
+
+
+def test_errors(hm, mini):
+    with pytest.raises(AssertionError):
+        mini.add_battaglia_profile("nfw")
+    with pytest.raises(AssertionError):
+        mini.add_battaglia_profile("electron")
+    with pytest.raises(ValueError):
+        mini.add_hod("gbad", mthresh=np.ones(3))
+    with pytest.raises(ValueError):
+        mini.add_hod("gbad2", ngal=np.ones(3))
+    with pytest.raises(ValueError):
+        mini.add_hod("gbad3", mthresh=10 ** 10.5 + mini.zs * 0, param_override={"nope": 1})
+    with pytest.raises(ValueError):
+        mini.get_power_1halo("nfw", "doesnotexist")
+    with pytest.raises(NotImplementedError):
+        hm.HaloModel(mini.zs, mini.ks, ms=mini.ms, accuracy='low', mass_function="tinker")
+    from hmvec_b200 import _capi as capi
+    assert capi.lib.hmv_uk_nfw(0, 1, 1, 16, None, None, None, None, None, None) == -1
+    assert "bad sizes" in capi.last_error()
