@@ -5,31 +5,41 @@
 // One CTA owns HB consecutive-mass halos of one redshift.  The (z,M,x) profile cube never exists: samples are
 // evaluated chunk by chunk into shared memory, the sine sums
 //        U_j = step * sum_n x_n y_n sin(2 pi j n / N)          ( == -Im rfft(x*y) * step, fft.py:49 )
-// are accumulated only for the bins j the target k-range needs (bin-skipping; the theta-cut bounds n), with the
-// twiddle advanced by a rotation recurrence re-seeded exactly (sincospi of a reduced integer phase) every chunk,
-// then u_j = U_j/kt_j/mnorm is linearly interpolated onto ks from shared memory (direct index j=floor(k/kout_1),
-// no search) and written once, coalesced.
+// are accumulated only for the bins j the target k-range needs (bin skipping; the theta-cut bounds n), then
+// u_j = U_j/kt_j/mnorm is linearly interpolated onto ks from shared memory (direct index j=floor(k/kout_1), no
+// search) and written once, coalesced.
+//
+// The sine matrix S[n][j] = sin(2 pi (n j mod N)/N) is halo independent.  For N <= 5400 it is read from a one-period
+// table staged in shared memory (index advanced by j mod N: two integer instructions and one LDS per (n,j), leaving
+// the FP64 pipe to the HB accumulations, two bins per thread sharing the sample loads).  Larger N fall back to a
+// rotation recurrence re-seeded exactly every chunk.  Because the number of bins a halo needs grows like M^(1/3)
+// (10 ... N/2), CTAs are launched in three bin-count classes with shared-memory footprints of 73 / 106 / 216 KB so
+// that the many small halos run 3 CTAs per SM instead of being sized for the largest one.
 #include "common.cuh"
 
 namespace hmv {
 
-constexpr int TT = 256;    // threads per CTA == samples per chunk
-constexpr int NCH = TT;
-
 struct TParams {
-  int nz, nm, nk, ldk, N, J, JS, nmg, do_mass_norm;
+  int nz, nm, nk, ldk, N, J, JS, nmg, do_mass_norm, jlo, jhi;
   double gamma, dx, step, kt1, kmax;
-  const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale;
+  const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab;
   double* uk;
 };
 
-template <int HB>
+__global__ void sine_table_kernel(int N, double* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) tab[i] = sinpi(2.0 * (double)i / (double)N);
+}
+
+template <int HB, int TT, bool TABLE>
 __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) {
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
-  double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
-  double* red = gs + NCH * HB;                // [32]
+  double* gs = Us + (size_t)HB * p.JS;        // [TT][HB]
+  double* red = gs + TT * HB;                 // [32]
+  double* T = red + 32;                       // [N] (TABLE only)
   __shared__ double h_cmax[HB], h_lxc[HB], h_alpha[HB], h_expo[HB], h_amp[HB], h_a[HB], h_oscale[HB];
+  __shared__ double h_k1[HB], h_kJ[HB], h_inv[HB], h_u1[HB];
   __shared__ int h_valid[HB];
 
   const int tid = threadIdx.x;
@@ -48,10 +58,13 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     h_alpha[tid] = p.alpha[r];
     h_expo[tid] = p.expo[r];
     h_amp[tid] = p.amp[r];
-    h_a[tid] = p.rs[r] * opz;                 // kout_j = kt_j / rs / (1+z)      (fft.py:92)
+    const double a = p.rs[r] * opz;           // kout_j = kt_j / rs / (1+z)      (fft.py:92)
+    h_a[tid] = a;
     h_oscale[tid] = p.outscale ? p.outscale[r] : 1.0;
+    h_k1[tid] = p.kt1 / a;
+    h_inv[tid] = a / p.kt1;
+    h_kJ[tid] = ((double)p.J * p.kt1) / a;
   }
-  for (int i = tid; i < HB * p.JS; i += TT) Us[i] = 0.0;
   __syncthreads();
 
   // sample and bin bounds shared by the HB halos of this CTA
@@ -61,15 +74,22 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     cmx = fmax(cmx, h_cmax[h]);
     if (h_valid[h]) amax = fmax(amax, h_a[h]);
   }
-  int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
+  const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
   const int jn = (int)fmin((double)p.J, floor(p.kmax * amax / p.kt1) + 2.0);
+  if (jn <= p.jlo || jn > p.jhi) return;      // not this launch's bin-count class (uniform over the CTA)
+
+  if (TABLE)
+    for (int i = tid; i < p.N; i += TT) T[i] = __ldg(p.sintab + i);
+  for (int h = 0; h < HB; ++h)
+    for (int j = tid; j <= jn + 1; j += TT) Us[(size_t)h * p.JS + j] = 0.0;
+  __syncthreads();
 
   const double twoN = 2.0 / (double)p.N;
   double msum[HB];
 #pragma unroll
   for (int h = 0; h < HB; ++h) msum[h] = 0.0;
 
-  for (int n0 = 0; n0 < nb; n0 += NCH) {
+  for (int n0 = 0; n0 < nb; n0 += TT) {
     {  // ---- evaluate x*y for sample n0+tid of every halo (theta-cut: x <= cmax, fft.py:79-81) ----
       const int n = n0 + tid;
       const double x = (double)(n + 1) * p.dx;
@@ -89,24 +109,72 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
       }
     }
     __syncthreads();
-    const int nlen = min(NCH, nb - n0);
-    for (int j = tid + 1; j <= jn; j += TT) {
-      double s, c, S, C;
-      sincospi(twoN * (double)(((long long)j * n0) % p.N), &s, &c);  // exact phase of sample n0
-      sincospi(twoN * (double)j, &S, &C);
-      double acc[HB];
+    const int nlen = min(TT, nb - n0);
+    if (TABLE) {
+      int jb = 1;
+      // two bins per thread while more than TT bins remain (they share the sample loads), then one
+      for (; jn - jb + 1 > TT; jb += 2 * TT) {
+        const int j0 = jb + tid;
+        const int j1 = (j0 + TT <= jn) ? j0 + TT : 0;   // j = 0 reads T[0] = 0: a harmless dummy
+        int i0 = (int)(((long long)j0 * n0) % p.N), i1 = (int)(((long long)j1 * n0) % p.N);
+        double a0[HB], a1[HB];
 #pragma unroll
-      for (int h = 0; h < HB; ++h) acc[h] = 0.0;
-      for (int nn = 0; nn < nlen; ++nn) {
-        const double* g = gs + nn * HB;
+        for (int h = 0; h < HB; ++h) { a0[h] = 0.0; a1[h] = 0.0; }
+#pragma unroll 2
+        for (int nn = 0; nn < nlen; ++nn) {
+          const double s0 = T[i0], s1 = T[i1];
+          i0 += j0; if (i0 >= p.N) i0 -= p.N;
+          i1 += j1; if (i1 >= p.N) i1 -= p.N;
+          const double* g = gs + nn * HB;
 #pragma unroll
-        for (int h = 0; h < HB; ++h) acc[h] = fma(g[h], s, acc[h]);
-        const double s2 = fma(s, C, c * S);
-        c = fma(c, C, -s * S);
-        s = s2;
+          for (int h = 0; h < HB; ++h) {
+            const double gv = g[h];
+            a0[h] = fma(gv, s0, a0[h]);
+            a1[h] = fma(gv, s1, a1[h]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < HB; ++h) {
+          Us[(size_t)h * p.JS + j0] += a0[h];
+          if (j1) Us[(size_t)h * p.JS + j1] += a1[h];
+        }
       }
+      const int j0 = jb + tid;
+      if (j0 <= jn) {
+        int i0 = (int)(((long long)j0 * n0) % p.N);
+        double a0[HB];
 #pragma unroll
-      for (int h = 0; h < HB; ++h) Us[(size_t)h * p.JS + j] += acc[h];
+        for (int h = 0; h < HB; ++h) a0[h] = 0.0;
+#pragma unroll 4
+        for (int nn = 0; nn < nlen; ++nn) {
+          const double s0 = T[i0];
+          i0 += j0; if (i0 >= p.N) i0 -= p.N;
+          const double* g = gs + nn * HB;
+#pragma unroll
+          for (int h = 0; h < HB; ++h) a0[h] = fma(g[h], s0, a0[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < HB; ++h) Us[(size_t)h * p.JS + j0] += a0[h];
+      }
+    } else {
+      for (int j = tid + 1; j <= jn; j += TT) {
+        double s, c, S, C;
+        sincospi(twoN * (double)(((long long)j * n0) % p.N), &s, &c);  // exact phase of sample n0
+        sincospi(twoN * (double)j, &S, &C);
+        double acc[HB];
+#pragma unroll
+        for (int h = 0; h < HB; ++h) acc[h] = 0.0;
+        for (int nn = 0; nn < nlen; ++nn) {
+          const double* g = gs + nn * HB;
+#pragma unroll
+          for (int h = 0; h < HB; ++h) acc[h] = fma(g[h], s, acc[h]);
+          const double s2 = fma(s, C, c * S);
+          c = fma(c, C, -s * S);
+          s = s2;
+        }
+#pragma unroll
+        for (int h = 0; h < HB; ++h) Us[(size_t)h * p.JS + j] += acc[h];
+      }
     }
     __syncthreads();
   }
@@ -116,7 +184,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 #pragma unroll
   for (int h = 0; h < HB; ++h) {
     const double mn = p.do_mass_norm ? block_sum(msum[h], red) : 1.0;
-    scale[h] = p.step / mn;
+    scale[h] = p.step / mn * h_oscale[h];
   }
   for (int j = tid + 1; j <= jn; j += TT) {
     const double ikt = 1.0 / ((double)j * p.kt1);
@@ -124,59 +192,65 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     for (int h = 0; h < HB; ++h) Us[(size_t)h * p.JS + j] *= scale[h] * ikt;
   }
   __syncthreads();
+  if (tid < HB) h_u1[tid] = Us[(size_t)tid * p.JS + 1];
+  __syncthreads();
 
   // ---- interpolation onto the target ks (fft.py:102-107): hold u_1 below bin 1, zero above bin J ----
-#pragma unroll 1
-  for (int h = 0; h < HB; ++h) {
-    if (!h_valid[h]) continue;
-    const double* U = Us + (size_t)h * p.JS;
-    const double kout1 = p.kt1 / h_a[h];
-    const double inv = h_a[h] / p.kt1;
-    const double koutJ = ((double)p.J * p.kt1) / h_a[h];
-    const double osc = h_oscale[h];
-    const double u1 = U[1];
-    double* out = p.uk + ((long long)z * p.nm + m0 + h) * (long long)p.ldk;
-    for (int k = tid; k < p.nk; k += TT) {
-      const double kk = p.ks[k];
+  double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
+  for (int k = tid; k < p.nk; k += TT) {
+    const double kk = __ldg(p.ks + k);
+#pragma unroll
+    for (int h = 0; h < HB; ++h) {
+      if (!h_valid[h]) continue;
       double v;
-      if (kk < kout1) {
-        v = u1;
-      } else if (kk > koutJ) {
+      if (kk < h_k1[h]) {
+        v = h_u1[h];
+      } else if (kk > h_kJ[h]) {
         v = 0.0;
       } else {
-        const double t = kk * inv;
+        const double* U = Us + (size_t)h * p.JS;
+        const double t = kk * h_inv[h];
         int j = (int)t;
         j = max(1, min(j, p.J - 1));
-        v = fma(t - (double)j, U[j + 1] - U[j], U[j]);
+        const double u0 = U[j];
+        v = fma(t - (double)j, U[j + 1] - u0, u0);
       }
-      out[k] = v * osc;
+      out0[(long long)h * p.ldk + k] = v;
     }
   }
 }
 
-template <int HB>
-static int launch_transform(const TParams& p, cudaStream_t st) {
-  const size_t smem = ((size_t)HB * p.JS + (size_t)NCH * HB + 32) * sizeof(double);
-  cudaError_t e = cudaFuncSetAttribute(profile_transform_kernel<HB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+template <int HB, int TT, bool TABLE>
+static size_t transform_smem(int JS, int N) {
+  return ((size_t)HB * JS + (size_t)TT * HB + 32 + (TABLE ? (size_t)N : 0)) * sizeof(double);
+}
+
+template <int HB, int TT, bool TABLE>
+static int launch_transform(const TParams& p, int jlo, int jhi, int JS, cudaStream_t st) {
+  const size_t smem = transform_smem<HB, TT, TABLE>(JS, p.N);
+  cudaError_t e = cudaFuncSetAttribute(profile_transform_kernel<HB, TT, TABLE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   TParams q = p;
   q.nmg = cdiv(p.nm, HB);
-  profile_transform_kernel<HB><<<q.nz * q.nmg, TT, smem, st>>>(q);
+  q.jlo = jlo; q.jhi = jhi; q.JS = JS;
+  profile_transform_kernel<HB, TT, TABLE><<<q.nz * q.nmg, TT, smem, st>>>(q);
   return check_launch("profile_transform_kernel");
 }
 
 }  // namespace hmv
 using namespace hmv;
 
+extern "C" long long hmv_profile_transform_ws_doubles(int nxs) { return nxs > 0 ? nxs : 0; }
+
 extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                                      double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
                                      const double* alpha_d, const double* expo_d, const double* amp_d,
                                      const double* outscale_d, double gamma, double xmax, int nxs, int do_mass_norm,
-                                     double* uk_d, void* stream) {
+                                     double* ws_d, double* uk_d, void* stream) {
   HMV_REQUIRE(nz > 0 && nm > 0 && nk > 0 && ldk >= nk, "hmv_profile_transform: bad sizes");
   HMV_REQUIRE(nxs >= 4 && xmax > 0, "hmv_profile_transform: need nxs>=4 and xmax>0");
-  HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && xc_d && alpha_d && expo_d && amp_d && uk_d,
+  HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && xc_d && alpha_d && expo_d && amp_d && ws_d && uk_d,
               "hmv_profile_transform: null pointer");
   TParams p;
   p.nz = nz; p.nm = nm; p.nk = nk; p.ldk = ldk; p.N = nxs; p.J = nxs / 2; p.JS = p.J + 2;
@@ -187,15 +261,29 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.kt1 = (1.0 * (1.0 / (nxs * p.step))) * 2.0 * M_PI;  // rfftfreq(N,step)[1]*2pi          (fft.py:50)
   p.kmax = kmax;
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
-  p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0;
+  p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
   cudaStream_t st = (cudaStream_t)stream;
-  // pick the widest halo batch whose bin table fits in 200 KB of shared memory
-  const size_t budget = 200 * 1024;
-  auto need = [&](int hb) { return ((size_t)hb * p.JS + (size_t)NCH * hb + 32) * sizeof(double); };
-  if (need(8) <= budget) return launch_transform<8>(p, st);
-  if (need(4) <= budget) return launch_transform<4>(p, st);
-  if (need(2) <= budget) return launch_transform<2>(p, st);
-  if (need(1) <= budget) return launch_transform<1>(p, st);
+  const size_t budget = 220 * 1024;
+  const int J = p.J;
+  if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
+    // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
+    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, ws_d);
+    int rc = check_launch("sine_table_kernel");
+    if (rc) return rc;
+    const int jA = 254, jB = 510;
+    rc = launch_transform<8, 512, true>(p, jB, J, J + 2, st);            // heavy CTAs first
+    if (rc) return rc;
+    if (J > jA) {
+      rc = launch_transform<8, 512, true>(p, jA, jB < J ? jB : J, (jB < J ? jB : J) + 2, st);
+      if (rc) return rc;
+    }
+    return launch_transform<8, 256, true>(p, 0, jA < J ? jA : J, (jA < J ? jA : J) + 2, st);
+  }
+  // large N: rotation recurrence, widest halo batch whose bin table fits
+  if (transform_smem<8, 256, false>(J + 2, nxs) <= budget) return launch_transform<8, 256, false>(p, 0, J, J + 2, st);
+  if (transform_smem<4, 256, false>(J + 2, nxs) <= budget) return launch_transform<4, 256, false>(p, 0, J, J + 2, st);
+  if (transform_smem<2, 256, false>(J + 2, nxs) <= budget) return launch_transform<2, 256, false>(p, 0, J, J + 2, st);
+  if (transform_smem<1, 256, false>(J + 2, nxs) <= budget) return launch_transform<1, 256, false>(p, 0, J, J + 2, st);
   return fail(HMV_E_LIMIT, "hmv_profile_transform: nxs=%d needs %zu B of shared memory per halo (limit %zu)", nxs,
-              need(1), budget);
+              transform_smem<1, 256, false>(J + 2, nxs), budget);
 }

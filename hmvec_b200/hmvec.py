@@ -162,7 +162,10 @@ class HaloModel(Cosmology):
 
     # ------------------------------------------------------------------ device plumbing
     def _cube(self):
-        return torch.zeros((self._nz, self._nm, self._ldk), dtype=torch.float64, device=self.device)
+        t = torch.empty((self._nz, self._nm, self._ldk), dtype=torch.float64, device=self.device)
+        if self._ldk > self._nk:
+            t[..., self._nk:] = 0.0          # pad columns are read (and ignored) by the 16-byte loads of hmv_power
+        return t
 
     def _duffy(self):
         tag = 'mean' if self.mdef == 'mean' else 'vir'
@@ -221,11 +224,12 @@ class HaloModel(Cosmology):
 
     def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm):
         out = self._cube()
+        ws = self._empty(int(capi.lib.hmv_profile_transform_ws_doubles(int(nxs))))
         capi.check(capi.lib.hmv_profile_transform(
             self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d), capi.ptr(self._ks_d),
             float(np.max(self._ks64)), capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
             capi.ptr(expo_d), capi.ptr(amp_d), capi.ptr(oscale_d), float(gamma), float(xmax), int(nxs),
-            int(bool(mass_norm)), capi.ptr(out), capi.stream()), "hmv_profile_transform")
+            int(bool(mass_norm)), capi.ptr(ws), capi.ptr(out), capi.stream()), "hmv_profile_transform")
         return out
 
     def _gnfw(self, kind, fit9, gamma, pres_alpha, amp_const, pref, xmax, nxs):
@@ -308,9 +312,11 @@ class HaloModel(Cosmology):
             out = self._transform(rs_d, self._cs_d, one, one, 2.0 * one, one, one, -1.0, xmax, nxs, mass_norm=True)
         else:
             out = self._cube()
+            ws = self._empty(int(capi.lib.hmv_uk_nfw_ws_doubles(self._nz, self._nm)))
             capi.check(capi.lib.hmv_uk_nfw(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d),
-                                           capi.ptr(self._ks_d), capi.ptr(self._cs_d), capi.ptr(self._rvir_d),
-                                           capi.ptr(out), capi.stream()), "hmv_uk_nfw")
+                                           capi.ptr(self._ks_d), float(np.max(self._ks64)), capi.ptr(self._cs_d),
+                                           capi.ptr(self._rvir_d), capi.ptr(ws), capi.ptr(out), capi.stream()),
+                       "hmv_uk_nfw")
         self.uk_profiles[name] = out
         return self.ks, LazyCube(self.uk_profiles, name)
 

@@ -55,9 +55,12 @@ int hmv_halo_geometry(int nz, int nm, const double* zs_d, const double* ms_d, co
 int hmv_mdelta(int nz, int nm, const double* ms_d, const double* cs_d, const double* drho1_d,
                const double* drho2_d, double* m2_d, void* stream);
 
-/* ---- a4: analytic NFW u(k|M,z)  (hmvec.py:346-353) --------------------------------------------------*/
-int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, const double* cs_d,
-               const double* rvir_d, double* uk_d, void* stream);
+/* ---- a4: analytic NFW u(k|M,z)  (hmvec.py:346-353) --------------------------------------------------
+ * ws_d: workspace of hmv_uk_nfw_ws_doubles() doubles (per-halo series coefficients, see k_nfw.cu). */
+long long hmv_uk_nfw_ws_doubles(int nz, int nm);
+int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
+               double kmax /* >= max(ks): lets whole rows skip the Si/Ci pass */, const double* cs_d,
+               const double* rvir_d, double* ws_d, double* uk_d, void* stream);
 
 /* ---- a6: Battaglia GNFW per-halo shape parameters  (hmvec.py:215-249,278-316,800-802,856-860,918-927)
  * The transform kernel evaluates  rho(x) = amp * (x/xc)^gamma * (1 + (x/xc)^alpha)^(-expo)  per halo.
@@ -76,11 +79,14 @@ int hmv_gnfw_params(int kind, int nz, int nm, const double* zs_d, const double* 
  * Per halo: samples x_n=(n+1) xmax/nxs, theta-cut at cmax, trapezoid mass norm, the rFFT-equivalent sine
  * sums U_j = step sum_n x_n y_n sin(2 pi j n/N), u_j = U_j/kt_j/mnorm, kout_j = kt_j/rs/(1+z), then linear
  * interpolation onto ks (hold u_1 below the first bin, 0 above the last).  The (z,M,x) cube is never stored.
- * outscale_d may be NULL (=1).  do_mass_norm as in generic_profile_fft.  ks need not be sorted. */
+ * outscale_d may be NULL (=1).  do_mass_norm as in generic_profile_fft.  ks need not be sorted.
+ * ws_d: workspace of hmv_profile_transform_ws_doubles(nxs) doubles (one period of the sine table). */
+long long hmv_profile_transform_ws_doubles(int nxs);
 int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
-                          double kmax /* = max(ks): bounds the bins computed */, const double* rs_d, const double* cmax_d, const double* xc_d, const double* alpha_d,
-                          const double* expo_d, const double* amp_d, const double* outscale_d, double gamma,
-                          double xmax, int nxs, int do_mass_norm, double* uk_d, void* stream);
+                          double kmax /* = max(ks): bounds the bins computed */, const double* rs_d,
+                          const double* cmax_d, const double* xc_d, const double* alpha_d, const double* expo_d,
+                          const double* amp_d, const double* outscale_d, double gamma, double xmax, int nxs,
+                          int do_mass_norm, double* ws_d, double* uk_d, void* stream);
 
 /* ---- a9: HOD occupations and their mass integrals  (hmvec.py:634-731, 462-466, 936-957) -------------
  * hodp[8] = (sig_log_mstellar, alphasat, Bsat, betasat, Bcut, betacut, Msat_override or <=0, Mcut_override or <=0)

@@ -223,5 +223,5 @@ def test_errors(hm, mini):
     with pytest.raises(NotImplementedError):
         hm.HaloModel(mini.zs, mini.ks, ms=mini.ms, accuracy='low', mass_function="tinker")
     from hmvec_b200 import _capi as capi
-    assert capi.lib.hmv_uk_nfw(0, 1, 1, 16, None, None, None, None, None, None) == -1
+    assert capi.lib.hmv_uk_nfw(0, 1, 1, 16, None, None, 1.0, None, None, None, None, None) == -1
     assert "bad sizes" in capi.last_error()
