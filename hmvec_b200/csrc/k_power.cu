@@ -147,8 +147,15 @@ __global__ void __launch_bounds__(PT) power_pair_kernel(const PairArgs a) {
 
 // ---------------------------------------------------------------------------------------------------------
 // six spectra {mm, ee, me, gg, gm, ge} in one pass over (u_m, u_e); HOD satellites follow u_m, centrals u_c = 1
-//   coef rows: A1 = w1 mu^2, c1 = w1 2 NcNs/ngal^2, c2 = w1 NsNsm1/ngal^2, B1 = w1 mu Nc/ngal, B2 = w1 mu Ns/ngal,
-//              D1 = w2 mu, D2 = w2 Ns/ngal ;  zoff6[z] = {1 - C_m, bg - C_g + sum w2 Nc/ngal}
+//   coef[z][m][8]: A1 = w1 mu^2, c1 = w1 2 NcNs/ngal^2, c2 = w1 NsNsm1/ngal^2, B1 = w1 mu Nc/ngal, B2 = w1 mu Ns/ngal,
+//                  D1 = w2 mu, D2 = w2 Ns/ngal, (pad) ;  zoff6[z] = {1 - C_m, bg - C_g + sum w2 Nc/ngal}
+//
+// HBM-bound stream: a CTA owns one redshift and a 512-wide k tile and walks the whole mass axis.  One producer
+// lane issues 1-D bulk async copies (cp.async.bulk -> the TMA unit) of SIX_R rows x 4 KB from each cube plus the
+// rows' 64-byte coefficient records into a SIX_NST-deep shared-memory ring, completion tracked by mbarriers
+// (full/empty pair per stage); eight consumer warps read the ring (each thread owns two adjacent k for ALL masses, so
+// there is no cross-thread reduction) and keep 18 FP64 accumulators in registers.  Memory-level parallelism comes
+// from the ring (up to 96 KB in flight per SM), not from registers or occupancy.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const double* __restrict__ ms,
                                                               const double* __restrict__ nzm,
@@ -157,8 +164,7 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
                                                               const double* __restrict__ NcNs,
                                                               const double* __restrict__ NsNsm1,
                                                               const double* __restrict__ ngal,
-                                                              double* __restrict__ coef, long long cstride,
-                                                              double* __restrict__ zoff) {
+                                                              double* __restrict__ coef, double* __restrict__ zoff) {
   __shared__ double red[32];
   const int z = blockIdx.x;
   const double ig = 1.0 / ngal[z], ig2 = ig * ig;
@@ -168,13 +174,11 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
     const double wt = trapz_weight(ms, m, nm);
     const double w1 = wt * nzm[i], w2 = w1 * bh[i], mu = ms[m] / rho_m0;
     const double nc = Nc[i] * ig, ns = Ns[i] * ig;
-    coef[0 * cstride + i] = w1 * mu * mu;
-    coef[1 * cstride + i] = w1 * 2.0 * NcNs[i] * ig2;
-    coef[2 * cstride + i] = w1 * NsNsm1[i] * ig2;
-    coef[3 * cstride + i] = w1 * mu * nc;
-    coef[4 * cstride + i] = w1 * mu * ns;
-    coef[5 * cstride + i] = w2 * mu;
-    coef[6 * cstride + i] = w2 * ns;
+    double2* c = reinterpret_cast<double2*>(coef + i * 8);
+    c[0] = make_double2(w1 * mu * mu, w1 * 2.0 * NcNs[i] * ig2);
+    c[1] = make_double2(w1 * NsNsm1[i] * ig2, w1 * mu * nc);
+    c[2] = make_double2(w1 * mu * ns, w2 * mu);
+    c[3] = make_double2(w2 * ns, 0.0);
     cm = fma(w2, mu, cm);
     cg = fma(w2, (Nc[i] + Ns[i]) * ig, cg);
     gb = fma(w2, Nc[i] + Ns[i], gb);
@@ -187,33 +191,98 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
   }
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int SIX_K = 512, SIX_R = 4, SIX_NST = 6, SIX_CT = 256;   // k per CTA, rows per stage, stages, consumers
+constexpr int SIX_STAGE_DOUBLES = 2 * SIX_R * SIX_K + SIX_R * 8;
+constexpr size_t SIX_SMEM = (size_t)SIX_NST * SIX_STAGE_DOUBLES * sizeof(double) + 2 * SIX_NST * sizeof(unsigned long long);
+
 struct SixArgs {
   int nz, nm, nk, ldk;
   const double *um, *ue, *coef;
-  long long cstride;
   const double *zoff, *ks, *Pzk;
   double kstar;
   double *p1h, *p2h;
 };
 
-__global__ void __launch_bounds__(PT) power_six_kernel(const SixArgs a) {
-  __shared__ double part[PW][9][KT];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int z = blockIdx.y, k0 = blockIdx.x * KT + 2 * lane;
-  const bool active = k0 < a.ldk;
+__global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs a) {
+  extern __shared__ __align__(128) unsigned char six_smem[];
+  double* ring = reinterpret_cast<double*>(six_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)SIX_NST * SIX_STAGE_DOUBLES);
+  unsigned long long* empty = full + SIX_NST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.y, k0 = blockIdx.x * SIX_K;
+  const int segk = min(SIX_K, a.ldk - k0);                 // doubles per row segment (multiple of 2)
   const long long zrow = (long long)z * a.nm;
-  const double* cf = a.coef + zrow;
+  const int nit = (a.nm + SIX_R - 1) / SIX_R;
+  if (tid == 0) {
+    for (int s = 0; s < SIX_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, SIX_CT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == SIX_CT / 32) {            // ---- producer warp: one elected lane drives the TMA unit ----
+    if (lane == 0) {
+      const unsigned segb = (unsigned)segk * 8u;
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % SIX_NST;
+        const unsigned ph = (unsigned)(it / SIX_NST) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);                     // first lap passes immediately
+        const int m0 = it * SIX_R, rows = min(SIX_R, a.nm - m0);
+        double* st = ring + (size_t)s * SIX_STAGE_DOUBLES;
+        mbar_expect_tx(full + s, (unsigned)rows * (2u * segb + 64u));
+        for (int r = 0; r < rows; ++r) {
+          const long long off = (zrow + m0 + r) * (long long)a.ldk + k0;
+          bulk_g2s(st + r * SIX_K, a.um + off, segb, full + s);
+          bulk_g2s(st + (SIX_R + r) * SIX_K, a.ue + off, segb, full + s);
+        }
+        bulk_g2s(st + 2 * SIX_R * SIX_K, a.coef + (zrow + m0) * 8, (unsigned)rows * 64u, full + s);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: thread owns k = k0 + 2 tid, +1 over the whole mass axis ----
+  const bool active = 2 * tid < segk;
   double2 acc[9];
 #pragma unroll
   for (int q = 0; q < 9; ++q) acc[q] = make_double2(0.0, 0.0);
-  if (active) {
-#pragma unroll 4
-    for (int m = w; m < a.nm; m += PW) {
-      const long long off = (zrow + m) * (long long)a.ldk + k0;
-      const double2 um = ld2(a.um + off), ue = ld2(a.ue + off);
-      const double A1 = __ldg(cf + m), c1 = __ldg(cf + a.cstride + m), c2 = __ldg(cf + 2 * a.cstride + m);
-      const double B1 = __ldg(cf + 3 * a.cstride + m), B2 = __ldg(cf + 4 * a.cstride + m);
-      const double D1 = __ldg(cf + 5 * a.cstride + m), D2 = __ldg(cf + 6 * a.cstride + m);
+  for (int it = 0; it < nit; ++it) {
+    const int s = it % SIX_NST;
+    const unsigned ph = (unsigned)(it / SIX_NST) & 1u;
+    const int rows = min(SIX_R, a.nm - it * SIX_R);
+    const double* st = ring + (size_t)s * SIX_STAGE_DOUBLES;
+    mbar_wait(full + s, ph);
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < SIX_R; ++r) {
+        if (r < rows) {
+          const double2 um = *reinterpret_cast<const double2*>(st + r * SIX_K + 2 * tid);
+          const double2 ue = *reinterpret_cast<const double2*>(st + (SIX_R + r) * SIX_K + 2 * tid);
+          const double2* c = reinterpret_cast<const double2*>(st + 2 * SIX_R * SIX_K + r * 8);
+          const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+          const double A1 = c01.x, c1 = c01.y, c2 = c23.x, B1 = c23.y, B2 = c45.x, D1 = c45.y, D2 = c67.x;
 #define HMV_SIX(c)                                                          \
   {                                                                         \
     const double q1 = um.c * um.c, q2 = ue.c * ue.c, q3 = um.c * ue.c;      \
@@ -227,37 +296,36 @@ __global__ void __launch_bounds__(PT) power_six_kernel(const SixArgs a) {
     acc[7].c = fma(D1, ue.c, acc[7].c);                                     \
     acc[8].c = fma(D2, um.c, acc[8].c);                                     \
   }
-      HMV_SIX(x)
-      HMV_SIX(y)
+          HMV_SIX(x)
+          HMV_SIX(y)
 #undef HMV_SIX
+        }
+      }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);                 // this warp is done with the stage
   }
+  if (!active) return;
+  const long long S = (long long)a.nz * a.nk;
+  const double zo0 = a.zoff[2 * z], zo1 = a.zoff[2 * z + 1];
 #pragma unroll
-  for (int q = 0; q < 9; ++q) { part[w][q][2 * lane] = acc[q].x; part[w][q][2 * lane + 1] = acc[q].y; }
-  __syncthreads();
-  if (threadIdx.x < KT) {
-    const int k = blockIdx.x * KT + threadIdx.x;
-    if (k < a.nk) {
-      double s[9];
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + 2 * tid + e;
+    if (k >= a.nk) break;
+    double sv[9];
 #pragma unroll
-      for (int q = 0; q < 9; ++q) {
-        double t = 0;
+    for (int q = 0; q < 9; ++q) sv[q] = e ? acc[q].y : acc[q].x;
+    const long long o = (long long)z * a.nk + k;
+    if (a.p1h) {
+      const double r = a.ks[k] / a.kstar, damp = 1.0 - exp(-r * r);          // hmvec.py:526
 #pragma unroll
-        for (int ww = 0; ww < PW; ++ww) t += part[ww][q][threadIdx.x];
-        s[q] = t;
-      }
-      const long long o = (long long)z * a.nk + k, S = (long long)a.nz * a.nk;
-      const double r = a.ks[k] / a.kstar, damp = 1.0 - exp(-r * r);
-      if (a.p1h) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) a.p1h[q * S + o] = s[q] * damp;
-      }
-      if (a.p2h) {
-        const double P = a.Pzk[o];
-        const double Lm = s[6] + a.zoff[2 * z], Le = s[7] + a.zoff[2 * z], Lg = s[8] + a.zoff[2 * z + 1];
-        a.p2h[0 * S + o] = P * Lm * Lm; a.p2h[1 * S + o] = P * Le * Le; a.p2h[2 * S + o] = P * Lm * Le;
-        a.p2h[3 * S + o] = P * Lg * Lg; a.p2h[4 * S + o] = P * Lg * Lm; a.p2h[5 * S + o] = P * Lg * Le;
-      }
+      for (int q = 0; q < 6; ++q) a.p1h[q * S + o] = sv[q] * damp;
+    }
+    if (a.p2h) {                                                           // hmvec.py:572
+      const double P = a.Pzk[o];
+      const double Lm = sv[6] + zo0, Le = sv[7] + zo0, Lg = sv[8] + zo1;
+      a.p2h[0 * S + o] = P * Lm * Lm; a.p2h[1 * S + o] = P * Le * Le; a.p2h[2 * S + o] = P * Lm * Le;
+      a.p2h[3 * S + o] = P * Lg * Lg; a.p2h[4 * S + o] = P * Lg * Lm; a.p2h[5 * S + o] = P * Lg * Le;
     }
   }
 }
@@ -278,7 +346,7 @@ using namespace hmv;
 
 extern "C" long long hmv_power_ws_doubles(int nz, int nm) {
   if (nz <= 0 || nm <= 0) return 0;
-  return 7LL * nz * nm + 2LL * nz;
+  return 8LL * nz * nm + 2LL * nz;   // hmv_power: 7 coefficient rows; hmv_power_six: [z][m][8] records; + zoff
 }
 
 extern "C" int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d,
@@ -298,7 +366,7 @@ extern "C" int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, co
   cudaStream_t st = (cudaStream_t)stream;
   const long long cs = (long long)nz * nm;
   double* coef = ws_d;
-  double* zoff = ws_d + 7 * cs;
+  double* zoff = ws_d + 8 * cs;
   int form = 0;
   if (A->kind == 1 && B->kind == 1) form = 1;            // hmvec.py:510-511 (uses leg A's HOD only)
   power_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, ta, tb, form, coef, cs, zoff);
@@ -336,18 +404,22 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
   HMV_REQUIRE(ms_d && ks_d && nzm_d && bh_d && um_d && ue_d && Nc_d && Ns_d && NcNs_d && NsNsm1_d && ngal_d && ws_d,
               "hmv_power_six: null pointer");
   HMV_REQUIRE(p2h_d == nullptr || Pzk_d != nullptr, "hmv_power_six: P2h requested without Pzk");
+  HMV_REQUIRE((ldk & 1) == 0 && (((unsigned long long)um_d | (unsigned long long)ue_d | (unsigned long long)ws_d) & 15ull) == 0,
+              "hmv_power_six: cubes and workspace must be 16-byte aligned with even ldk (bulk async copies)");
   cudaStream_t st = (cudaStream_t)stream;
   const long long cs = (long long)nz * nm;
   double* coef = ws_d;
-  double* zoff = ws_d + 7 * cs;
+  double* zoff = ws_d + 8 * cs;
   power_six_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, Nc_d, Ns_d, NcNs_d, NsNsm1_d, ngal_d, coef,
-                                            cs, zoff);
+                                            zoff);
   int rc = check_launch("power_six_prep_kernel");
   if (rc) return rc;
   SixArgs a;
-  a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.um = um_d; a.ue = ue_d; a.coef = coef; a.cstride = cs;
+  a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.um = um_d; a.ue = ue_d; a.coef = coef;
   a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar; a.p1h = p1h_d; a.p2h = p2h_d;
-  dim3 grid(cdiv(nk, KT), nz);
-  power_six_kernel<<<grid, PT, 0, st>>>(a);
+  cudaError_t e = cudaFuncSetAttribute(power_six_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIX_SMEM);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_six_kernel smem opt-in (%zu B): %s", SIX_SMEM, cudaGetErrorString(e));
+  dim3 grid(cdiv(ldk, SIX_K), nz);
+  power_six_kernel<<<grid, SIX_CT + 32, SIX_SMEM, st>>>(a);
   return check_launch("power_six_kernel");
 }
