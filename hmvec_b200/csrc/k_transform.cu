@@ -31,12 +31,15 @@ __global__ void sine_table_kernel(int N, double* __restrict__ tab) {
   if (i < N) tab[i] = sinpi(2.0 * (double)i / (double)N);
 }
 
+constexpr int NCH = 256;   // samples evaluated per chunk
+
 template <int HB, int TT, bool TABLE>
 __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) {
+  static_assert(TT % NCH == 0 && HB % (TT / NCH) == 0, "threads must tile the (sample, halo) chunk");
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
-  double* gs = Us + (size_t)HB * p.JS;        // [TT][HB]
-  double* red = gs + TT * HB;                 // [32]
+  double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
+  double* red = gs + NCH * HB;                // [32]
   double* T = red + 32;                       // [N] (TABLE only)
   __shared__ double h_cmax[HB], h_lxc[HB], h_alpha[HB], h_expo[HB], h_amp[HB], h_a[HB], h_oscale[HB];
   __shared__ double h_k1[HB], h_kJ[HB], h_inv[HB], h_u1[HB];
@@ -89,27 +92,30 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 #pragma unroll
   for (int h = 0; h < HB; ++h) msum[h] = 0.0;
 
-  for (int n0 = 0; n0 < nb; n0 += TT) {
-    {  // ---- evaluate x*y for sample n0+tid of every halo (theta-cut: x <= cmax, fft.py:79-81) ----
-      const int n = n0 + tid;
+  for (int n0 = 0; n0 < nb; n0 += NCH) {
+    {  // ---- evaluate x*y for sample n0 + (tid % NCH) of this thread's share of the halos (theta-cut, fft.py:79-81)
+      constexpr int HPT = HB / (TT / NCH);      // halos per thread
+      const int sn = tid % NCH, hb = (tid / NCH) * HPT;
+      const int n = n0 + sn;
       const double x = (double)(n + 1) * p.dx;
       const double lx = log(x);
       const double w = (n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx;  // np.trapz weights on xs (fft.py:84)
 #pragma unroll
-      for (int h = 0; h < HB; ++h) {
+      for (int hh = 0; hh < HPT; ++hh) {
+        const int h = hb + hh;
         double v = 0.0;
         if (n < p.N && x <= h_cmax[h]) {
           const double lt = lx - h_lxc[h];
           // amp * t^gamma * (1+t^alpha)^(-expo)
           const double rho = h_amp[h] * exp(p.gamma * lt - h_expo[h] * log1p(exp(h_alpha[h] * lt)));
           v = x * rho;
-          msum[h] = fma(w * x, v, msum[h]);
+          msum[hh] = fma(w * x, v, msum[hh]);
         }
-        gs[tid * HB + h] = v;
+        gs[sn * HB + h] = v;
       }
     }
     __syncthreads();
-    const int nlen = min(TT, nb - n0);
+    const int nlen = min(NCH, nb - n0);
     if (TABLE) {
       int jb = 1;
       // two bins per thread while more than TT bins remain (they share the sample loads), then one
@@ -181,10 +187,17 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 
   // ---- mass norm (fft.py:83-87) and u_j = U_j / kt_j / mnorm (fft.py:91) ----
   double scale[HB];
+  {
+    constexpr int HPT = HB / (TT / NCH);
+    const int hb = (tid / NCH) * HPT;
 #pragma unroll
-  for (int h = 0; h < HB; ++h) {
-    const double mn = p.do_mass_norm ? block_sum(msum[h], red) : 1.0;
-    scale[h] = p.step / mn * h_oscale[h];
+    for (int h = 0; h < HB; ++h) {
+      double mine = 0.0;
+#pragma unroll
+      for (int hh = 0; hh < HPT; ++hh) mine = (hb + hh == h) ? msum[hh] : mine;
+      const double mn = p.do_mass_norm ? block_sum(mine, red) : 1.0;
+      scale[h] = p.step / mn * h_oscale[h];
+    }
   }
   for (int j = tid + 1; j <= jn; j += TT) {
     const double ikt = 1.0 / ((double)j * p.kt1);
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 
 template <int HB, int TT, bool TABLE>
 static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)TT * HB + 32 + (TABLE ? (size_t)N : 0)) * sizeof(double);
+  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)N : 0)) * sizeof(double);
 }
 
 template <int HB, int TT, bool TABLE>
@@ -263,7 +276,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t budget = 220 * 1024;
+  const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
   if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
     // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
