@@ -47,11 +47,11 @@ _SIGS = {
     "hmv_mass_function": (_i, [_i, _i, _p, _p, _d, _d, _d, _d, _d, _p, _p, _p]),
     "hmv_halo_geometry": (_i, [_i, _i, _p, _p, _p, _d, _d, _d, _d, _p, _p, _p]),
     "hmv_mdelta": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
-    "hmv_uk_nfw_ws_doubles": (_ll, [_i, _i]),
+    "hmv_uk_nfw_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_uk_nfw": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p]),
     "hmv_gnfw_params": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _d,
                              _p, _p, _p, _p, _p, _p, _p, _p]),
-    "hmv_profile_transform_ws_doubles": (_ll, [_i]),
+    "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_profile_transform": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_hod": (_i, [_i, _i, _p, _p, _p, C.POINTER(_d), _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_hod_bisect": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _p, _p, _p]),

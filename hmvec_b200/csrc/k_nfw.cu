@@ -18,7 +18,7 @@
 
 namespace hmv {
 
-constexpr int NFW_T = 256, NFW_E = 4, NFW_NMAX = 40;
+constexpr int NFW_T = 256, NFW_E = 8, NFW_NMAX = 42, NFW_CH = 32 * NFW_E;   // NMAX even: 16-byte aligned rows
 constexpr double NFW_XC_MAX = 16.0;
 
 // ---- per-halo series coefficients A[row][NFW_NMAX] ---------------------------------------------------------
@@ -59,23 +59,46 @@ __global__ void __launch_bounds__(128) nfw_coef_kernel(long long rows, const dou
   }
 }
 
+// odd term count n with y^n/(2n+1)! < 1e-19 (y = xc^2): tabulated at the low end, linear bound above
 __device__ __forceinline__ int nfw_terms(double xc) {
   const float xf = (float)xc;
-  // smallest n with y^n/(2n+1)! < 1e-19 (y = xc^2), tabulated at the low end, linear bound above
-  return xf < 0.03f ? 5 : xf < 0.3f ? 7 : xf < 1.0f ? 10 : min(NFW_NMAX, (int)(1.8f * xf + 10.5f));
+  const int n = xf < 0.03f ? 5 : xf < 0.3f ? 7 : xf < 1.0f ? 10 : min(NFW_NMAX - 1, (int)(1.8f * xf + 10.5f));
+  return n | 1;
 }
 
-// TAIL=false: the warp-uniform series chunks (lean: few registers, high occupancy).  TAIL=true: the remaining
-// chunks (any element with x c > 16), which need the Si/Ci routines -- a separate instantiation so that their
-// register footprint does not cap the occupancy of the series pass.  Both passes take the same per-chunk decision.
+// sum_{i<n} A[i] y^i for odd n, coefficients fetched as aligned pairs
+__device__ __forceinline__ double nfw_horner(const double* __restrict__ A, int n, double y) {
+  double u = A[n - 1];
+  for (int i = n - 2; i >= 1; i -= 2) {
+    const double2 a2 = *reinterpret_cast<const double2*>(A + i - 1);
+    u = fma(u, y, a2.y);
+    u = fma(u, y, a2.x);
+  }
+  return u;
+}
+
+// max of ks over each NFW_CH-wide chunk: lets both passes classify a chunk with one load
+__global__ void nfw_chunkmax_kernel(int nk, const double* __restrict__ ks, double* __restrict__ kcmax) {
+  const int chunk = blockIdx.x, lane = threadIdx.x;
+  double m = 0.0;
+  for (int k = chunk * NFW_CH + lane; k < min(nk, (chunk + 1) * NFW_CH); k += 32) m = fmax(m, ks[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) kcmax[chunk] = m;
+}
+
+// TAIL=false: chunks that lie entirely in the series regime (lean: few registers, high occupancy).  TAIL=true: the
+// remaining chunks (some element with x c > 16), which need the Si/Ci routines -- a separate instantiation so that
+// their register footprint does not cap the occupancy of the series pass.
 template <bool TAIL>
 __global__ void __launch_bounds__(NFW_T) uk_nfw_kernel(int nm, int nk, int ldk, const double* __restrict__ zs,
                                                         const double* __restrict__ ks,
                                                         const double* __restrict__ cs,
                                                         const double* __restrict__ rvir,
-                                                        const double* __restrict__ coef, double kmax,
+                                                        const double* __restrict__ coef,
+                                                        const double* __restrict__ kcmax, double kmax,
                                                         double* __restrict__ uk) {
-  __shared__ double A[NFW_NMAX];
+  __shared__ __align__(16) double A[NFW_NMAX];
   const long long row = blockIdx.x;                   // row = z*nm + m
   const int z = (int)(row / nm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -85,55 +108,47 @@ __global__ void __launch_bounds__(NFW_T) uk_nfw_kernel(int nm, int nk, int ldk, 
   if (TAIL) {   // rows whose whole k-range is in the series regime have nothing to do here
     if (kmax * ac <= NFW_XC_MAX) return;
   }
-  const double ln1pc = log1p(c);
-  const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
   if (threadIdx.x < NFW_NMAX) A[threadIdx.x] = coef[row * NFW_NMAX + threadIdx.x];
   __syncthreads();
   double* out = uk + row * (long long)ldk;
-  const int nchunks = (nk + 32 * NFW_E - 1) / (32 * NFW_E);
+  const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
   for (int chunk = warp; chunk < nchunks; chunk += NFW_T / 32) {
-    const int kbase = chunk * (32 * NFW_E) + lane;
-    double kk[NFW_E], y[NFW_E], u[NFW_E];
-    int nt = 0;
-    bool ser = true;
-#pragma unroll
-    for (int e = 0; e < NFW_E; ++e) {
-      const int k = min(kbase + 32 * e, nk - 1);
-      kk[e] = __ldg(ks + k);
-      const double xc = kk[e] * ac;
-      y[e] = xc * xc;
-      nt = max(nt, nfw_terms(xc));
-      ser = ser && (xc <= NFW_XC_MAX);
-    }
-    const bool all_ser = __all_sync(0xffffffffu, ser);
-    if (all_ser == TAIL) continue;
+    const double xcm = __ldg(kcmax + chunk) * ac;
+    if ((xcm <= NFW_XC_MAX) == TAIL) continue;
+    const int kbase = chunk * NFW_CH + lane;
     if (!TAIL) {
-      nt = __reduce_max_sync(0xffffffffu, nt);        // warp-uniform trip count
+      const int nt = nfw_terms(xcm);                  // warp-uniform trip count
+      double y[NFW_E], u[NFW_E];
+#pragma unroll
+      for (int e = 0; e < NFW_E; ++e) {
+        const double xc = __ldg(ks + min(kbase + 32 * e, nk - 1)) * ac;
+        y[e] = xc * xc;
+      }
       const double top = A[nt - 1];
 #pragma unroll
       for (int e = 0; e < NFW_E; ++e) u[e] = top;
-      for (int i = nt - 2; i >= 0; --i) {
-        const double ai = A[i];
+      for (int i = nt - 2; i >= 1; i -= 2) {
+        const double2 a2 = *reinterpret_cast<const double2*>(A + i - 1);
 #pragma unroll
-        for (int e = 0; e < NFW_E; ++e) u[e] = fma(u[e], y[e], ai);
+        for (int e = 0; e < NFW_E; ++e) u[e] = fma(u[e], y[e], a2.y);
+#pragma unroll
+        for (int e = 0; e < NFW_E; ++e) u[e] = fma(u[e], y[e], a2.x);
       }
-    } else {
 #pragma unroll
       for (int e = 0; e < NFW_E; ++e) {
-        if (y[e] <= NFW_XC_MAX * NFW_XC_MAX) {
-          const int n = nfw_terms(kk[e] * ac);
-          double v = A[n - 1];
-          for (int i = n - 2; i >= 0; --i) v = fma(v, y[e], A[i]);
-          u[e] = v;
-        } else {
-          u[e] = nfw_bracket(kk[e] * a, c, ln1pc) * inv_mc;
-        }
+        const int k = kbase + 32 * e;
+        if (k < nk) out[k] = u[e];
       }
-    }
-#pragma unroll
-    for (int e = 0; e < NFW_E; ++e) {
-      const int k = kbase + 32 * e;
-      if (k < nk) out[k] = u[e];
+    } else {
+      const double ln1pc = log1p(c);
+      const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
+#pragma unroll 1
+      for (int e = 0; e < NFW_E; ++e) {
+        const int k = kbase + 32 * e;
+        if (k >= nk) break;
+        const double kk = __ldg(ks + k), xc = kk * ac;
+        out[k] = (xc <= NFW_XC_MAX) ? nfw_horner(A, nfw_terms(xc), xc * xc) : nfw_bracket(kk * a, c, ln1pc) * inv_mc;
+      }
     }
   }
 }
@@ -147,9 +162,9 @@ __global__ void sici_test_kernel(int n, const double* __restrict__ x, double* __
 }  // namespace hmv
 using namespace hmv;
 
-extern "C" long long hmv_uk_nfw_ws_doubles(int nz, int nm) {
-  if (nz <= 0 || nm <= 0) return 0;
-  return (long long)nz * nm * NFW_NMAX;
+extern "C" long long hmv_uk_nfw_ws_doubles(int nz, int nm, int nk) {
+  if (nz <= 0 || nm <= 0 || nk <= 0) return 0;
+  return (long long)nz * nm * NFW_NMAX + (nk + NFW_CH - 1) / NFW_CH;   // series coefficients + per-chunk max(k)
 }
 
 extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
@@ -163,10 +178,14 @@ extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, c
   nfw_coef_kernel<<<cdiv(rows, 128), 128, 0, st>>>(rows, cs_d, ws_d);
   int rc = check_launch("nfw_coef_kernel");
   if (rc) return rc;
-  uk_nfw_kernel<false><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kmax, uk_d);
+  double* kcmax = ws_d + rows * NFW_NMAX;
+  nfw_chunkmax_kernel<<<(nk + NFW_CH - 1) / NFW_CH, 32, 0, st>>>(nk, ks_d, kcmax);
+  rc = check_launch("nfw_chunkmax_kernel");
+  if (rc) return rc;
+  uk_nfw_kernel<false><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kcmax, kmax, uk_d);
   rc = check_launch("uk_nfw_kernel<series>");
   if (rc) return rc;
-  uk_nfw_kernel<true><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kmax, uk_d);
+  uk_nfw_kernel<true><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kcmax, kmax, uk_d);
   return check_launch("uk_nfw_kernel<tail>");
 }
 

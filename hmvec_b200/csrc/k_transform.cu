@@ -23,17 +23,84 @@ struct TParams {
   int nz, nm, nk, ldk, N, J, JS, nmg, do_mass_norm, jlo, jhi;
   double gamma, dx, step, kt1, kmax;
   const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab;
+  const int* jn_cta;
   double* uk;
 };
 
+// Table slot of phase index m.  Lanes hold consecutive bins j, so at sample n they read indices (j n) mod N -- an
+// arithmetic progression of stride n.  Skewing by m/16 + m/256 turns the even strides (2..256-fold bank conflicts
+// on 8-byte words) into conflict-free ones.
+__device__ __forceinline__ int skew(int m) { return m + (m >> 4) + (m >> 8); }
+static inline int skew_host(int m) { return m + (m >> 4) + (m >> 8); }
+
 __global__ void sine_table_kernel(int N, double* __restrict__ tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) tab[i] = sinpi(2.0 * (double)i / (double)N);
+  if (i < N) tab[skew(i)] = sinpi(2.0 * (double)i / (double)N);
+}
+
+// bins needed by each CTA (group of HB halos): jn = floor(kmax * max_h(rs (1+z)) / kt_1) + 2, capped at N/2
+__global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double kmax, double kt1,
+                                 const double* __restrict__ zs, const double* __restrict__ rs,
+                                 int* __restrict__ jn_cta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nz * nmg) return;
+  const int z = b / nmg, mg = nmg - 1 - (b - z * nmg);
+  double amax = 0.0;
+  for (int h = 0; h < HB; ++h) {
+    const int m = mg * HB + h;
+    if (m < nm) amax = fmax(amax, rs[(long long)z * nm + m] * (1.0 + zs[z]));
+  }
+  jn_cta[b] = (int)fmin((double)J, floor(kmax * amax / kt1) + 2.0);
+}
+
+// U[h][j] += sum_nn gs[nn][h] * T[(j (n0+nn)) mod N] for NJ bins per thread and HPT halos starting at h0; the next
+// sample's table values are fetched before the current FMAs (software prefetch hides the LDS latency).
+template <int HB, int HPT, int NJ>
+__device__ __forceinline__ void accum_table(const double* __restrict__ T, const double* __restrict__ gs,
+                                            double* __restrict__ Us, int JS, int N, int n0, int nlen, int jfirst,
+                                            int jstride, int jn, int h0) {
+  int j[NJ], idx[NJ];
+  double a[NJ][HPT], s[NJ];
+#pragma unroll
+  for (int q = 0; q < NJ; ++q) {
+    const int jj = jfirst + q * jstride;
+    j[q] = (jj <= jn) ? jj : 0;                  // bin 0 reads T[0] = 0: a harmless dummy
+    idx[q] = (int)(((unsigned)j[q] * (unsigned)n0) % (unsigned)N);   // j*n0 < 2^31 (checked on the host)
+    s[q] = T[skew(idx[q])];
+#pragma unroll
+    for (int h = 0; h < HPT; ++h) a[q][h] = 0.0;
+  }
+#pragma unroll 2
+  for (int nn = 0; nn < nlen; ++nn) {
+    double sn[NJ];
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) {
+      idx[q] += j[q];
+      if (idx[q] >= N) idx[q] -= N;
+      sn[q] = T[skew(idx[q])];
+    }
+    const double* g = gs + nn * HB + h0;
+#pragma unroll
+    for (int h = 0; h < HPT; ++h) {
+      const double gv = g[h];
+#pragma unroll
+      for (int q = 0; q < NJ; ++q) a[q][h] = fma(gv, s[q], a[q][h]);
+    }
+#pragma unroll
+    for (int q = 0; q < NJ; ++q) s[q] = sn[q];
+  }
+#pragma unroll
+  for (int q = 0; q < NJ; ++q) {
+    if (j[q]) {
+#pragma unroll
+      for (int h = 0; h < HPT; ++h) Us[(size_t)(h0 + h) * JS + j[q]] += a[q][h];
+    }
+  }
 }
 
 constexpr int NCH = 256;   // samples evaluated per chunk
 
-template <int HB, int TT, bool TABLE>
+template <int HB, int TT, bool TABLE, int MAXNJ>
 __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) {
   static_assert(TT % NCH == 0 && HB % (TT / NCH) == 0, "threads must tile the (sample, halo) chunk");
   extern __shared__ double smem[];
@@ -46,6 +113,8 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
   __shared__ int h_valid[HB];
 
   const int tid = threadIdx.x;
+  const int jn = p.jn_cta[blockIdx.x];
+  if (jn <= p.jlo || jn > p.jhi) return;      // not this launch's bin-count class (uniform over the CTA)
   const int z = blockIdx.x / p.nmg;
   const int mg = p.nmg - 1 - (blockIdx.x - z * p.nmg);  // heavy (large-M, many-bin) groups are scheduled first
   const int m0 = mg * HB;
@@ -71,18 +140,15 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
   __syncthreads();
 
   // sample and bin bounds shared by the HB halos of this CTA
-  double cmx = -1.0, amax = 0.0;
+  double cmx = -1.0;
 #pragma unroll
-  for (int h = 0; h < HB; ++h) {
-    cmx = fmax(cmx, h_cmax[h]);
-    if (h_valid[h]) amax = fmax(amax, h_a[h]);
-  }
+  for (int h = 0; h < HB; ++h) cmx = fmax(cmx, h_cmax[h]);
   const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
-  const int jn = (int)fmin((double)p.J, floor(p.kmax * amax / p.kt1) + 2.0);
-  if (jn <= p.jlo || jn > p.jhi) return;      // not this launch's bin-count class (uniform over the CTA)
 
-  if (TABLE)
-    for (int i = tid; i < p.N; i += TT) T[i] = __ldg(p.sintab + i);
+  if constexpr (TABLE) {
+    const int nsk = skew(p.N - 1) + 1;
+    for (int i = tid; i < nsk; i += TT) T[i] = __ldg(p.sintab + i);
+  }
   for (int h = 0; h < HB; ++h)
     for (int j = tid; j <= jn + 1; j += TT) Us[(size_t)h * p.JS + j] = 0.0;
   __syncthreads();
@@ -116,51 +182,26 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     }
     __syncthreads();
     const int nlen = min(NCH, nb - n0);
-    if (TABLE) {
+    if constexpr (TABLE) {
       int jb = 1;
-      // two bins per thread while more than TT bins remain (they share the sample loads), then one
-      for (; jn - jb + 1 > TT; jb += 2 * TT) {
-        const int j0 = jb + tid;
-        const int j1 = (j0 + TT <= jn) ? j0 + TT : 0;   // j = 0 reads T[0] = 0: a harmless dummy
-        int i0 = (int)(((long long)j0 * n0) % p.N), i1 = (int)(((long long)j1 * n0) % p.N);
-        double a0[HB], a1[HB];
-#pragma unroll
-        for (int h = 0; h < HB; ++h) { a0[h] = 0.0; a1[h] = 0.0; }
-#pragma unroll 2
-        for (int nn = 0; nn < nlen; ++nn) {
-          const double s0 = T[i0], s1 = T[i1];
-          i0 += j0; if (i0 >= p.N) i0 -= p.N;
-          i1 += j1; if (i1 >= p.N) i1 -= p.N;
-          const double* g = gs + nn * HB;
-#pragma unroll
-          for (int h = 0; h < HB; ++h) {
-            const double gv = g[h];
-            a0[h] = fma(gv, s0, a0[h]);
-            a1[h] = fma(gv, s1, a1[h]);
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < HB; ++h) {
-          Us[(size_t)h * p.JS + j0] += a0[h];
-          if (j1) Us[(size_t)h * p.JS + j1] += a1[h];
-        }
+      if constexpr (MAXNJ >= 4) {
+        for (; jn - jb + 1 > 2 * TT; jb += 4 * TT)   // four bins per thread while more than 2 TT bins remain
+          accum_table<HB, HB, 4>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
       }
-      const int j0 = jb + tid;
-      if (j0 <= jn) {
-        int i0 = (int)(((long long)j0 * n0) % p.N);
-        double a0[HB];
-#pragma unroll
-        for (int h = 0; h < HB; ++h) a0[h] = 0.0;
-#pragma unroll 4
-        for (int nn = 0; nn < nlen; ++nn) {
-          const double s0 = T[i0];
-          i0 += j0; if (i0 >= p.N) i0 -= p.N;
-          const double* g = gs + nn * HB;
-#pragma unroll
-          for (int h = 0; h < HB; ++h) a0[h] = fma(g[h], s0, a0[h]);
-        }
-#pragma unroll
-        for (int h = 0; h < HB; ++h) Us[(size_t)h * p.JS + j0] += a0[h];
+      const int rem = jn - jb + 1;
+      if (MAXNJ >= 2 && rem > TT) {
+        if constexpr (MAXNJ >= 2) accum_table<HB, HB, 2>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
+      } else if (rem > TT / 2 || HB < 8) {
+        if (jb + tid <= jn) accum_table<HB, HB, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
+      } else if (rem > TT / 4) {                       // few bins left: split the halos over the idle threads
+        const int part = tid / (TT / 2), jl = tid % (TT / 2);
+        if (jb + jl <= jn) accum_table<HB, HB / 2, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 2));
+      } else if (rem > TT / 8) {
+        const int part = tid / (TT / 4), jl = tid % (TT / 4);
+        if (jb + jl <= jn) accum_table<HB, HB / 4, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 4));
+      } else if (rem > 0) {
+        const int part = tid / (TT / 8), jl = tid % (TT / 8);
+        if (jb + jl <= jn) accum_table<HB, HB / 8, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 8));
       }
     } else {
       for (int j = tid + 1; j <= jn; j += TT) {
@@ -209,52 +250,66 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
   __syncthreads();
 
   // ---- interpolation onto the target ks (fft.py:102-107): hold u_1 below bin 1, zero above bin J ----
+  // t = k / kout_1 is the fractional bin index: t < 1 -> u_1 (np.interp's left=), t > J -> 0 (right=), else the
+  // two neighbouring bins.  Per-halo constants live in registers; the only shared-memory traffic is U[j], U[j+1].
+  double inv[HB], u1[HB];
+#pragma unroll
+  for (int h = 0; h < HB; ++h) { inv[h] = h_inv[h]; u1[h] = h_u1[h]; }
+  const int nvalid = min(HB, p.nm - m0);
+  const double tJ = (double)p.J;
   double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
   for (int k = tid; k < p.nk; k += TT) {
     const double kk = __ldg(p.ks + k);
+    double* o = out0 + k;
 #pragma unroll
     for (int h = 0; h < HB; ++h) {
-      if (!h_valid[h]) continue;
-      double v;
-      if (kk < h_k1[h]) {
-        v = h_u1[h];
-      } else if (kk > h_kJ[h]) {
-        v = 0.0;
-      } else {
-        const double* U = Us + (size_t)h * p.JS;
-        const double t = kk * h_inv[h];
-        int j = (int)t;
-        j = max(1, min(j, p.J - 1));
-        const double u0 = U[j];
-        v = fma(t - (double)j, U[j + 1] - u0, u0);
+      if (h < nvalid) {
+        const double t = kk * inv[h];
+        double v = u1[h];
+        if (t >= 1.0) {
+          if (t > tJ) {
+            v = 0.0;
+          } else {
+            const double* U = Us + (size_t)h * p.JS;
+            const int j = min((int)t, p.J - 1);
+            const double u0 = U[j];
+            v = fma(t - (double)j, U[j + 1] - u0, u0);
+          }
+        }
+        o[(long long)h * p.ldk] = v;
       }
-      out0[(long long)h * p.ldk + k] = v;
     }
   }
 }
 
 template <int HB, int TT, bool TABLE>
 static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)N : 0)) * sizeof(double);
+  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)skew_host(N - 1) + 1 : 0)) * sizeof(double);
 }
 
-template <int HB, int TT, bool TABLE>
+template <int HB, int TT, bool TABLE, int MAXNJ>
 static int launch_transform(const TParams& p, int jlo, int jhi, int JS, cudaStream_t st) {
   const size_t smem = transform_smem<HB, TT, TABLE>(JS, p.N);
-  cudaError_t e = cudaFuncSetAttribute(profile_transform_kernel<HB, TT, TABLE>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = profile_transform_kernel<HB, TT, TABLE, MAXNJ>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   TParams q = p;
   q.nmg = cdiv(p.nm, HB);
   q.jlo = jlo; q.jhi = jhi; q.JS = JS;
-  profile_transform_kernel<HB, TT, TABLE><<<q.nz * q.nmg, TT, smem, st>>>(q);
+  kern<<<q.nz * q.nmg, TT, smem, st>>>(q);
   return check_launch("profile_transform_kernel");
 }
 
 }  // namespace hmv
 using namespace hmv;
 
-extern "C" long long hmv_profile_transform_ws_doubles(int nxs) { return nxs > 0 ? nxs : 0; }
+extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
+  if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
+  // skewed one-period sine table + one int per CTA (bin counts; a CTA holds at least one halo)
+  return (long long)skew_host(nxs - 1) + 2 + ((long long)nz * nm + 1) / 2 + 2;
+}
 
 extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                                      double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
@@ -263,6 +318,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
                                      double* ws_d, double* uk_d, void* stream) {
   HMV_REQUIRE(nz > 0 && nm > 0 && nk > 0 && ldk >= nk, "hmv_profile_transform: bad sizes");
   HMV_REQUIRE(nxs >= 4 && xmax > 0, "hmv_profile_transform: need nxs>=4 and xmax>0");
+  HMV_REQUIRE((long long)nxs * (nxs / 2) < 2147483647LL, "hmv_profile_transform: nxs=%d too large (phase index overflow)", nxs);
   HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && xc_d && alpha_d && expo_d && amp_d && ws_d && uk_d,
               "hmv_profile_transform: null pointer");
   TParams p;
@@ -275,7 +331,14 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.kmax = kmax;
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
+  int* jn_cta = reinterpret_cast<int*>(ws_d + ((skew_host(nxs - 1) + 2 + 1) & ~1));
+  p.jn_cta = jn_cta;
   cudaStream_t st = (cudaStream_t)stream;
+  auto bin_counts = [&](int HB) {
+    const int nmg = cdiv(nm, HB);
+    bin_count_kernel<<<cdiv((long long)nz * nmg, 256), 256, 0, st>>>(nz, nm, nmg, HB, p.J, kmax, p.kt1, zs_d, rs_d, jn_cta);
+    return check_launch("bin_count_kernel");
+  };
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
   if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
@@ -283,20 +346,25 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
     sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, ws_d);
     int rc = check_launch("sine_table_kernel");
     if (rc) return rc;
+    rc = bin_counts(8);
+    if (rc) return rc;
     const int jA = 254, jB = 510;
-    rc = launch_transform<8, 512, true>(p, jB, J, J + 2, st);            // heavy CTAs first
+    rc = launch_transform<8, 512, true, 4>(p, jB, J, J + 2, st);            // heavy CTAs first
     if (rc) return rc;
     if (J > jA) {
-      rc = launch_transform<8, 512, true>(p, jA, jB < J ? jB : J, (jB < J ? jB : J) + 2, st);
+      rc = launch_transform<8, 256, true, 2>(p, jA, jB < J ? jB : J, (jB < J ? jB : J) + 2, st);
       if (rc) return rc;
     }
-    return launch_transform<8, 256, true>(p, 0, jA < J ? jA : J, (jA < J ? jA : J) + 2, st);
+    return launch_transform<8, 256, true, 1>(p, 0, jA < J ? jA : J, (jA < J ? jA : J) + 2, st);
   }
   // large N: rotation recurrence, widest halo batch whose bin table fits
-  if (transform_smem<8, 256, false>(J + 2, nxs) <= budget) return launch_transform<8, 256, false>(p, 0, J, J + 2, st);
-  if (transform_smem<4, 256, false>(J + 2, nxs) <= budget) return launch_transform<4, 256, false>(p, 0, J, J + 2, st);
-  if (transform_smem<2, 256, false>(J + 2, nxs) <= budget) return launch_transform<2, 256, false>(p, 0, J, J + 2, st);
-  if (transform_smem<1, 256, false>(J + 2, nxs) <= budget) return launch_transform<1, 256, false>(p, 0, J, J + 2, st);
+#define HMV_ROT(HBV)                                                                   \
+  if (transform_smem<HBV, 256, false>(J + 2, nxs) <= budget) {                         \
+    const int rc = bin_counts(HBV);                                                    \
+    return rc ? rc : launch_transform<HBV, 256, false, 1>(p, 0, J, J + 2, st);            \
+  }
+  HMV_ROT(8) HMV_ROT(4) HMV_ROT(2) HMV_ROT(1)
+#undef HMV_ROT
   return fail(HMV_E_LIMIT, "hmv_profile_transform: nxs=%d needs %zu B of shared memory per halo (limit %zu)", nxs,
               transform_smem<1, 256, false>(J + 2, nxs), budget);
 }

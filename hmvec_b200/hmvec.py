@@ -224,7 +224,7 @@ class HaloModel(Cosmology):
 
     def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm):
         out = self._cube()
-        ws = self._empty(int(capi.lib.hmv_profile_transform_ws_doubles(int(nxs))))
+        ws = self._empty(int(capi.lib.hmv_profile_transform_ws_doubles(self._nz, self._nm, int(nxs))))
         capi.check(capi.lib.hmv_profile_transform(
             self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d), capi.ptr(self._ks_d),
             float(np.max(self._ks64)), capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
@@ -312,7 +312,7 @@ class HaloModel(Cosmology):
             out = self._transform(rs_d, self._cs_d, one, one, 2.0 * one, one, one, -1.0, xmax, nxs, mass_norm=True)
         else:
             out = self._cube()
-            ws = self._empty(int(capi.lib.hmv_uk_nfw_ws_doubles(self._nz, self._nm)))
+            ws = self._empty(int(capi.lib.hmv_uk_nfw_ws_doubles(self._nz, self._nm, self._nk)))
             capi.check(capi.lib.hmv_uk_nfw(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d),
                                            capi.ptr(self._ks_d), float(np.max(self._ks64)), capi.ptr(self._cs_d),
                                            capi.ptr(self._rvir_d), capi.ptr(ws), capi.ptr(out), capi.stream()),

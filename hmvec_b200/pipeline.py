@@ -119,8 +119,8 @@ class GridSix(object):
             self.d[k] = E(nz, nm)
         self.d["ngal"], self.d["bg"], self.d["l10"] = E(nz), E(nz), E(nz)
         self.d["sig_ws"] = E(int(capi.lib.hmv_sigma2_ws_doubles(nz, nm, self.nks)))
-        self.d["nfw_ws"] = E(int(capi.lib.hmv_uk_nfw_ws_doubles(nz, nm)))
-        self.d["tr_ws"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(self.nxs)))
+        self.d["nfw_ws"] = E(int(capi.lib.hmv_uk_nfw_ws_doubles(nz, nm, nk)))
+        self.d["tr_ws"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(nz, nm, self.nxs)))
         self.d["pow_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
         self.d["bis_ws"] = E(nz * (capi.HMV_BISECT_MAXIT + 2))
         self.mask = torch.empty(1, dtype=torch.int64, device=self.device)
@@ -192,7 +192,7 @@ class GridSix(object):
         self._mark(2)
         capi.check(L.hmv_uk_nfw(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["cs"]), ptr(d["rvir"]),
                                 ptr(d["nfw_ws"]), ptr(self.um), st), "hmv_uk_nfw")
-        n += 3
+        n += 4
         self._mark(3)
         capi.check(L.hmv_mdelta(nz, nm, ptr(d["ms"]), ptr(d["cs"]), ptr(d["drho1"]), ptr(d["drho2"]), ptr(d["m200c"]),
                                 st), "hmv_mdelta")
@@ -204,7 +204,7 @@ class GridSix(object):
                                            ptr(d["cmax"]), ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]),
                                            ptr(d["oscale"]), self.gamma, self.xmax, self.nxs, 1, ptr(d["tr_ws"]),
                                            ptr(self.ue), st), "hmv_profile_transform")
-        n += 6
+        n += 7
         self._mark(4)
         capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]), self.hodp,
                                     float(p['hod_bisection_search_min_log10mthresh']),

@@ -57,7 +57,7 @@ int hmv_mdelta(int nz, int nm, const double* ms_d, const double* cs_d, const dou
 
 /* ---- a4: analytic NFW u(k|M,z)  (hmvec.py:346-353) --------------------------------------------------
  * ws_d: workspace of hmv_uk_nfw_ws_doubles() doubles (per-halo series coefficients, see k_nfw.cu). */
-long long hmv_uk_nfw_ws_doubles(int nz, int nm);
+long long hmv_uk_nfw_ws_doubles(int nz, int nm, int nk);
 int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                double kmax /* >= max(ks): lets whole rows skip the Si/Ci pass */, const double* cs_d,
                const double* rvir_d, double* ws_d, double* uk_d, void* stream);
@@ -80,8 +80,8 @@ int hmv_gnfw_params(int kind, int nz, int nm, const double* zs_d, const double* 
  * sums U_j = step sum_n x_n y_n sin(2 pi j n/N), u_j = U_j/kt_j/mnorm, kout_j = kt_j/rs/(1+z), then linear
  * interpolation onto ks (hold u_1 below the first bin, 0 above the last).  The (z,M,x) cube is never stored.
  * outscale_d may be NULL (=1).  do_mass_norm as in generic_profile_fft.  ks need not be sorted.
- * ws_d: workspace of hmv_profile_transform_ws_doubles(nxs) doubles (one period of the sine table). */
-long long hmv_profile_transform_ws_doubles(int nxs);
+ * ws_d: workspace of hmv_profile_transform_ws_doubles(nz,nm,nxs) doubles (sine table + per-CTA bin counts). */
+long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs);
 int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                           double kmax /* = max(ks): bounds the bins computed */, const double* rs_d,
                           const double* cmax_d, const double* xc_d, const double* alpha_d, const double* expo_d,
