@@ -46,15 +46,25 @@ __global__ void __launch_bounds__(128) nfw_coef_kernel(long long rows, const dou
       A[n] = pref * sf * ko;
     }
   } else {
+    // Gauss-Legendre: node-major so that s^(2n+1) is a running product (no pow), one accumulator per moment
+    double acc[NFW_NMAX];
+#pragma unroll
+    for (int n = 0; n < NFW_NMAX; ++n) acc[n] = 0.0;
+    for (int q = 0; q < 64; ++q) {
+      const double s = c_gl64_s[q], d = 1.0 + c * s, s2 = s * s;
+      const double base = c_gl64_w[q] / (d * d);
+      double pw = s;
+#pragma unroll
+      for (int n = 0; n < NFW_NMAX; ++n) {
+        acc[n] = fma(base, pw, acc[n]);
+        pw *= s2;
+      }
+    }
     double sf = 1.0;
+#pragma unroll
     for (int n = 0; n < NFW_NMAX; ++n) {
       if (n > 0) sf = -sf / ((double)(2 * n) * (double)(2 * n + 1));
-      double acc = 0.0;
-      for (int q = 0; q < 64; ++q) {
-        const double s = c_gl64_s[q], d = 1.0 + c * s;
-        acc = fma(c_gl64_w[q] / (d * d), pow(s, (double)(2 * n + 1)), acc);
-      }
-      A[n] = pref * sf * acc;
+      A[n] = pref * sf * acc[n];
     }
   }
 }
@@ -91,7 +101,7 @@ __global__ void nfw_chunkmax_kernel(int nk, const double* __restrict__ ks, doubl
 // remaining chunks (some element with x c > 16), which need the Si/Ci routines -- a separate instantiation so that
 // their register footprint does not cap the occupancy of the series pass.
 template <bool TAIL>
-__global__ void __launch_bounds__(NFW_T) uk_nfw_kernel(int nm, int nk, int ldk, const double* __restrict__ zs,
+__global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nm, int nk, int ldk, const double* __restrict__ zs,
                                                         const double* __restrict__ ks,
                                                         const double* __restrict__ cs,
                                                         const double* __restrict__ rvir,
@@ -112,11 +122,11 @@ __global__ void __launch_bounds__(NFW_T) uk_nfw_kernel(int nm, int nk, int ldk, 
   __syncthreads();
   double* out = uk + row * (long long)ldk;
   const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
-  for (int chunk = warp; chunk < nchunks; chunk += NFW_T / 32) {
-    const double xcm = __ldg(kcmax + chunk) * ac;
-    if ((xcm <= NFW_XC_MAX) == TAIL) continue;
-    const int kbase = chunk * NFW_CH + lane;
-    if (!TAIL) {
+  if (!TAIL) {
+    for (int chunk = warp; chunk < nchunks; chunk += NFW_T / 32) {
+      const double xcm = __ldg(kcmax + chunk) * ac;
+      if (xcm > NFW_XC_MAX) continue;                 // left to the tail pass
+      const int kbase = chunk * NFW_CH + lane;
       const int nt = nfw_terms(xcm);                  // warp-uniform trip count
       double y[NFW_E], u[NFW_E];
 #pragma unroll
@@ -139,16 +149,19 @@ __global__ void __launch_bounds__(NFW_T) uk_nfw_kernel(int nm, int nk, int ldk, 
         const int k = kbase + 32 * e;
         if (k < nk) out[k] = u[e];
       }
-    } else {
-      const double ln1pc = log1p(c);
-      const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
-#pragma unroll 1
-      for (int e = 0; e < NFW_E; ++e) {
-        const int k = kbase + 32 * e;
-        if (k >= nk) break;
-        const double kk = __ldg(ks + k), xc = kk * ac;
-        out[k] = (xc <= NFW_XC_MAX) ? nfw_horner(A, nfw_terms(xc), xc * xc) : nfw_bracket(kk * a, c, ln1pc) * inv_mc;
-      }
+    }
+  } else {
+    // every warp visits every tail chunk and takes its own 32-wide slice of it: the Si/Ci work of a row is spread
+    // evenly over the CTA's warps however few chunks are in the tail
+    static_assert(NFW_T / 32 == NFW_E, "one slice per warp");
+    const double ln1pc = log1p(c);
+    const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+      if (__ldg(kcmax + chunk) * ac <= NFW_XC_MAX) continue;
+      const int k = chunk * NFW_CH + 32 * warp + lane;
+      if (k >= nk) continue;
+      const double kk = __ldg(ks + k), xc = kk * ac;
+      out[k] = (xc <= NFW_XC_MAX) ? nfw_horner(A, nfw_terms(xc), xc * xc) : nfw_bracket(kk * a, c, ln1pc) * inv_mc;
     }
   }
 }
