@@ -1,0 +1,138 @@
+"""GridSix (the allocation-free launch sequence bench.py times) against the golden vectors and the drop-in HaloModel,
+plus the z-sharded path: emulated on one GPU with a stand-in communicator, and for real over NCCL when the box has
+two or more GPUs.  Tolerance rtol 1e-6 (FP64)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def setup(golden_mini):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    from hmvec_b200 import pipeline
+    g = golden_mini
+    inp = pipeline.make_inputs(g["zs"], g["ms"], g["ks"], ngal=g["g2_ngal_target"], ells=g["ells"])
+    return g, inp, pipeline
+
+
+def _run(pipeline, inp, **kw):
+    import torch
+    gs = pipeline.GridSix(inp, **kw)
+    gs.upload()
+    gs.run()
+    out = gs.spectra()
+    torch.cuda.synchronize()
+    return gs, out
+
+
+def test_gridsix_matches_golden_and_halomodel(setup):
+    g, inp, pipeline = setup
+    gs, (p1, p2, ckk, ckg) = _run(pipeline, inp)
+    for tag, gold in (("mm", "mm"), ("ee", "ee"), ("me", "me"), ("gg", "g2g2"), ("ge", "g2e")):
+        assert_close(p1[tag], g["P1h_" + gold], 1e-6, name="P1h_" + tag)
+        assert_close(p2[tag], g["P2h_" + gold], 1e-6, name="P2h_" + tag)
+    assert_close(ckk, g["C_kk"], 1e-6, name="C_kk")
+    assert int(gs.iters.item()) > 1
+    import hmvec_b200 as hm
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    h.add_hod("g2", ngal=g["g2_ngal_target"])
+    assert_close(p1["gm"], h.get_power_1halo("g2", "nfw"), 1e-9, name="P1h_gm")
+    assert_close(p2["gm"], h.get_power_2halo("g2", "nfw"), 1e-9, name="P2h_gm")
+    assert_close(ckg, h.C_kg(g["ells"], g["zs"], g["ks"], p1["gm"] + p2["gm"], gzs=0.8, lzs=2.5), 1e-9, name="C_kg")
+    assert gs.launches_per_run >= 20
+
+
+class _StandInComm(object):
+    """Plays the other rank of a 2-way z split on a single GPU: AND with the other slab's pass mask, all-gather by
+    concatenating the other slab's stored spectra (slab order given by `first`)."""
+
+    def __init__(self, other_mask, other_P, first):
+        self.other_mask, self.other_P, self.first = other_mask, other_P, first
+
+    def all_reduce_and(self, mask):
+        mask &= self.other_mask
+        return mask
+
+    def all_gather_z(self, local):
+        import torch
+        parts = (local, self.other_P) if self.first else (self.other_P, local)
+        return torch.cat(parts, dim=-2).contiguous()
+
+
+def test_z_sharding_emulated_on_one_gpu(setup):
+    """Two slabs (4 + 2 redshifts) with the global bisection stop and the gathered Limber step reproduce the
+    unsharded answer exactly -- the coupling a per-slab bisection would break (utils.py:26)."""
+    import torch
+    g, inp, pipeline = setup
+    _, (f1, f2, fkk, fkg) = _run(pipeline, inp)
+    nz = g["zs"].size
+    sa, sb = slice(0, 4), slice(4, nz)
+    ia, ib = pipeline.slab_inputs(inp, sa), pipeline.slab_inputs(inp, sb)
+    # pass 1: each slab alone, to learn its mask and its spectra slabs
+    ga = pipeline.GridSix(ia, nz_total_zs=g["zs"]); ga.has_limber = False; ga.upload(); ga.run()
+    gb = pipeline.GridSix(ib, nz_total_zs=g["zs"]); gb.has_limber = False; gb.upload(); gb.run()
+    torch.cuda.synchronize()
+    ma, mb = ga.mask.clone(), gb.mask.clone()
+    gb2 = pipeline.GridSix(ib, zcomm=_StandInComm(ma, None, False), nz_total_zs=g["zs"]); gb2.has_limber = False
+    gb2.upload(); gb2.run(); torch.cuda.synchronize()
+    Pb = torch.stack((gb2.p1[0], gb2.p2[0], gb2.p1[4], gb2.p2[4])).clone()
+    ga2 = pipeline.GridSix(ia, zcomm=_StandInComm(mb, Pb, True), nz_total_zs=g["zs"])
+    ga2.upload(); ga2.run()
+    a1, a2, akk, akg = ga2.spectra()
+    b1, b2, _, _ = gb2.spectra()
+    for t in pipeline.TAGS:
+        assert_close(np.concatenate([a1[t], b1[t]]), f1[t], 1e-12, name="sharded P1h_" + t)
+        assert_close(np.concatenate([a2[t], b2[t]]), f2[t], 1e-12, name="sharded P2h_" + t)
+    assert_close(akk, fkk, 1e-12, name="sharded C_kk")
+    assert_close(akg, fkg, 1e-12, name="sharded C_kg")
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from conftest import load_golden
+        from hmvec_b200 import pipeline, zshard
+        g = load_golden("mini")
+        inp = pipeline.make_inputs(g["zs"], g["ms"], g["ks"], ngal=g["g2_ngal_target"], ells=g["ells"])
+        zc = zshard.ZComm(g["zs"].size)
+        gs = pipeline.GridSix(pipeline.slab_inputs(inp, zc.slab), zcomm=zc, nz_total_zs=g["zs"])
+        gs.upload(); gs.run()
+        p1, p2, ckk, ckg = gs.spectra()
+        q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_z_sharding_nccl_two_gpus(setup):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (covered on one GPU by test_z_sharding_emulated_on_one_gpu)")
+    import torch.multiprocessing as mp
+    g, inp, pipeline = setup
+    _, (f1, f2, fkk, fkg) = _run(pipeline, inp)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=300) for _ in procs), key=lambda o: o[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert_close(np.concatenate([out[0][3], out[1][3]]), f1["ge"], 1e-12)
+    assert_close(np.concatenate([out[0][4], out[1][4]]), f2["gg"], 1e-12)
+    for o in out:
+        assert_close(o[5], fkk, 1e-12)
+        assert_close(o[6], fkg, 1e-12)

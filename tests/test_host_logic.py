@@ -1,0 +1,79 @@
+"""Host-side producers of the product package (background, EH98 P_lin, Simpson weights, windows, slabs, bisection)
+against the CPU oracle / scipy.  CPU-only."""
+import warnings
+
+import numpy as np
+import pytest
+from scipy.integrate import simpson
+
+from conftest import assert_close
+from oracle import hmvec_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def cosmo():
+    from hmvec_b200.cosmology import Cosmology
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return Cosmology({}, accuracy='low')
+
+
+def test_simpson_weights_match_scipy():
+    from hmvec_b200.cosmology import simpson_weights
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 4, 7, 10, 101, 1000, 10000):
+        x = np.geomspace(1e-4, 2000, n) if n > 2 else np.array([0.3, 1.7])
+        y = rng.standard_normal((3, n))
+        assert_close(y @ simpson_weights(x), simpson(y, x=x, axis=-1), 1e-12, 1e-15)
+
+
+def test_background_and_linear_power(cosmo, golden_mini):
+    g = golden_mini
+    zs = g["zs"]
+    assert_close(cosmo.hubble_parameter(zs), g["hubble"], 1e-12)
+    assert_close(cosmo.comoving_radial_distance(zs), g["chi"], 1e-11)
+    assert_close(cosmo.rho_critical_z(zs), g["rho_crit"], 1e-12)
+    assert_close(cosmo.P_lin_approx(g["ks"], zs), g["Pzk"], 1e-9)
+    assert_close(cosmo.lensing_window(zs, 2.5), g["lens_window_25"], 1e-9)
+    assert_close(cosmo.lensing_window(zs, g["lz"], g["ldndz"]), g["lens_window_dndz"], 1e-9)
+    assert float(np.ravel(cosmo.comoving_radial_distance(1100.))[0]) == pytest.approx(orc.Background().chi(1100.), rel=1e-9)
+
+
+def test_make_inputs_and_slabs(golden_mini):
+    from hmvec_b200 import pipeline, zshard
+    g = golden_mini
+    inp = pipeline.make_inputs(g["zs"], g["ms"], g["ks"], ells=g["ells"])
+    assert_close(inp["Pzk"], g["Pzk"], 1e-9)
+    assert_close(inp["sPzk"][:, ::10], g["sPzk_sub"], 1e-9)
+    assert inp["kw"].shape == inp["ks_sig"].shape == (10000,)
+    b = zshard.slab_bounds(g["zs"].size, 4)
+    assert b[0] == 0 and b[-1] == g["zs"].size and np.all(np.diff(b) >= 1)
+    parts = [pipeline.slab_inputs(inp, zshard.slab(g["zs"].size, r, 4)) for r in range(4)]
+    assert_close(np.concatenate([p["Pzk"] for p in parts]), inp["Pzk"], 0)
+    assert_close(np.concatenate([p["zs"] for p in parts]), g["zs"], 0)
+    assert parts[0]["chis"].size == g["zs"].size          # Limber inputs stay replicated
+    for nz, w in ((200, 8), (7, 3), (5, 8)):
+        bb = zshard.slab_bounds(nz, w)
+        assert bb[-1] == nz and np.diff(bb).max() - np.diff(bb).min() <= 1
+
+
+def test_utils_bisection(golden_kat):
+    from hmvec_b200 import utils
+    utils.test_bisection_search()
+    y = utils.vectorized_bisection_search(golden_kat["bisect_x"], np.sqrt, (1, 40), 'increasing', verbose=False)
+    assert_close(y, golden_kat["bisect_y"], 1e-14)
+    with pytest.raises(AssertionError):
+        utils.vectorized_bisection_search(np.ones(2), np.sqrt, (1, 40), 'sideways')
+
+
+def test_device_ops_fail_loudly_without_gpu(cosmo):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cosmo.get_sigma2_R(np.array([1.0, 2.0]), np.array([0.5]))
+    from hmvec_b200 import HaloModel
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            HaloModel(np.array([0.1]), np.geomspace(1e-3, 1, 8), ms=np.geomspace(1e12, 1e14, 4), accuracy='low')
