@@ -281,7 +281,7 @@ def run_b200(a):
                        "l2": "inputs exceed L2 (two %.1f GB cubes per rank)" % (8e-9 * nzl * nm * g.ldk)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": g.h2d_bytes() * world,
                     "d2h_bytes_per_step": g.d2h_bytes() * world, "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": int(g.launches_per_run * a.steps), "clocks": clocks, "roofline": roof, "kernels": kernels}
+            "gpu_launches": int(g.launches_per_run * a.steps * world), "clocks": clocks, "roofline": roof, "kernels": kernels}
 
     if world == 1 and not a.no_cpu:
         v, dt = cpu_sample(a, 1, zper=a.cpu_nz)
