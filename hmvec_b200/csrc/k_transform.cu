@@ -33,9 +33,10 @@ struct TParams {
 __device__ __forceinline__ int skew(int m) { return m + (m >> 4) + (m >> 8); }
 static inline int skew_host(int m) { return m + (m >> 4) + (m >> 8); }
 
+// half-wave table (N even): sin(2 pi m/N) for m < N/2; the other half is its negative
 __global__ void sine_table_kernel(int N, double* __restrict__ tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) tab[skew(i)] = sinpi(2.0 * (double)i / (double)N);
+  if (i < N / 2) tab[skew(i)] = sinpi(2.0 * (double)i / (double)N);
 }
 
 // bins needed by each CTA (group of HB halos): jn = floor(kmax * max_h(rs (1+z)) / kt_1) + 2, capped at N/2
@@ -53,20 +54,29 @@ __global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double 
   jn_cta[b] = (int)fmin((double)J, floor(kmax * amax / kt1) + 2.0);
 }
 
-// U[h][j] += sum_nn gs[nn][h] * T[(j (n0+nn)) mod N] for NJ bins per thread and HPT halos starting at h0; the next
-// sample's table values are fetched before the current FMAs (software prefetch hides the LDS latency).
+// U[h][j] += sum_nn gs[nn][h] * sin(2 pi j (n0+nn)/N) for NJ bins per thread and HPT halos starting at h0.
+// The phase index (j n) mod N is tracked as (index mod N/2, sign bit): sin repeats with a sign flip after half a
+// period, so the table holds N/2 entries.  The next sample's table values are fetched before the current FMAs
+// (software prefetch hides the LDS latency).
+__device__ __forceinline__ double apply_sign(double v, int sgn) {
+  return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v));
+}
+
 template <int HB, int HPT, int NJ>
 __device__ __forceinline__ void accum_table(const double* __restrict__ T, const double* __restrict__ gs,
                                             double* __restrict__ Us, int JS, int N, int n0, int nlen, int jfirst,
                                             int jstride, int jn, int h0) {
-  int j[NJ], idx[NJ];
+  const int H = N >> 1;
+  int j[NJ], idx[NJ], sgn[NJ];
   double a[NJ][HPT], s[NJ];
 #pragma unroll
   for (int q = 0; q < NJ; ++q) {
     const int jj = jfirst + q * jstride;
     j[q] = (jj <= jn) ? jj : 0;                  // bin 0 reads T[0] = 0: a harmless dummy
-    idx[q] = (int)(((unsigned)j[q] * (unsigned)n0) % (unsigned)N);   // j*n0 < 2^31 (checked on the host)
-    s[q] = T[skew(idx[q])];
+    const int t = (int)(((unsigned)j[q] * (unsigned)n0) % (unsigned)N);   // j*n0 < 2^31 (checked on the host)
+    sgn[q] = (t >= H) ? (int)0x80000000 : 0;
+    idx[q] = (t >= H) ? t - H : t;
+    s[q] = apply_sign(T[skew(idx[q])], sgn[q]);
 #pragma unroll
     for (int h = 0; h < HPT; ++h) a[q][h] = 0.0;
   }
@@ -76,8 +86,8 @@ __device__ __forceinline__ void accum_table(const double* __restrict__ T, const 
 #pragma unroll
     for (int q = 0; q < NJ; ++q) {
       idx[q] += j[q];
-      if (idx[q] >= N) idx[q] -= N;
-      sn[q] = T[skew(idx[q])];
+      if (idx[q] >= H) { idx[q] -= H; sgn[q] ^= (int)0x80000000; }
+      sn[q] = apply_sign(T[skew(idx[q])], sgn[q]);
     }
     const double* g = gs + nn * HB + h0;
 #pragma unroll
@@ -146,7 +156,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
   const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
 
   if constexpr (TABLE) {
-    const int nsk = skew(p.N - 1) + 1;
+    const int nsk = skew(p.N / 2 - 1) + 1;
     for (int i = tid; i < nsk; i += TT) T[i] = __ldg(p.sintab + i);
   }
   for (int h = 0; h < HB; ++h)
@@ -184,9 +194,16 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     const int nlen = min(NCH, nb - n0);
     if constexpr (TABLE) {
       int jb = 1;
-      if constexpr (MAXNJ >= 4) {
-        for (; jn - jb + 1 > 2 * TT; jb += 4 * TT)   // four bins per thread while more than 2 TT bins remain
-          accum_table<HB, HB, 4>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
+      if constexpr (MAXNJ >= 4) {                      // as many bins per thread as the remaining count needs
+        while (jn - jb + 1 > 2 * TT) {
+          if (jn - jb + 1 > 3 * TT) {
+            accum_table<HB, HB, 4>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
+            jb += 4 * TT;
+          } else {
+            accum_table<HB, HB, 3>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
+            jb += 3 * TT;
+          }
+        }
       }
       const int rem = jn - jb + 1;
       if (MAXNJ >= 2 && rem > TT) {
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 
 template <int HB, int TT, bool TABLE>
 static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)skew_host(N - 1) + 1 : 0)) * sizeof(double);
+  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)skew_host(N / 2 - 1) + 1 : 0)) * sizeof(double);
 }
 
 template <int HB, int TT, bool TABLE, int MAXNJ>
@@ -341,21 +358,28 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   };
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
-  if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
+  if ((nxs & 1) == 0 && transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
     // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
     sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, ws_d);
     int rc = check_launch("sine_table_kernel");
     if (rc) return rc;
     rc = bin_counts(8);
     if (rc) return rc;
-    const int jA = 254, jB = 510;
-    rc = launch_transform<8, 512, true, 4>(p, jB, J, J + 2, st);            // heavy CTAs first
-    if (rc) return rc;
-    if (J > jA) {
-      rc = launch_transform<8, 256, true, 2>(p, jA, jB < J ? jB : J, (jB < J ? jB : J) + 2, st);
+    const int jA = 254, jB = 510, jC = 1022;           // class upper bounds: 4 / 3 / 2 / 1 CTAs fit per SM
+    auto hi = [&](int j) { return j < J ? j : J; };
+    if (J > jC) {
+      rc = launch_transform<8, 512, true, 4>(p, jC, J, J + 2, st);            // heavy CTAs first
       if (rc) return rc;
     }
-    return launch_transform<8, 256, true, 1>(p, 0, jA < J ? jA : J, (jA < J ? jA : J) + 2, st);
+    if (J > jB) {
+      rc = launch_transform<8, 256, true, 4>(p, jB, hi(jC), hi(jC) + 2, st);
+      if (rc) return rc;
+    }
+    if (J > jA) {
+      rc = launch_transform<8, 256, true, 2>(p, jA, hi(jB), hi(jB) + 2, st);
+      if (rc) return rc;
+    }
+    return launch_transform<8, 256, true, 1>(p, 0, hi(jA), hi(jA) + 2, st);
   }
   // large N: rotation recurrence, widest halo batch whose bin table fits
 #define HMV_ROT(HBV)                                                                   \
