@@ -156,12 +156,18 @@ __global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nm, int
     static_assert(NFW_T / 32 == NFW_E, "one slice per warp");
     const double ln1pc = log1p(c);
     const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-      if (__ldg(kcmax + chunk) * ac <= NFW_XC_MAX) continue;
-      const int k = chunk * NFW_CH + 32 * warp + lane;
-      if (k >= nk) continue;
-      const double kk = __ldg(ks + k), xc = kk * ac;
-      out[k] = (xc <= NFW_XC_MAX) ? nfw_horner(A, nfw_terms(xc), xc * xc) : nfw_bracket(kk * a, c, ln1pc) * inv_mc;
+    for (int cb = 0; cb < nchunks; cb += 32) {        // 32 chunks per ballot: visit only the tail chunks
+      const int cc = cb + lane;
+      unsigned tail = __ballot_sync(0xffffffffu, cc < nchunks && __ldg(kcmax + min(cc, nchunks - 1)) * ac > NFW_XC_MAX);
+      while (tail) {
+        const int chunk = cb + __ffs(tail) - 1;
+        tail &= tail - 1;
+        const int k = chunk * NFW_CH + 32 * warp + lane;
+        if (k < nk) {
+          const double kk = __ldg(ks + k), xc = kk * ac;
+          out[k] = (xc <= NFW_XC_MAX) ? nfw_horner(A, nfw_terms(xc), xc * xc) : nfw_bracket(kk * a, c, ln1pc) * inv_mc;
+        }
+      }
     }
   }
 }

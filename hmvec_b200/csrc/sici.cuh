@@ -1,6 +1,6 @@
 // sici.cuh -- FP64 device sine/cosine integrals for the analytic NFW profile (reference hmvec.py:349-352
 // calls scipy.special.sici).  Own derivation (tools/gen_sici_tables.py): Maclaurin series for x <= 4,
-// auxiliary functions f,g through piecewise degree-13 polynomials in s = 16/x^2 for x > 4.
+// auxiliary functions f,g through 128 uniform-segment degree-6 polynomials in s = 16/x^2 for x > 4.
 // Max error vs 50-digit mpmath: 2e-16 relative on f,g; 4e-16 relative on Si, 2e-15 absolute on Ci (x<=4).
 #pragma once
 #include "sici_tables.inc"
@@ -21,38 +21,28 @@ __device__ __forceinline__ void sici_series(double z, double& S, double& C) {
   C = c;
 }
 
-__device__ __forceinline__ int sici_segment(double s) {
-  return (s > c_seg_edge[1]) + (s > c_seg_edge[2]) + (s > c_seg_edge[3]) + (s > c_seg_edge[4]) +
-         (s > c_seg_edge[5]) + (s > c_seg_edge[6]) + (s > c_seg_edge[7]);
-}
-
-// f(x), g(x) for x > 4:  Si = pi/2 - f cos x - g sin x,  Ci = f sin x - g cos x
-__device__ __forceinline__ void sici_fg(double x, double& f, double& g) {
-  const double rx = 1.0 / x, rx2 = rx * rx, s = 16.0 * rx2;
-  const int seg = sici_segment(s);
-  const double u = (s - c_seg_mid[seg]) * c_seg_iscale[seg];
-  const double* cf = c_F + seg * (HMV_SICI_DEG + 1);
-  const double* cg = c_G + seg * (HMV_SICI_DEG + 1);
-  double F = cf[HMV_SICI_DEG], G = cg[HMV_SICI_DEG];
+// f(x), g(x) for x > 4 from the reciprocal rx = 1/x:  Si = pi/2 - f cos x - g sin x,  Ci = f sin x - g cos x.
+// s = 16/x^2 in (0,1] is cut into HMV_SICI_NSEG uniform segments (index = one multiply + float->int); each holds
+// degree-HMV_SICI_DEG polynomials for F = x f and G = x^2 g whose coefficient pairs are read as double2 (L1).
+__device__ __forceinline__ void sici_fg_r(double rx, double& f, double& g) {
+  const double rx2 = rx * rx;
+  const double t = (16.0 * HMV_SICI_NSEG) * rx2;
+  const int seg = min(HMV_SICI_NSEG - 1, (int)t);
+  const double u = fma(2.0, t - (double)seg, -1.0);
+  const double2* co = g_sici_FG + seg * (HMV_SICI_DEG + 1);
+  double2 c = __ldg(co + HMV_SICI_DEG);
+  double F = c.x, G = c.y;
 #pragma unroll
   for (int i = HMV_SICI_DEG - 1; i >= 0; --i) {
-    F = fma(F, u, cf[i]);
-    G = fma(G, u, cg[i]);
+    c = __ldg(co + i);
+    F = fma(F, u, c.x);
+    G = fma(G, u, c.y);
   }
   f = F * rx;
   g = G * rx2;
 }
 
-__device__ __forceinline__ double sici_g(double x) {
-  const double rx = 1.0 / x, rx2 = rx * rx, s = 16.0 * rx2;
-  const int seg = sici_segment(s);
-  const double u = (s - c_seg_mid[seg]) * c_seg_iscale[seg];
-  const double* cg = c_G + seg * (HMV_SICI_DEG + 1);
-  double G = cg[HMV_SICI_DEG];
-#pragma unroll
-  for (int i = HMV_SICI_DEG - 1; i >= 0; --i) G = fma(G, u, cg[i]);
-  return G * rx2;
-}
+__device__ __forceinline__ void sici_fg(double x, double& f, double& g) { sici_fg_r(1.0 / x, f, g); }
 
 // General-purpose pair (used by tests through hmv_sici_test): Si(x), Ci(x) for x > 0.
 __device__ __forceinline__ void sici(double x, double& si, double& ci) {
@@ -78,12 +68,13 @@ __device__ __forceinline__ void sici(double x, double& si, double& ci) {
 //   X <= 4     :  series at both, Ci X - Ci x = ln(1+c) + Z C(Z) - z C(z)
 __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) {
   const double X = (1.0 + c) * x;
+  const double rX = 1.0 / X;
   if (x > 4.0) {
-    double fX, gX, scx, ccx;
-    sici_fg(X, fX, gX);
-    const double gx = sici_g(x);
+    double fX, gX, fx, gx, scx, ccx;
+    sici_fg_r(rX, fX, gX);
+    sici_fg_r((1.0 + c) * rX, fx, gx);     // 1/x = (1+c)/X: one reciprocal serves both arguments
     sincos(c * x, &scx, &ccx);
-    return fX * scx - gX * ccx + gx - scx / X;
+    return fX * scx - gX * ccx + gx - scx * rX;
   }
   double sx, cx, S, C;
   sincos(x, &sx, &cx);
@@ -91,18 +82,18 @@ __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) 
   sici_series(z, S, C);
   if (X > 4.0) {
     double fX, gX, sX, cX;
-    sici_fg(X, fX, gX);
+    sici_fg_r(rX, fX, gX);
     sincos(X, &sX, &cX);
     const double siX = M_PI_2 - fX * cX - gX * sX, ciX = fX * sX - gX * cX;
     const double six = x * S, cix = HMV_EULER + log(x) + z * C;
     const double scx = sX * cx - cX * sx;  // sin(X - x) = sin(c x)
-    return sx * (siX - six) - scx / X + cx * (ciX - cix);
+    return sx * (siX - six) - scx * rX + cx * (ciX - cix);
   }
   double S2, C2;
   const double Z = X * X;
   sici_series(Z, S2, C2);
   const double dsi = X * S2 - x * S, dci = ln1pc + (Z * C2 - z * C);
-  return sx * dsi - sin(c * x) / X + cx * dci;
+  return sx * dsi - sin(c * x) * rX + cx * dci;
 }
 
 }  // namespace hmv
