@@ -110,6 +110,54 @@ __device__ __forceinline__ void accum_table(const double* __restrict__ T, const 
 
 constexpr int NCH = 256;   // samples evaluated per chunk
 
+// Tensor-core form of the same contraction: D[halo][bin] += A[halo][sample] * B[sample][bin] with FP64
+// mma.sync m8n8k4 (SASS DMMA.8x8x4).  M = the CTA's 8 halos, K = 4 consecutive samples, N = 8 consecutive bins.
+// DMMA has the DFMA pipe's peak on B200 (36.9 vs 35.0 TFLOP/s, tools/micro/dmma_bench.cu) but needs one issue slot
+// per 256 FMAs instead of eight, which is what the per-thread DFMA form was short of (ncu: issue-bound by the
+// phase-index arithmetic).  Lane (kq = lane%4, nq = lane/4) supplies A = gs[sample nn+kq][halo nq] and, per tile,
+// B = sin(2 pi (bin nq)(sample nn+kq)/N) from the half-wave table, and owns D[halo nq][bins 2kq, 2kq+1].
+template <int NT>
+__device__ __forceinline__ void accum_mma(const double* __restrict__ T, const double* __restrict__ gs,
+                                          double* __restrict__ Us, int JS, int N, int n0, int nlen, int jw, int jn,
+                                          int lane) {
+  constexpr int HB = 8;
+  const int H = N >> 1, kq = lane & 3, nq = lane >> 2;
+  int idx[NT], sgn[NT], stepi[NT], steps[NT];
+  double c[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int jj = jw + 8 * t + nq;
+    const int j = (jj <= jn) ? jj : 0;                 // bin 0: sin == 0, contributes nothing
+    const int ph = (int)(((unsigned)j * (unsigned)(n0 + kq)) % (unsigned)N);
+    sgn[t] = (ph >= H) ? (int)0x80000000 : 0;
+    idx[t] = (ph >= H) ? ph - H : ph;
+    const int st = (int)((4u * (unsigned)j) % (unsigned)N);     // phase advance per 4 samples
+    steps[t] = (st >= H) ? (int)0x80000000 : 0;
+    stepi[t] = (st >= H) ? st - H : st;
+    c[t][0] = 0.0; c[t][1] = 0.0;
+  }
+  const double* ga = gs + kq * HB + nq;
+#pragma unroll 2
+  for (int nn = 0; nn < nlen; nn += 4) {
+    const double a = ga[nn * HB];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const double b = apply_sign(T[skew(idx[t])], sgn[t]);
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+      idx[t] += stepi[t];
+      sgn[t] ^= steps[t];
+      if (idx[t] >= H) { idx[t] -= H; sgn[t] ^= (int)0x80000000; }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int b0 = jw + 8 * t + 2 * kq;
+    if (b0 <= jn) Us[(size_t)nq * JS + b0] += c[t][0];
+    if (b0 + 1 <= jn) Us[(size_t)nq * JS + b0 + 1] += c[t][1];
+  }
+}
+
 template <int HB, int TT, bool TABLE, int MAXNJ>
 __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) {
   static_assert(TT % NCH == 0 && HB % (TT / NCH) == 0, "threads must tile the (sample, halo) chunk");
@@ -193,32 +241,29 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
     __syncthreads();
     const int nlen = min(NCH, nb - n0);
     if constexpr (TABLE) {
-      int jb = 1;
-      if constexpr (MAXNJ >= 4) {                      // as many bins per thread as the remaining count needs
-        while (jn - jb + 1 > 2 * TT) {
-          if (jn - jb + 1 > 3 * TT) {
-            accum_table<HB, HB, 4>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
-            jb += 4 * TT;
-          } else {
-            accum_table<HB, HB, 3>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
-            jb += 3 * TT;
+      static_assert(!TABLE || HB == 8, "the tensor-core path contracts 8 halos per tile");
+      // bins 1..jn in tiles of 8; each pass gives every warp NT consecutive tiles (NT sized to what is left)
+      constexpr int NW = TT / 32;
+      const int warp = tid >> 5, lane = tid & 31;
+      const int ntile = (jn + 7) >> 3;
+      for (int t0 = 0; t0 < ntile;) {
+        const int per = (ntile - t0 + NW - 1) / NW;
+        const int jw = 1 + 8 * (t0 + warp * ((per > 4 && MAXNJ >= 8) ? 8 : per > 2 ? 4 : per > 1 ? 2 : 1));
+        if (per > 4 && MAXNJ >= 8) {
+          if constexpr (MAXNJ >= 8) {
+            if (jw <= jn) accum_mma<8>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
           }
+          t0 += 8 * NW;
+        } else if (per > 2) {
+          if (jw <= jn) accum_mma<4>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
+          t0 += 4 * NW;
+        } else if (per > 1) {
+          if (jw <= jn) accum_mma<2>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
+          t0 += 2 * NW;
+        } else {
+          if (jw <= jn) accum_mma<1>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
+          t0 += NW;
         }
-      }
-      const int rem = jn - jb + 1;
-      if (MAXNJ >= 2 && rem > TT) {
-        if constexpr (MAXNJ >= 2) accum_table<HB, HB, 2>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
-      } else if (rem > TT / 2 || HB < 8) {
-        if (jb + tid <= jn) accum_table<HB, HB, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + tid, TT, jn, 0);
-      } else if (rem > TT / 4) {                       // few bins left: split the halos over the idle threads
-        const int part = tid / (TT / 2), jl = tid % (TT / 2);
-        if (jb + jl <= jn) accum_table<HB, HB / 2, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 2));
-      } else if (rem > TT / 8) {
-        const int part = tid / (TT / 4), jl = tid % (TT / 4);
-        if (jb + jl <= jn) accum_table<HB, HB / 4, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 4));
-      } else if (rem > 0) {
-        const int part = tid / (TT / 8), jl = tid % (TT / 8);
-        if (jb + jl <= jn) accum_table<HB, HB / 8, 1>(T, gs, Us, p.JS, p.N, n0, nlen, jb + jl, TT, jn, part * (HB / 8));
       }
     } else {
       for (int j = tid + 1; j <= jn; j += TT) {
@@ -368,18 +413,18 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
     const int jA = 254, jB = 510, jC = 1022;           // class upper bounds: 4 / 3 / 2 / 1 CTAs fit per SM
     auto hi = [&](int j) { return j < J ? j : J; };
     if (J > jC) {
-      rc = launch_transform<8, 512, true, 4>(p, jC, J, J + 2, st);            // heavy CTAs first
+      rc = launch_transform<8, 512, true, 8>(p, jC, J, J + 2, st);            // heavy CTAs first
       if (rc) return rc;
     }
     if (J > jB) {
-      rc = launch_transform<8, 256, true, 4>(p, jB, hi(jC), hi(jC) + 2, st);
+      rc = launch_transform<8, 256, true, 8>(p, jB, hi(jC), hi(jC) + 2, st);
       if (rc) return rc;
     }
     if (J > jA) {
-      rc = launch_transform<8, 256, true, 2>(p, jA, hi(jB), hi(jB) + 2, st);
+      rc = launch_transform<8, 256, true, 8>(p, jA, hi(jB), hi(jB) + 2, st);
       if (rc) return rc;
     }
-    return launch_transform<8, 256, true, 1>(p, 0, hi(jA), hi(jA) + 2, st);
+    return launch_transform<8, 256, true, 4>(p, 0, hi(jA), hi(jA) + 2, st);
   }
   // large N: rotation recurrence, widest halo batch whose bin table fits
 #define HMV_ROT(HBV)                                                                   \
