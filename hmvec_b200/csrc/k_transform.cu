@@ -9,12 +9,19 @@
 // u_j = U_j/kt_j/mnorm is linearly interpolated onto ks from shared memory (direct index j=floor(k/kout_1), no
 // search) and written once, coalesced.
 //
-// The sine matrix S[n][j] = sin(2 pi (n j mod N)/N) is halo independent.  For N <= 5400 it is read from a one-period
-// table staged in shared memory (index advanced by j mod N: two integer instructions and one LDS per (n,j), leaving
-// the FP64 pipe to the HB accumulations, two bins per thread sharing the sample loads).  Larger N fall back to a
-// rotation recurrence re-seeded exactly every chunk.  Because the number of bins a halo needs grows like M^(1/3)
-// (10 ... N/2), CTAs are launched in three bin-count classes with shared-memory footprints of 73 / 106 / 216 KB so
-// that the many small halos run 3 CTAs per SM instead of being sized for the largest one.
+// The sine matrix S[n][j] = sin(2 pi n j/N) is halo independent, so the sums are a dense contraction
+// [8 halos x samples] x [samples x bins] and run on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
+// A lane's B-operand element is sin(phi_j (s + 4 i)) for its fixed (bin j, sample offset): an arithmetic sequence of
+// angles, advanced with the three-term recurrence  b_{i+1} = 2 cos(4 phi_j) b_i - b_{i-1}  (one DFMA per DMMA) and
+// re-seeded exactly from a {sin,cos} table (global memory, L1-resident) at every 256-sample chunk, which bounds the
+// recurrence round-off at 64^2 ulp/2 ~ 5e-13.  Why tensor cores: DMMA has the DFMA pipe's peak on B200 (36.9 vs 35.0
+// TFLOP/s, tools/micro/dmma_bench.cu) but takes ONE issue slot per 256 FMAs; the per-thread DFMA form was issue-bound
+// on phase-index arithmetic and a DMMA form fed from a shared-memory sine table was shared-memory bandwidth bound
+// (0.74 wavefronts/cycle/SM: the 32 table addresses of a B fragment are effectively random, ~6 wavefronts per
+// fragment) -- ncu evidence in profiles/.  nxs too large for 8 halos' bin tables in shared memory (> ~6400) or odd
+// falls back to a DFMA rotation recurrence.  Because the number of bins a halo needs grows like M^(1/3)
+// (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints (33 / 49 / 82 / 176 KB)
+// let the many small halos run several CTAs per SM instead of all being sized for the largest one.
 #include "common.cuh"
 
 namespace hmv {
@@ -27,16 +34,16 @@ struct TParams {
   double* uk;
 };
 
-// Table slot of phase index m.  Lanes hold consecutive bins j, so at sample n they read indices (j n) mod N -- an
-// arithmetic progression of stride n.  Skewing by m/16 + m/256 turns the even strides (2..256-fold bank conflicts
-// on 8-byte words) into conflict-free ones.
-__device__ __forceinline__ int skew(int m) { return m + (m >> 4) + (m >> 8); }
-static inline int skew_host(int m) { return m + (m >> 4) + (m >> 8); }
+constexpr int NCH = 256;   // samples evaluated per chunk
 
-// half-wave table (N even): sin(2 pi m/N) for m < N/2; the other half is its negative
-__global__ void sine_table_kernel(int N, double* __restrict__ tab) {
+// {sin, cos}(2 pi m/N) for m < N: seeds of the tensor-core path (read with __ldg, 16 bytes per entry)
+__global__ void sine_table_kernel(int N, double2* __restrict__ tab) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N / 2) tab[skew(i)] = sinpi(2.0 * (double)i / (double)N);
+  if (i < N) {
+    double sn, cs;
+    sincospi(2.0 * (double)i / (double)N, &sn, &cs);
+    tab[i] = make_double2(sn, cs);
+  }
 }
 
 // bins needed by each CTA (group of HB halos): jn = floor(kmax * max_h(rs (1+z)) / kt_1) + 2, capped at N/2
@@ -54,86 +61,26 @@ __global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double 
   jn_cta[b] = (int)fmin((double)J, floor(kmax * amax / kt1) + 2.0);
 }
 
-// U[h][j] += sum_nn gs[nn][h] * sin(2 pi j (n0+nn)/N) for NJ bins per thread and HPT halos starting at h0.
-// The phase index (j n) mod N is tracked as (index mod N/2, sign bit): sin repeats with a sign flip after half a
-// period, so the table holds N/2 entries.  The next sample's table values are fetched before the current FMAs
-// (software prefetch hides the LDS latency).
-__device__ __forceinline__ double apply_sign(double v, int sgn) {
-  return __hiloint2double(__double2hiint(v) ^ sgn, __double2loint(v));
-}
-
-template <int HB, int HPT, int NJ>
-__device__ __forceinline__ void accum_table(const double* __restrict__ T, const double* __restrict__ gs,
-                                            double* __restrict__ Us, int JS, int N, int n0, int nlen, int jfirst,
-                                            int jstride, int jn, int h0) {
-  const int H = N >> 1;
-  int j[NJ], idx[NJ], sgn[NJ];
-  double a[NJ][HPT], s[NJ];
-#pragma unroll
-  for (int q = 0; q < NJ; ++q) {
-    const int jj = jfirst + q * jstride;
-    j[q] = (jj <= jn) ? jj : 0;                  // bin 0 reads T[0] = 0: a harmless dummy
-    const int t = (int)(((unsigned)j[q] * (unsigned)n0) % (unsigned)N);   // j*n0 < 2^31 (checked on the host)
-    sgn[q] = (t >= H) ? (int)0x80000000 : 0;
-    idx[q] = (t >= H) ? t - H : t;
-    s[q] = apply_sign(T[skew(idx[q])], sgn[q]);
-#pragma unroll
-    for (int h = 0; h < HPT; ++h) a[q][h] = 0.0;
-  }
-#pragma unroll 2
-  for (int nn = 0; nn < nlen; ++nn) {
-    double sn[NJ];
-#pragma unroll
-    for (int q = 0; q < NJ; ++q) {
-      idx[q] += j[q];
-      if (idx[q] >= H) { idx[q] -= H; sgn[q] ^= (int)0x80000000; }
-      sn[q] = apply_sign(T[skew(idx[q])], sgn[q]);
-    }
-    const double* g = gs + nn * HB + h0;
-#pragma unroll
-    for (int h = 0; h < HPT; ++h) {
-      const double gv = g[h];
-#pragma unroll
-      for (int q = 0; q < NJ; ++q) a[q][h] = fma(gv, s[q], a[q][h]);
-    }
-#pragma unroll
-    for (int q = 0; q < NJ; ++q) s[q] = sn[q];
-  }
-#pragma unroll
-  for (int q = 0; q < NJ; ++q) {
-    if (j[q]) {
-#pragma unroll
-      for (int h = 0; h < HPT; ++h) Us[(size_t)(h0 + h) * JS + j[q]] += a[q][h];
-    }
-  }
-}
-
-constexpr int NCH = 256;   // samples evaluated per chunk
-
-// Tensor-core form of the same contraction: D[halo][bin] += A[halo][sample] * B[sample][bin] with FP64
-// mma.sync m8n8k4 (SASS DMMA.8x8x4).  M = the CTA's 8 halos, K = 4 consecutive samples, N = 8 consecutive bins.
-// DMMA has the DFMA pipe's peak on B200 (36.9 vs 35.0 TFLOP/s, tools/micro/dmma_bench.cu) but needs one issue slot
-// per 256 FMAs instead of eight, which is what the per-thread DFMA form was short of (ncu: issue-bound by the
-// phase-index arithmetic).  Lane (kq = lane%4, nq = lane/4) supplies A = gs[sample nn+kq][halo nq] and, per tile,
-// B = sin(2 pi (bin nq)(sample nn+kq)/N) from the half-wave table, and owns D[halo nq][bins 2kq, 2kq+1].
+// U[halo][bin] += sum_n gs[n][halo] sin(2 pi bin (n0+n)/N) on the tensor cores: D[8 halos][8 bins] += A[8][4] B[4][8]
+// per mma.sync m8n8k4.  Lane (kq = lane%4, nq = lane/4) supplies A = gs[sample nn+kq][halo nq] and, per tile t,
+// B = sin(phi_j (n0+nn+kq)) for bin j = jw + 8 t + nq, and owns D[halo nq][bins 2kq, 2kq+1] of every tile.
 template <int NT>
-__device__ __forceinline__ void accum_mma(const double* __restrict__ T, const double* __restrict__ gs,
+__device__ __forceinline__ void accum_mma(const double2* __restrict__ tab, const double* __restrict__ gs,
                                           double* __restrict__ Us, int JS, int N, int n0, int nlen, int jw, int jn,
                                           int lane) {
   constexpr int HB = 8;
-  const int H = N >> 1, kq = lane & 3, nq = lane >> 2;
-  int idx[NT], sgn[NT], stepi[NT], steps[NT];
-  double c[NT][2];
+  const int kq = lane & 3, nq = lane >> 2;
+  double bc[NT], bp[NT], tc[NT], c[NT][2];
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
     const int jj = jw + 8 * t + nq;
-    const int j = (jj <= jn) ? jj : 0;                 // bin 0: sin == 0, contributes nothing
-    const int ph = (int)(((unsigned)j * (unsigned)(n0 + kq)) % (unsigned)N);
-    sgn[t] = (ph >= H) ? (int)0x80000000 : 0;
-    idx[t] = (ph >= H) ? ph - H : ph;
-    const int st = (int)((4u * (unsigned)j) % (unsigned)N);     // phase advance per 4 samples
-    steps[t] = (st >= H) ? (int)0x80000000 : 0;
-    stepi[t] = (st >= H) ? st - H : st;
+    const unsigned j = (jj <= jn) ? (unsigned)jj : 0u;          // bin 0: sin == 0, contributes nothing
+    const unsigned ph = (j * (unsigned)(n0 + kq)) % (unsigned)N;  // j*n < 2^31 (checked on the host)
+    const unsigned st = (4u * j) % (unsigned)N;                   // phase advance per 4 samples
+    const unsigned pp = ph >= st ? ph - st : ph + (unsigned)N - st;
+    bc[t] = __ldg(tab + ph).x;
+    bp[t] = __ldg(tab + pp).x;
+    tc[t] = 2.0 * __ldg(tab + st).y;
     c[t][0] = 0.0; c[t][1] = 0.0;
   }
   const double* ga = gs + kq * HB + nq;
@@ -142,12 +89,11 @@ __device__ __forceinline__ void accum_mma(const double* __restrict__ T, const do
     const double a = ga[nn * HB];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      const double b = apply_sign(T[skew(idx[t])], sgn[t]);
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
-      idx[t] += stepi[t];
-      sgn[t] ^= steps[t];
-      if (idx[t] >= H) { idx[t] -= H; sgn[t] ^= (int)0x80000000; }
+                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(bc[t]));
+      const double bn = fma(tc[t], bc[t], -bp[t]);
+      bp[t] = bc[t];
+      bc[t] = bn;
     }
   }
 #pragma unroll
@@ -159,13 +105,12 @@ __device__ __forceinline__ void accum_mma(const double* __restrict__ T, const do
 }
 
 template <int HB, int TT, bool TABLE, int MAXNJ>
-__global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) {
+__global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
   static_assert(TT % NCH == 0 && HB % (TT / NCH) == 0, "threads must tile the (sample, halo) chunk");
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
   double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
   double* red = gs + NCH * HB;                // [32]
-  double* T = red + 32;                       // [N] (TABLE only)
   __shared__ double h_cmax[HB], h_lxc[HB], h_alpha[HB], h_expo[HB], h_amp[HB], h_a[HB], h_oscale[HB];
   __shared__ double h_k1[HB], h_kJ[HB], h_inv[HB], h_u1[HB];
   __shared__ int h_valid[HB];
@@ -203,10 +148,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
   for (int h = 0; h < HB; ++h) cmx = fmax(cmx, h_cmax[h]);
   const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
 
-  if constexpr (TABLE) {
-    const int nsk = skew(p.N / 2 - 1) + 1;
-    for (int i = tid; i < nsk; i += TT) T[i] = __ldg(p.sintab + i);
-  }
+  const double2* T = reinterpret_cast<const double2*>(p.sintab);
   for (int h = 0; h < HB; ++h)
     for (int j = tid; j <= jn + 1; j += TT) Us[(size_t)h * p.JS + j] = 0.0;
   __syncthreads();
@@ -346,7 +288,7 @@ __global__ void __launch_bounds__(TT) profile_transform_kernel(const TParams p) 
 
 template <int HB, int TT, bool TABLE>
 static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (TABLE ? (size_t)skew_host(N / 2 - 1) + 1 : 0)) * sizeof(double);
+  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (size_t)0 * (TABLE ? N : 0)) * sizeof(double);
 }
 
 template <int HB, int TT, bool TABLE, int MAXNJ>
@@ -369,8 +311,8 @@ using namespace hmv;
 
 extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
-  // skewed one-period sine table + one int per CTA (bin counts; a CTA holds at least one halo)
-  return (long long)skew_host(nxs - 1) + 2 + ((long long)nz * nm + 1) / 2 + 2;
+  // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
+  return 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2;
 }
 
 extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
@@ -393,7 +335,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.kmax = kmax;
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
-  int* jn_cta = reinterpret_cast<int*>(ws_d + ((skew_host(nxs - 1) + 2 + 1) & ~1));
+  int* jn_cta = reinterpret_cast<int*>(ws_d + 2 * (size_t)nxs + 2);
   p.jn_cta = jn_cta;
   cudaStream_t st = (cudaStream_t)stream;
   auto bin_counts = [&](int HB) {
@@ -403,9 +345,9 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   };
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
-  if ((nxs & 1) == 0 && transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
+  if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
     // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
-    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, ws_d);
+    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d));
     int rc = check_launch("sine_table_kernel");
     if (rc) return rc;
     rc = bin_counts(8);
@@ -421,7 +363,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
       if (rc) return rc;
     }
     if (J > jA) {
-      rc = launch_transform<8, 256, true, 8>(p, jA, hi(jB), hi(jB) + 2, st);
+      rc = launch_transform<8, 256, true, 4>(p, jA, hi(jB), hi(jB) + 2, st);
       if (rc) return rc;
     }
     return launch_transform<8, 256, true, 4>(p, 0, hi(jA), hi(jA) + 2, st);
