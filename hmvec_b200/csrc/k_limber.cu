@@ -66,6 +66,23 @@ __global__ void __launch_bounds__(256) dfma_kernel(int iters, double seed, doubl
   if (s == 1.2345) sink[0] = s;   // never true; keeps the chains alive
 }
 
+__global__ void __launch_bounds__(256) dmma_kernel(int iters, double* __restrict__ sink) {
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  double c[8][2];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[q][0]), "+d"(c[q][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += c[q][0] + c[q][1];
+  if (s == 1.2345) sink[0] = s;   // never true; keeps the chains alive
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst,
                                                     long long n2) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -111,6 +128,35 @@ extern "C" double hmv_bench_dfma(int iters, void* stream) {
   cudaFree(sink);
   if (cudaGetLastError() != cudaSuccess) return -1.0;
   const double flop = 2.0 * 8.0 * (double)iters * blocks * threads;
+  return flop / (best * 1e-3) / 1e12;
+}
+
+extern "C" double hmv_bench_dmma(int iters, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  double* sink = nullptr;
+  if (cudaMalloc(&sink, 8) != cudaSuccess) return -1.0;
+  const int blocks = sms * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  dmma_kernel<<<blocks, threads, 0, st>>>(iters / 8 + 1, sink);  // warm-up
+  float best = 1e30f;
+  for (int r = 0; r < 3; ++r) {
+    cudaEventRecord(e0, st);
+    dmma_kernel<<<blocks, threads, 0, st>>>(iters, sink);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(sink);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  // one m8n8k4 = 256 FMA = 512 flop per warp instruction, 8 per iteration per warp
+  const double flop = 512.0 * 8.0 * (double)iters * blocks * (threads / 32);
   return flop / (best * 1e-3) / 1e12;
 }
 

@@ -165,6 +165,8 @@ int hmv_sici_test(int n, const double* x_d, double* si_d, double* ci_d, void* st
  * hmv_bench_dfma: dependent-chain-free DFMA micro-benchmark; returns achieved FP64 TFLOP/s (2 flop per FMA)
  * on the current device, timed with CUDA events.  hmv_bench_copy: device copy GB/s (read+write bytes). */
 double hmv_bench_dfma(int iters, void* stream);
+/* hmv_bench_dmma: the same for FP64 tensor-core mma.sync m8n8k4 (512 flop per warp instruction). */
+double hmv_bench_dmma(int iters, void* stream);
 double hmv_bench_copy(const double* src_d, double* dst_d, long long n, int reps, void* stream);
 
 #ifdef __cplusplus
