@@ -7,7 +7,7 @@
 
 namespace hmv {
 
-constexpr int HT = 256;
+constexpr int HT = 1024;   // one CTA per redshift: the bisection is latency-bound, so use the whole CTA width
 constexpr int NTAB = 4000;  // hmvec.py:641
 
 struct HodP { double sig, alphasat, Bsat, betasat, Bcut, betacut, Msat_ov, Mcut_ov; };
@@ -62,7 +62,8 @@ __device__ __forceinline__ SatScale sat_scales(const Shmr& s, const HodP& hp, do
 __device__ __forceinline__ void occupations(double M, double lmstar, double lth, const HodP& hp, const SatScale& sc,
                                             double& Nc, double& Ns) {
   Nc = 0.5 * (1.0 - erf((lth - lmstar) / (M_SQRT2 * hp.sig)));               // hmvec.py:701-703
-  Ns = Nc * pow(M / sc.Msat, hp.alphasat) * exp(-sc.Mcut / M);                // hmvec.py:716
+  const double r = M / sc.Msat;
+  Ns = Nc * (hp.alphasat == 1.0 ? r : pow(r, hp.alphasat)) * exp(-sc.Mcut / M);   // hmvec.py:716
 }
 
 // shared staging used by both kernels: tab[NTAB], lmstar[nm], wn[nm] = trapz_weight * nzm

@@ -1,4 +1,4 @@
-// k_sigma2.cu -- K3: sigma^2(R,z) contraction, K3b: Sheth-Tormen mass function and bias.
+// k_sigma2.cu -- K3: sigma^2(R,z) contraction (FP64 tensor cores), K3b: Sheth-Tormen mass function and bias.
 // Reference arithmetic: cosmology.py:30-38 (Wkr), :245-269 (get_sigma2_R), hmvec.py:133-185.
 #include "common.cuh"
 
@@ -23,7 +23,9 @@ __global__ void w2_table_kernel(int nm, int nks, const double* __restrict__ ks, 
   W2T[idx] = w * w;
 }
 
-// ---- contraction C[z][m] = sum_k (sPzk[z][k]*kw[k]) * W2T[k][m] ; register-tiled FP64 GEMM -------------
+// ---- contraction C[z][m] = sum_k (sPzk[z][k]*kw[k]) * W2T[k][m] : FP64 tensor-core GEMM ---------------------
+// CTA tile 32 (z) x 64 (m), k staged 16 at a time through shared memory; warp w owns the 8 x 32 strip
+// (rows 8 (w&3), columns 32 (w>>2)) as four mma.sync m8n8k4 tiles.  Split-k across blockIdx.z.
 constexpr int BM = 32, BN = 64, BK = 16, GT = 256;
 
 __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks, int kchunk,
@@ -31,13 +33,14 @@ __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks
                                                          const double* __restrict__ kw,
                                                          const double* __restrict__ W2T, double* __restrict__ out,
                                                          long long out_split_stride) {
-  __shared__ double As[BK][BM + 2];
-  __shared__ double Bs[BK][BN];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, microtile 2(z) x 4(m)
+  __shared__ double As[BK][BM + 1];
+  __shared__ double Bs[BK][BN + 8];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int kq = lane & 3, nq = lane >> 2;
+  const int wz = (w & 3) * 8, wn = (w >> 2) * 32;
   const int z0 = blockIdx.y * BM, m0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * kchunk, kend = min(nks, kbeg + kchunk);
-  double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
   // loader indices
   const int az = tid >> 3, ak = (tid & 7) * 2;     // A: 32 z x 16 k, 2 k per thread
   const int bk = tid >> 4, bm = (tid & 15) * 4;    // B: 16 k x 64 m, 4 m per thread
@@ -54,25 +57,25 @@ __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const double a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
-      const double b0 = Bs[kk][tx * 4], b1 = Bs[kk][tx * 4 + 1], b2 = Bs[kk][tx * 4 + 2], b3 = Bs[kk][tx * 4 + 3];
-      acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
-      acc[0][2] = fma(a0, b2, acc[0][2]); acc[0][3] = fma(a0, b3, acc[0][3]);
-      acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
-      acc[1][2] = fma(a1, b2, acc[1][2]); acc[1][3] = fma(a1, b3, acc[1][3]);
+    for (int kk = 0; kk < BK; kk += 4) {
+      const double a = As[kk + kq][wz + nq];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const double b = Bs[kk + kq][wn + 8 * t + nq];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+      }
     }
     __syncthreads();
   }
   double* o = out + (long long)blockIdx.z * out_split_stride;
+  const int z = z0 + wz + nq;
+  if (z < nz) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int z = z0 + ty * 2 + i;
-    if (z >= nz) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int m = m0 + tx * 4 + j;
-      if (m < nm) o[(long long)z * nm + m] = acc[i][j];
+    for (int t = 0; t < 4; ++t) {
+      const int m = m0 + wn + 8 * t + 2 * kq;
+      if (m < nm) o[(long long)z * nm + m] = c[t][0];
+      if (m + 1 < nm) o[(long long)z * nm + m + 1] = c[t][1];
     }
   }
 }
