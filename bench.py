@@ -224,14 +224,13 @@ def run_b200(a):
 
     # ---- end to end through pinned host buffers -----------------------------------------------------------------
     for _ in range(2):
-        g.upload(); g.run(); g.download()
+        g.upload(); g.run(overlap_d2h=True); g.finish_e2e()
     barrier()
     e0.record()
     for s in range(a.steps):
-        g.upload()
-        g.run()
-        g.download()
-        torch.cuda.current_stream().synchronize()     # the step's results are on the host before the next one starts
+        g.upload()                   # pinned host -> HBM: linear power, background, ngal targets
+        g.run(overlap_d2h=True)      # spectra go back chunk by chunk while later z-chunks are still being reduced
+        g.finish_e2e()               # the step's results are on the host before the next one starts
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

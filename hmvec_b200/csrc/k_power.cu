@@ -220,6 +220,7 @@ constexpr size_t SIX_SMEM = (size_t)SIX_NST * SIX_STAGE_DOUBLES * sizeof(double)
 
 struct SixArgs {
   int nz, nm, nk, ldk;
+  long long spec_stride;   // doubles between consecutive spectra in p1h/p2h
   const double *um, *ue, *coef;
   const double *zoff, *ks, *Pzk;
   double kstar;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs
     if (lane == 0) mbar_arrive(empty + s);                 // this warp is done with the stage
   }
   if (!active) return;
-  const long long S = (long long)a.nz * a.nk;
+  const long long S = a.spec_stride;
   const double zo0 = a.zoff[2 * z], zo1 = a.zoff[2 * z + 1];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
@@ -397,7 +398,7 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
                              const double* nzm_d, const double* bh_d, const double* Pzk_d, double rho_m0,
                              double kstar, const double* um_d, const double* ue_d, const double* Nc_d,
                              const double* Ns_d, const double* NcNs_d, const double* NsNsm1_d, const double* ngal_d,
-                             double* ws_d, double* p1h_d, double* p2h_d, void* stream) {
+                             double* ws_d, long long spec_stride, double* p1h_d, double* p2h_d, void* stream) {
   HMV_REQUIRE(nz > 0 && nm >= 2 && nk > 0 && ldk >= nk, "hmv_power_six: bad sizes");
   HMV_REQUIRE((ldk & 1) == 0, "hmv_power_six: ldk must be even; got %d", ldk);
   HMV_REQUIRE(nz <= 65535, "hmv_power_six: nz=%d exceeds grid.y limit 65535", nz);
@@ -415,6 +416,8 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
   int rc = check_launch("power_six_prep_kernel");
   if (rc) return rc;
   SixArgs a;
+  HMV_REQUIRE(spec_stride == 0 || spec_stride >= (long long)nz * nk, "hmv_power_six: spec_stride smaller than nz*nk");
+  a.spec_stride = spec_stride ? spec_stride : (long long)nz * nk;
   a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.um = um_d; a.ue = ue_d; a.coef = coef;
   a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar; a.p1h = p1h_d; a.p2h = p2h_d;
   cudaError_t e = cudaFuncSetAttribute(power_six_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIX_SMEM);

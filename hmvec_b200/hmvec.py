@@ -504,7 +504,7 @@ class HaloModel(Cosmology):
                                           capi.ptr(self.uk_profiles.device(matter)),
                                           capi.ptr(self.uk_profiles.device(electron)), capi.ptr(d['Nc']),
                                           capi.ptr(d['Ns']), capi.ptr(d['NcNs']), capi.ptr(d['NsNsm1']),
-                                          capi.ptr(d['ngal']), capi.ptr(ws), capi.ptr(p1), capi.ptr(p2),
+                                          capi.ptr(d['ngal']), capi.ptr(ws), 0, capi.ptr(p1), capi.ptr(p2),
                                           capi.stream()), "hmv_power_six")
         tags = ("mm", "ee", "me", "gg", "gm", "ge")
         if not to_host:

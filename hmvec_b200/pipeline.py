@@ -147,6 +147,9 @@ class GridSix(object):
             self.h_cl = torch.empty((2, self.nl), dtype=torch.float64).pin_memory()
         self.launches_per_run = 0
         self._ev = None
+        self.d2h_chunks = 5
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
 
     # ------------------------------------------------------------------ host <-> device
     def h2d_bytes(self):
@@ -166,14 +169,23 @@ class GridSix(object):
         if self.has_limber:
             self.h_cl.copy_(self.cl, non_blocking=True)
 
+    def finish_e2e(self):
+        """After run(overlap_d2h=True): copy the C_ell and wait until every result is in the pinned host buffers."""
+        if self.has_limber:
+            self.h_cl.copy_(self.cl, non_blocking=True)
+        self.copy_stream.synchronize()
+        torch.cuda.current_stream().synchronize()
+
     # ------------------------------------------------------------------ the launch sequence
     def _mark(self, i):
         if self._ev is not None:
             self._ev[i].record()
 
-    def run(self, events=None):
+    def run(self, events=None, overlap_d2h=False):
         """Issue the whole path on the current stream.  `events`: optional list of len(STAGES)+1 CUDA events
-        recorded at the stage boundaries (per-kernel timing for the roofline report)."""
+        recorded at the stage boundaries (per-kernel timing for the roofline report).  overlap_d2h: end-to-end mode --
+        the spectra leave for the pinned host buffers chunk by chunk on a copy stream while later chunks compute;
+        finish with `finish_e2e()`."""
         L, d, ptr, st = capi.lib, self.d, capi.ptr, capi.stream()
         nz, nm, nk, ldk = self.nz, self.nm, self.nk, self.ldk
         p = self.p
@@ -220,11 +232,29 @@ class GridSix(object):
                              st), "hmv_hod")
         n += 4
         self._mark(5)
-        capi.check(L.hmv_power_six(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
-                                   ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), ptr(self.um), ptr(self.ue),
-                                   ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NcNs"]), ptr(d["NsNsm1"]), ptr(d["ngal"]),
-                                   ptr(d["pow_ws"]), ptr(self.p1), ptr(self.p2), st), "hmv_power_six")
-        n += 2
+        # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
+        nchunk = self.d2h_chunks if overlap_d2h else 1
+        zb = np.linspace(0, nz, nchunk + 1).round().astype(int)
+        S = nz * nk
+        off = lambda t, z0, w: C.c_void_p(t.data_ptr() + 8 * z0 * w)
+        for ci in range(nchunk):
+            z0, z1 = int(zb[ci]), int(zb[ci + 1])
+            if z1 == z0:
+                continue
+            capi.check(L.hmv_power_six(z1 - z0, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), off(d["nzm"], z0, nm),
+                                       off(d["bh"], z0, nm), off(d["Pzk"], z0, nk), self.rho_m0,
+                                       float(p['kstar_damping']), off(self.um, z0, nm * ldk), off(self.ue, z0, nm * ldk),
+                                       off(d["Nc"], z0, nm), off(d["Ns"], z0, nm), off(d["NcNs"], z0, nm),
+                                       off(d["NsNsm1"], z0, nm), off(d["ngal"], z0, 1), ptr(d["pow_ws"]), S,
+                                       off(self.p1, z0, nk), off(self.p2, z0, nk), st), "hmv_power_six")
+            n += 2
+            if overlap_d2h:
+                self.ev_chunk[ci].record()
+                self.copy_stream.wait_event(self.ev_chunk[ci])
+                with torch.cuda.stream(self.copy_stream):
+                    for q in range(6):       # one contiguous [z1-z0, nk] block per spectrum: plain async memcpys
+                        self.h_p1[q, z0:z1].copy_(self.p1[q, z0:z1], non_blocking=True)
+                        self.h_p2[q, z0:z1].copy_(self.p2[q, z0:z1], non_blocking=True)
         self._mark(6)
         if self.has_limber:
             n += self._limber(st)

@@ -147,8 +147,10 @@ int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, const double*
 int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d, const double* nzm_d,
                   const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, const double* um_d,
                   const double* ue_d, const double* Nc_d, const double* Ns_d, const double* NcNs_d,
-                  const double* NsNsm1_d, const double* ngal_d, double* ws_d, double* p1h_d, double* p2h_d,
-                  void* stream);
+                  const double* NsNsm1_d, const double* ngal_d, double* ws_d,
+                  long long spec_stride /* doubles between spectra in the outputs; 0 = nz*nk.  A caller working
+                                           through z in chunks passes the full-grid stride and offset pointers */,
+                  double* p1h_d, double* p2h_d, void* stream);
 
 /* ---- a16: Limber integral  (cosmology.py:867-904) ---------------------------------------------------
  * C_l = trapz_gz( pref[gz] * P(k=(l+1/2)/chi[gz], gz) )  (ngz>1) or pref*P (ngz==1); P by bilinear

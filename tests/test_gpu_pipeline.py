@@ -47,6 +47,13 @@ def test_gridsix_matches_golden_and_halomodel(setup):
     assert_close(p2["gm"], h.get_power_2halo("g2", "nfw"), 1e-9, name="P2h_gm")
     assert_close(ckg, h.C_kg(g["ells"], g["zs"], g["ks"], p1["gm"] + p2["gm"], gzs=0.8, lzs=2.5), 1e-9, name="C_kg")
     assert gs.launches_per_run >= 20
+    # end-to-end mode: z-chunked reduction with the device->host copies overlapped; same numbers in the pinned buffers
+    gs.h_p1.zero_(); gs.h_p2.zero_(); gs.h_cl.zero_()
+    gs.upload(); gs.run(overlap_d2h=True); gs.finish_e2e()
+    for i, tag in enumerate(pipeline.TAGS):
+        assert_close(gs.h_p1[i].numpy(), p1[tag], 0, name="e2e P1h_" + tag)
+        assert_close(gs.h_p2[i].numpy(), p2[tag], 0, name="e2e P2h_" + tag)
+    assert_close(gs.h_cl[0].numpy(), ckk, 0, name="e2e C_kk")
 
 
 class _StandInComm(object):
