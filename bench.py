@@ -186,7 +186,8 @@ def run_b200(a):
     inp = pipeline.make_inputs(zs, ms, ks, ells=ells)
     zc = zshard.ZComm(a.nz, None) if world > 1 else None
     sl = zc.slab if zc is not None else slice(0, a.nz)
-    g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs)
+    g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs,
+                         fused_nfw=a.fused_nfw)
     g.upload()
     torch.cuda.synchronize()
 
@@ -256,9 +257,14 @@ def run_b200(a):
     alg_bytes = {
         "uk_nfw": 8.0 * nzl * nm * nk,                                  # store of the cube (K2; FP64-pipe bound)
         "uk_electron": 8.0 * nzl * nm * nk,                             # store of the cube (K1; FP64-pipe bound)
-        "power_six": nzl * nk * (16.0 * nm + 96.0 + 8.0),               # read 2 cubes once, write 12 spectra, read Pzk
+        # two-cube kernel: read 2 cubes once, write 12 spectra, read Pzk.  Fused kernel: one cube + 448 B of per-halo
+        # coefficient/NFW records per (z,M) for each of the ceil(nk/512) k tiles
+        "power_six": (nzl * nk * (16.0 * nm + 96.0 + 8.0) if not g.fused_nfw else
+                      nzl * nk * (8.0 * nm + 96.0 + 8.0) + 448.0 * nzl * nm * ((g.ldk + 511) // 512)),
         "sigma2": 8.0 * (nzl * g.nks + 2.0 * g.nks * nm + nzl * nm),    # sPzk + W2 table write/read + sigma2 out
     }
+    if g.fused_nfw:
+        del alg_bytes["uk_nfw"]          # no NFW cube in the spectra-only fusion
     kernels = {}
     for name, ms_ in zip(g.STAGES, stage_ms):
         k = {"ms": float(ms_)}
@@ -298,14 +304,22 @@ def run_b200(a):
     roof.update(ms_per_launch=kernels[dom]["ms"], traffic=traffic.get(dom) if world == 1 else None,
                 fp64_dfma_peak_tflops_measured=fp64_tf, fp64_dmma_peak_tflops_measured=dmma_tf)
     # the HBM-bound kernel of the path, for reference beside the dominant one
-    roof["hbm_kernel"] = {"kernel": "power_six_kernel (K5)", "achieved": kernels["power_six"]["gbs"], "peak": hbm_peak,
+    roof["hbm_kernel"] = {"kernel": "power_six_nfw_kernel (K5+K2 fused)" if g.fused_nfw else "power_six_kernel (K5)", "achieved": kernels["power_six"]["gbs"], "peak": hbm_peak,
                           "unit": "GB/s", "frac": kernels["power_six"]["frac_hbm"],
                           "traffic": traffic.get("power_six") if world == 1 else None}
 
+    wl_bytes = 8.0 * a.nz * a.nm * a.nk * 4 + 96.0 * a.nz * a.nk      # whole C4 workload, 1.28e11 B
+    roof["workload"] = {"alg_bytes_per_step": wl_bytes, "achieved": wl_bytes / (ms_total / a.steps * 1e-3) / 1e9 / world,
+                        "peak": hbm_peak, "unit": "GB/s per GPU",
+                        "frac": wl_bytes / (ms_total / a.steps * 1e-3) / 1e9 / world / hbm_peak,
+                        "note": "SURVEY 8(d) algorithmic traffic of the whole step (2 cubes written + read once, 12 "
+                                "spectra) over the step time"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": "z-sharded x%d" % world,
+                       "nfw": "evaluated inside the mass reduction (spectra-only fusion)" if g.fused_nfw else
+                              "cube materialised in HBM",
                        "l2": "inputs exceed L2 (two %.1f GB cubes per rank)" % (8e-9 * nzl * nm * g.ldk)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": g.h2d_bytes() * world,
                     "d2h_bytes_per_step": g.d2h_bytes() * world, "ms_per_step": ms_e2e / a.steps},
@@ -333,6 +347,9 @@ def main():
     ap.add_argument("--nl", type=int, default=1000)
     ap.add_argument("--cpu-nz", type=int, default=2, help="redshifts in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fused-nfw", action="store_true",
+                    help="evaluate the NFW profile inside the mass reduction (hmv_power_six_nfw) instead of writing "
+                         "its cube to HBM and reading it back (hmv_uk_nfw + hmv_power_six, the faster default)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -60,6 +60,9 @@ _SIGS = {
     "hmv_power_ws_doubles": (_ll, [_i, _i]),
     "hmv_power": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _d, _d, C.POINTER(Tracer), C.POINTER(Tracer), _p, _p, _p, _p]),
     "hmv_power_six": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p]),
+    "hmv_power_six_nfw_ws_doubles": (_ll, [_i, _i]),
+    "hmv_power_six_nfw": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll,
+                               _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "hmv_bench_dfma": (_d, [_i, _p]),
     "hmv_bench_dmma": (_d, [_i, _p]),

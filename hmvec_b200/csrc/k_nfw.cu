@@ -13,13 +13,11 @@
 // One CTA per halo row (z,M); each warp walks 128-wide k chunks (4 elements per lane, warp-uniform term count)
 // and writes the row once, coalesced: 8 B/element of algorithmic traffic.
 #include "common.cuh"
-#include "sici.cuh"
-#include "gl64.inc"
+#include "nfw_device.cuh"
 
 namespace hmv {
 
-constexpr int NFW_T = 256, NFW_E = 8, NFW_NMAX = 42, NFW_CH = 32 * NFW_E;   // NMAX even: 16-byte aligned rows
-constexpr double NFW_XC_MAX = 16.0;
+constexpr int NFW_T = 256, NFW_E = 8, NFW_CH = 32 * NFW_E;
 
 // ---- per-halo series coefficients A[row][NFW_NMAX] ---------------------------------------------------------
 __global__ void __launch_bounds__(128) nfw_coef_kernel(long long rows, const double* __restrict__ cs,
@@ -27,64 +25,7 @@ __global__ void __launch_bounds__(128) nfw_coef_kernel(long long rows, const dou
   const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
   const double c = cs[row];
-  const double mc = log1p(c) - c / (1.0 + c);
-  double* A = coef + row * NFW_NMAX;
-  const double pref = c * c / mc;
-  if (c >= 1.5) {
-    // Ktilde_m = (1/c^(m+1)) int_0^c t^m/(1+t)^2 dt :  K_m = 1/(c^2 (m-1)) - (2/c) K_(m-1) - K_(m-2)/c^2
-    // (upward recurrence: the homogeneous solutions (-1/c)^m (a + b m) decay relative to K_m when c > 1)
-    const double ic = 1.0 / c, ic2 = ic * ic;
-    double k0 = 1.0 / (1.0 + c), k1 = mc * ic2;
-    double sf = 1.0;                      // (-1)^n / (2n+1)!
-    A[0] = pref * k1;
-    for (int n = 1; n < NFW_NMAX; ++n) {
-      const int m = 2 * n;                // even moment, then the odd one we need
-      const double ke = ic2 / (double)(m - 1) - 2.0 * ic * k1 - ic2 * k0;
-      const double ko = ic2 / (double)m - 2.0 * ic * ke - ic2 * k1;
-      k0 = ke; k1 = ko;
-      sf = -sf / ((double)(2 * n) * (double)(2 * n + 1));
-      A[n] = pref * sf * ko;
-    }
-  } else {
-    // Gauss-Legendre: node-major so that s^(2n+1) is a running product (no pow), one accumulator per moment
-    double acc[NFW_NMAX];
-#pragma unroll
-    for (int n = 0; n < NFW_NMAX; ++n) acc[n] = 0.0;
-    for (int q = 0; q < 64; ++q) {
-      const double s = c_gl64_s[q], d = 1.0 + c * s, s2 = s * s;
-      const double base = c_gl64_w[q] / (d * d);
-      double pw = s;
-#pragma unroll
-      for (int n = 0; n < NFW_NMAX; ++n) {
-        acc[n] = fma(base, pw, acc[n]);
-        pw *= s2;
-      }
-    }
-    double sf = 1.0;
-#pragma unroll
-    for (int n = 0; n < NFW_NMAX; ++n) {
-      if (n > 0) sf = -sf / ((double)(2 * n) * (double)(2 * n + 1));
-      A[n] = pref * sf * acc[n];
-    }
-  }
-}
-
-// odd term count n with y^n/(2n+1)! < 1e-19 (y = xc^2): tabulated at the low end, linear bound above
-__device__ __forceinline__ int nfw_terms(double xc) {
-  const float xf = (float)xc;
-  const int n = xf < 0.03f ? 5 : xf < 0.3f ? 7 : xf < 1.0f ? 10 : min(NFW_NMAX - 1, (int)(1.8f * xf + 10.5f));
-  return n | 1;
-}
-
-// sum_{i<n} A[i] y^i for odd n, coefficients fetched as aligned pairs
-__device__ __forceinline__ double nfw_horner(const double* __restrict__ A, int n, double y) {
-  double u = A[n - 1];
-  for (int i = n - 2; i >= 1; i -= 2) {
-    const double2 a2 = *reinterpret_cast<const double2*>(A + i - 1);
-    u = fma(u, y, a2.y);
-    u = fma(u, y, a2.x);
-  }
-  return u;
+  nfw_series_coefficients(c, log1p(c) - c / (1.0 + c), coef + row * NFW_NMAX);
 }
 
 // max of ks over each NFW_CH-wide chunk: lets both passes classify a chunk with one load

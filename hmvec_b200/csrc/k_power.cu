@@ -6,6 +6,7 @@
 // trapezoid-in-linear-M weights (folded into per-(z,M) coefficient rows by a small prep kernel), the 1-halo
 // damping, the consistency terms and P_lin.  Algorithmic traffic: 8*nm bytes per (z,k) per distinct cube read.
 #include "common.cuh"
+#include "nfw_device.cuh"
 
 namespace hmv {
 
@@ -209,6 +210,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!ok);
 }
+// producer-side wait: back off between polls so the spinning lane does not eat the consumers' issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -331,6 +342,176 @@ __global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Spectra-only fusion: the six spectra with the NFW matter profile evaluated IN the reduction instead of being read
+// from a cube.  u_NFW(k|M,z) depends on the halo only through (c, a = r_s (1+z)) and a 42-coefficient series, so a
+// 384-byte per-halo record replaces an 8*nk-byte cube row: the kernel streams only the electron cube (half the
+// HBM traffic of power_six_kernel and no 32 GB NFW store/reload) and spends the freed time in the FP64 pipe.
+//   rec[z][m][48] = { A[0..42) series coefficients, c, a, a*c, ln(1+c), 1/m_c, 0 }
+// Same ring/mbarrier structure as power_six_kernel; stage = SIX_R rows x (4 KB of u_e + 64 B coefficients + 384 B
+// NFW record).  k tiles are the slow grid dimension, highest k first: the Si/Ci-heavy tiles are scheduled first.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int NREC = 48;
+
+__global__ void __launch_bounds__(128) nfw_record_kernel(int nz, int nm, const double* __restrict__ zs,
+                                                          const double* __restrict__ cs,
+                                                          const double* __restrict__ rvir, double* __restrict__ rec) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (long long)nz * nm) return;
+  const int z = (int)(row / nm);
+  const double c = cs[row];
+  const double ln1pc = log1p(c), mc = ln1pc - c / (1.0 + c);
+  double* r = rec + row * NREC;
+  nfw_series_coefficients(c, mc, r);
+  const double a = rvir[row] / c * (1.0 + zs[z]);     // x = k * rs * (1+z), hmvec.py:342,349
+  r[42] = c; r[43] = a; r[44] = a * c; r[45] = ln1pc; r[46] = 1.0 / mc; r[47] = 0.0;
+}
+
+constexpr int FSX_NST = 6;
+constexpr int FSX_STAGE_DOUBLES = SIX_R * SIX_K + SIX_R * 8 + SIX_R * NREC;
+constexpr size_t FSX_SMEM = (size_t)FSX_NST * FSX_STAGE_DOUBLES * sizeof(double) + 2 * FSX_NST * sizeof(unsigned long long);
+
+struct FusedArgs {
+  int nz, nm, nk, ldk;
+  long long spec_stride;
+  const double *ue, *coef, *rec;
+  const double *zoff, *ks, *Pzk;
+  double kstar;
+  double *p1h, *p2h;
+};
+
+__device__ __forceinline__ double nfw_u(const double* __restrict__ r, double kk) {
+  const double xc = kk * r[44];
+  if (xc <= NFW_XC_MAX) return nfw_horner(r, nfw_terms(xc), xc * xc);
+  return nfw_bracket(kk * r[43], r[42], r[45]) * r[46];
+}
+
+constexpr int FSX_CT = 512;   // consumer threads: one k each (16 warps keep the FP64 pipe fed through the Horner chains)
+
+#define HMV_SIX1(um, ue, cp)                                                          \
+  {                                                                                   \
+    const double2 c01 = (cp)[0], c23 = (cp)[1], c45 = (cp)[2], c67 = (cp)[3];         \
+    const double q1 = um * um, q2 = ue * ue, q3 = um * ue;                            \
+    acc[0] = fma(c01.x, q1, acc[0]);                                                  \
+    acc[1] = fma(c01.x, q2, acc[1]);                                                  \
+    acc[2] = fma(c01.x, q3, acc[2]);                                                  \
+    acc[3] = fma(c01.y, um, fma(c23.x, q1, acc[3]));                                  \
+    acc[4] = fma(c23.y, um, fma(c45.x, q1, acc[4]));                                  \
+    acc[5] = fma(c23.y, ue, fma(c45.x, q3, acc[5]));                                  \
+    acc[6] = fma(c45.y, um, acc[6]);                                                  \
+    acc[7] = fma(c45.y, ue, acc[7]);                                                  \
+    acc[8] = fma(c67.x, um, acc[8]);                                                  \
+  }
+
+__global__ void __launch_bounds__(FSX_CT + 32, 1) power_six_nfw_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char six_smem[];
+  double* ring = reinterpret_cast<double*>(six_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)FSX_NST * FSX_STAGE_DOUBLES);
+  unsigned long long* empty = full + FSX_NST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.x, k0 = (gridDim.y - 1 - blockIdx.y) * SIX_K;
+  const int segk = min(SIX_K, a.ldk - k0);
+  const long long zrow = (long long)z * a.nm;
+  const int nit = (a.nm + SIX_R - 1) / SIX_R;
+  // this thread's wavenumber and the largest one of the tile (decides series vs Si/Ci per halo row for the whole CTA)
+  const int k = k0 + tid;
+  const bool active = tid < FSX_CT && k < a.nk;
+  const double kk = active ? __ldg(a.ks + k) : 0.0;
+  double kmax_tile = kk;                 // per WARP: 32 adjacent k decide series vs Si/Ci and the term count
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kmax_tile = fmax(kmax_tile, __shfl_xor_sync(0xffffffffu, kmax_tile, o));
+  if (tid == 0) {
+    for (int s = 0; s < FSX_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, FSX_CT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == FSX_CT / 32) {            // ---- producer warp ----
+    if (lane == 0) {
+      const unsigned segb = (unsigned)segk * 8u;
+      int s = 0;
+      unsigned ph = 0;
+      for (int it = 0; it < nit; ++it) {
+        mbar_wait_sleep(empty + s, ph ^ 1u);
+        const int m0 = it * SIX_R, rows = min(SIX_R, a.nm - m0);
+        double* st = ring + (size_t)s * FSX_STAGE_DOUBLES;
+        mbar_expect_tx(full + s, (unsigned)rows * (segb + 64u + NREC * 8u));
+        for (int r = 0; r < rows; ++r)
+          bulk_g2s(st + r * SIX_K, a.ue + (zrow + m0 + r) * (long long)a.ldk + k0, segb, full + s);
+        bulk_g2s(st + SIX_R * SIX_K, a.coef + (zrow + m0) * 8, (unsigned)rows * 64u, full + s);
+        bulk_g2s(st + SIX_R * SIX_K + SIX_R * 8, a.rec + (zrow + m0) * NREC, (unsigned)rows * NREC * 8u, full + s);
+        if (++s == FSX_NST) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: thread owns wavenumber k over the whole mass axis ----
+  double acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+  int s = 0;
+  unsigned ph = 0;
+  const double* st = ring;
+  for (int it = 0, mleft = a.nm; it < nit; ++it, mleft -= SIX_R) {
+    const int rows = min(SIX_R, mleft);
+    const double* recs = st + SIX_R * SIX_K + SIX_R * 8;
+    const double2* cfs = reinterpret_cast<const double2*>(st + SIX_R * SIX_K);
+    mbar_wait(full + s, ph);
+#pragma unroll 1
+    for (int r = 0; r < rows; r += 2) {
+      const double* r0 = recs + r * NREC;
+      const bool two = r + 1 < rows;
+      const double* r1 = two ? r0 + NREC : r0;
+      const double ac0 = r0[44], ac1 = r1[44];
+      double um0, um1;
+      if (kmax_tile * fmax(ac0, ac1) <= NFW_XC_MAX) {
+        // both rows are in the series regime for every k of the tile: two interleaved Horner chains with a
+        // CTA-uniform term count (set by the tile's largest k)
+        const int nt = nfw_terms(kmax_tile * fmax(ac0, ac1));
+        const double x0 = kk * ac0, x1 = kk * ac1, y0 = x0 * x0, y1 = x1 * x1;
+        um0 = r0[nt - 1]; um1 = r1[nt - 1];
+#pragma unroll 2
+        for (int i = nt - 2; i >= 1; i -= 2) {
+          const double2 a0 = *reinterpret_cast<const double2*>(r0 + i - 1);
+          const double2 a1 = *reinterpret_cast<const double2*>(r1 + i - 1);
+          um0 = fma(um0, y0, a0.y); um1 = fma(um1, y1, a1.y);
+          um0 = fma(um0, y0, a0.x); um1 = fma(um1, y1, a1.x);
+        }
+      } else {
+        um0 = nfw_u(r0, kk);
+        um1 = nfw_u(r1, kk);
+      }
+      const double ue0 = st[r * SIX_K + tid];
+      HMV_SIX1(um0, ue0, cfs + r * 4)
+      if (two) {
+        const double ue1 = st[(r + 1) * SIX_K + tid];
+        HMV_SIX1(um1, ue1, cfs + (r + 1) * 4)
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    st += FSX_STAGE_DOUBLES;
+    if (++s == FSX_NST) { s = 0; ph ^= 1u; st = ring; }
+  }
+  if (!active) return;
+  const long long S = a.spec_stride;
+  const double zo0 = a.zoff[2 * z], zo1 = a.zoff[2 * z + 1];
+  const long long o = (long long)z * a.nk + k;
+  if (a.p1h) {
+    const double r = kk / a.kstar, damp = 1.0 - exp(-r * r);          // hmvec.py:526
+#pragma unroll
+    for (int q = 0; q < 6; ++q) a.p1h[q * S + o] = acc[q] * damp;
+  }
+  if (a.p2h) {                                                         // hmvec.py:572
+    const double P = a.Pzk[o];
+    const double Lm = acc[6] + zo0, Le = acc[7] + zo0, Lg = acc[8] + zo1;
+    a.p2h[0 * S + o] = P * Lm * Lm; a.p2h[1 * S + o] = P * Le * Le; a.p2h[2 * S + o] = P * Lm * Le;
+    a.p2h[3 * S + o] = P * Lg * Lg; a.p2h[4 * S + o] = P * Lg * Lm; a.p2h[5 * S + o] = P * Lg * Le;
+  }
+}
+#undef HMV_SIX1
+
 static int tracer_args(const hmv_tracer* t, const char* which, TracerArgs* out) {
   HMV_REQUIRE(t != nullptr, "hmv_power: tracer %s is null", which);
   HMV_REQUIRE(t->kind >= 0 && t->kind <= 2, "hmv_power: tracer %s has unknown kind %d", which, t->kind);
@@ -425,4 +606,46 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
   dim3 grid(cdiv(ldk, SIX_K), nz);
   power_six_kernel<<<grid, SIX_CT + 32, SIX_SMEM, st>>>(a);
   return check_launch("power_six_kernel");
+}
+
+extern "C" long long hmv_power_six_nfw_ws_doubles(int nz, int nm) {
+  if (nz <= 0 || nm <= 0) return 0;
+  return (8LL + NREC) * nz * nm + 2LL * nz;   // coefficient records + NFW records + zoff
+}
+
+extern "C" int hmv_power_six_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ms_d,
+                                 const double* ks_d, const double* nzm_d, const double* bh_d, const double* Pzk_d,
+                                 double rho_m0, double kstar, const double* cs_d, const double* rvir_d,
+                                 const double* ue_d, const double* Nc_d, const double* Ns_d, const double* NcNs_d,
+                                 const double* NsNsm1_d, const double* ngal_d, double* ws_d, long long spec_stride,
+                                 double* p1h_d, double* p2h_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2 && nk > 0 && ldk >= nk, "hmv_power_six_nfw: bad sizes");
+  HMV_REQUIRE(nz <= 2147483647 && cdiv(ldk, SIX_K) <= 65535, "hmv_power_six_nfw: grid limit");
+  HMV_REQUIRE(zs_d && ms_d && ks_d && nzm_d && bh_d && cs_d && rvir_d && ue_d && Nc_d && Ns_d && NcNs_d && NsNsm1_d &&
+                  ngal_d && ws_d, "hmv_power_six_nfw: null pointer");
+  HMV_REQUIRE(p2h_d == nullptr || Pzk_d != nullptr, "hmv_power_six_nfw: P2h requested without Pzk");
+  HMV_REQUIRE((ldk & 1) == 0 && (((unsigned long long)ue_d | (unsigned long long)ws_d) & 15ull) == 0,
+              "hmv_power_six_nfw: cube and workspace must be 16-byte aligned with even ldk (bulk async copies)");
+  HMV_REQUIRE(spec_stride == 0 || spec_stride >= (long long)nz * nk, "hmv_power_six_nfw: spec_stride smaller than nz*nk");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cs = (long long)nz * nm;
+  double* coef = ws_d;
+  double* rec = ws_d + 8 * cs;
+  double* zoff = rec + NREC * cs;
+  power_six_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, Nc_d, Ns_d, NcNs_d, NsNsm1_d, ngal_d, coef,
+                                            zoff);
+  int rc = check_launch("power_six_prep_kernel");
+  if (rc) return rc;
+  nfw_record_kernel<<<cdiv(cs, 128), 128, 0, st>>>(nz, nm, zs_d, cs_d, rvir_d, rec);
+  rc = check_launch("nfw_record_kernel");
+  if (rc) return rc;
+  FusedArgs a;
+  a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.spec_stride = spec_stride ? spec_stride : (long long)nz * nk;
+  a.ue = ue_d; a.coef = coef; a.rec = rec; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar;
+  a.p1h = p1h_d; a.p2h = p2h_d;
+  cudaError_t e = cudaFuncSetAttribute(power_six_nfw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSX_SMEM);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_six_nfw_kernel smem opt-in (%zu B): %s", FSX_SMEM, cudaGetErrorString(e));
+  dim3 grid(nz, cdiv(ldk, SIX_K));
+  power_six_nfw_kernel<<<grid, FSX_CT + 32, FSX_SMEM, st>>>(a);
+  return check_launch("power_six_nfw_kernel");
 }

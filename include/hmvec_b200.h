@@ -152,6 +152,17 @@ int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const dou
                                            through z in chunks passes the full-grid stride and offset pointers */,
                   double* p1h_d, double* p2h_d, void* stream);
 
+/* Spectra-only fusion of a4 + a12-a14: the same six spectra with the analytic NFW matter profile (hmvec.py:346-353,
+ * from cs_d, rvir_d as in hmv_uk_nfw) evaluated inside the mass reduction instead of read from a cube; only the
+ * electron cube ue_d is streamed.  For callers that want the spectra and never look at uk_profiles['nfw'].
+ * ws_d: hmv_power_six_nfw_ws_doubles(nz,nm) doubles. */
+long long hmv_power_six_nfw_ws_doubles(int nz, int nm);
+int hmv_power_six_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ms_d, const double* ks_d,
+                      const double* nzm_d, const double* bh_d, const double* Pzk_d, double rho_m0, double kstar,
+                      const double* cs_d, const double* rvir_d, const double* ue_d, const double* Nc_d,
+                      const double* Ns_d, const double* NcNs_d, const double* NsNsm1_d, const double* ngal_d,
+                      double* ws_d, long long spec_stride, double* p1h_d, double* p2h_d, void* stream);
+
 /* ---- a16: Limber integral  (cosmology.py:867-904) ---------------------------------------------------
  * C_l = trapz_gz( pref[gz] * P(k=(l+1/2)/chi[gz], gz) )  (ngz>1) or pref*P (ngz==1); P by bilinear
  * interpolation in linear (k,z) with out-of-range coordinates clamped to the table edge. pref = H W1 W2/chi^2.

@@ -32,9 +32,11 @@ def _run(pipeline, inp, **kw):
     return gs, out
 
 
-def test_gridsix_matches_golden_and_halomodel(setup):
+@pytest.mark.parametrize("fused", [True, False])
+def test_gridsix_matches_golden_and_halomodel(setup, fused):
+    """fused=True: NFW evaluated inside the reduction (hmv_power_six_nfw); False: NFW cube materialised first."""
     g, inp, pipeline = setup
-    gs, (p1, p2, ckk, ckg) = _run(pipeline, inp)
+    gs, (p1, p2, ckk, ckg) = _run(pipeline, inp, fused_nfw=fused)
     for tag, gold in (("mm", "mm"), ("ee", "ee"), ("me", "me"), ("gg", "g2g2"), ("ge", "g2e")):
         assert_close(p1[tag], g["P1h_" + gold], 1e-6, name="P1h_" + tag)
         assert_close(p2[tag], g["P2h_" + gold], 1e-6, name="P2h_" + tag)
