@@ -73,7 +73,8 @@ __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) 
     double fX, gX, fx, gx, scx, ccx;
     sici_fg_r(rX, fX, gX);
     sici_fg_r((1.0 + c) * rX, fx, gx);     // 1/x = (1+c)/X: one reciprocal serves both arguments
-    sincos(c * x, &scx, &ccx);
+    // sincospi: exact mod-2 argument reduction (c x is O(1e3) here; the 1/pi scaling costs ~2 ulp of phase, <1e-12)
+    sincospi(c * x * M_1_PI, &scx, &ccx);
     return fX * scx - gX * ccx + gx - scx * rX;
   }
   double sx, cx, S, C;
