@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhmvec_b200.so")
 
 HMV_BISECT_MAXIT = 64
+HMV_BISECT_ROUND1 = 24      # iterations of the first bisection round (rtol 1e-4 on [7,14] needs ~19)
 
 
 class HmvError(RuntimeError):
@@ -54,7 +55,7 @@ _SIGS = {
     "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_profile_transform": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_hod": (_i, [_i, _i, _p, _p, _p, C.POINTER(_d), _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "hmv_hod_bisect": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _p, _p, _p]),
+    "hmv_hod_bisect": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_hod_pick": (_i, [_i, _p, _p, _d, _p, _p, _p]),
     "hmv_hod_solve": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _d, _p, _p, _p, _p]),
     "hmv_power_ws_doubles": (_ll, [_i, _i]),

@@ -124,17 +124,22 @@ __global__ void __launch_bounds__(HT) hod_bisect_kernel(int nm, const double* __
                                                          const double* __restrict__ ms,
                                                          const double* __restrict__ nzm,
                                                          const double* __restrict__ target, HodP hp, double ylo,
-                                                         double yhi, double rtol, double* __restrict__ ys,
-                                                         unsigned long long* __restrict__ pass) {
+                                                         double yhi, double rtol, int it0, int it1,
+                                                         const unsigned long long* __restrict__ gmask,
+                                                         double* __restrict__ ys, unsigned long long* __restrict__ pass,
+                                                         double* __restrict__ ylr) {
   extern __shared__ double sm[];
   double *tab = sm, *lmstar = tab + NTAB, *wn = lmstar + nm, *red = wn + nm;
   const int z = blockIdx.x;
+  // a continuation round has nothing to do once every redshift (of every rank) has converged in an earlier round
+  if (it0 > 0 && gmask[0] != 0ull) return;
   const Shmr s = shmr_params(zs[z]);
   stage(z, nm, ms, nzm, s, tab, lmstar, wn);
   const double x = target[z];
   double yl = ylo, yr = yhi;
   unsigned long long mask = 0ull;
-  for (int it = 0; it < HMV_BISECT_MAXIT; ++it) {
+  if (it0 > 0) { yl = ylr[2 * z]; yr = ylr[2 * z + 1]; mask = pass[z]; }
+  for (int it = it0; it < it1; ++it) {
     const double y = 0.5 * (yl + yr);                       // utils.py:27
     const SatScale sc = sat_scales(s, hp, y);
     double sn = 0.0;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(HT) hod_bisect_kernel(int nm, const double* __
     if (!(fabs(err) > rtol)) mask |= (1ull << it);          // utils.py:26
     if (threadIdx.x == 0) ys[(long long)z * HMV_BISECT_MAXIT + it] = y;
   }
-  if (threadIdx.x == 0) pass[z] = mask;
+  if (threadIdx.x == 0) { pass[z] = mask; ylr[2 * z] = yl; ylr[2 * z + 1] = yr; }
 }
 
 // AND of the per-z pass masks of this device's redshifts -> mask[0] (bit it = every local z passes at iteration it)
@@ -213,8 +218,10 @@ extern "C" int hmv_hod(int nz, int nm, const double* zs_d, const double* ms_d, c
 
 extern "C" int hmv_hod_bisect(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
                               const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
-                              double* ws_d, unsigned long long* mask_d, void* stream) {
+                              int it_begin, int it_end, double* ws_d, unsigned long long* mask_d, void* stream) {
   HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_hod_bisect: need nz>0, nm>=2");
+  HMV_REQUIRE(0 <= it_begin && it_begin < it_end && it_end <= HMV_BISECT_MAXIT,
+              "hmv_hod_bisect: iteration range [%d,%d) must lie in [0,%d]", it_begin, it_end, HMV_BISECT_MAXIT);
   HMV_REQUIRE(zs_d && ms_d && nzm_d && ngal_target_d && hodp_h && ws_d && mask_d, "hmv_hod_bisect: null pointer");
   size_t smem;
   int rc = hod_smem(nm, &smem);
@@ -224,8 +231,9 @@ extern "C" int hmv_hod_bisect(int nz, int nm, const double* zs_d, const double* 
   double* ys = ws_d;
   unsigned long long* pass = (unsigned long long*)(ws_d + (size_t)nz * HMV_BISECT_MAXIT);
   cudaStream_t st = (cudaStream_t)stream;
-  hod_bisect_kernel<<<nz, HT, smem, st>>>(nm, zs_d, ms_d, nzm_d, ngal_target_d, load_hodp(hodp_h), ylo, yhi, rtol, ys,
-                                          pass);
+  double* ylr = ws_d + (size_t)nz * (HMV_BISECT_MAXIT + 1);
+  hod_bisect_kernel<<<nz, HT, smem, st>>>(nm, zs_d, ms_d, nzm_d, ngal_target_d, load_hodp(hodp_h), ylo, yhi, rtol,
+                                          it_begin, it_end, mask_d, ys, pass, ylr);
   rc = check_launch("hod_bisect_kernel");
   if (rc) return rc;
   hod_mask_reduce_kernel<<<1, 256, 0, st>>>(nz, pass, mask_d);
@@ -245,8 +253,9 @@ extern "C" int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* m
                              const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
                              double A_log10mthresh, double* ws_d, double* log10mthresh_d, int* iters_d, void* stream) {
   HMV_REQUIRE(ws_d != nullptr, "hmv_hod_solve: null workspace");
-  unsigned long long* mask = (unsigned long long*)(ws_d + (size_t)nz * (HMV_BISECT_MAXIT + 1));
-  int rc = hmv_hod_bisect(nz, nm, zs_d, ms_d, nzm_d, ngal_target_d, hodp_h, ylo, yhi, rtol, ws_d, mask, stream);
+  unsigned long long* mask = (unsigned long long*)(ws_d + (size_t)nz * (HMV_BISECT_MAXIT + 3));
+  int rc = hmv_hod_bisect(nz, nm, zs_d, ms_d, nzm_d, ngal_target_d, hodp_h, ylo, yhi, rtol, 0, HMV_BISECT_MAXIT, ws_d,
+                          mask, stream);
   if (rc) return rc;
   return hmv_hod_pick(nz, ws_d, mask, A_log10mthresh, log10mthresh_d, iters_d, stream);
 }

@@ -379,16 +379,19 @@ class HaloModel(Cosmology):
         its midpoint and a pass bit; the answer is the midpoint of the first iteration at which EVERY redshift
         passes -- across all ranks when the z axis is sharded (one 8-byte all-reduce)."""
         nz, nm = self._nz, self._nm
-        ws = self._empty(nz * (capi.HMV_BISECT_MAXIT + 2))
+        ws = self._empty(nz * (capi.HMV_BISECT_MAXIT + 4))
         mask_d = torch.empty(1, dtype=torch.int64, device=self.device)
-        capi.check(capi.lib.hmv_hod_bisect(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d), capi.ptr(self._nzm_d),
-                                           capi.ptr(target_d), hodp,
-                                           float(pp['hod_bisection_search_min_log10mthresh']),
-                                           float(pp['hod_bisection_search_max_log10mthresh']),
-                                           float(pp['hod_bisection_search_rtol']), capi.ptr(ws),
-                                           C.c_void_p(mask_d.data_ptr()), capi.stream()), "hmv_hod_bisect")
-        if self._zcomm is not None:
-            self._zcomm.all_reduce_and(mask_d)
+        # two rounds: the usual solve converges within the first (rtol 1e-4 on [7,14] takes ~19 iterations), and the
+        # continuation returns immediately on the device when it did -- no host synchronisation in between
+        for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
+            capi.check(capi.lib.hmv_hod_bisect(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d),
+                                               capi.ptr(self._nzm_d), capi.ptr(target_d), hodp,
+                                               float(pp['hod_bisection_search_min_log10mthresh']),
+                                               float(pp['hod_bisection_search_max_log10mthresh']),
+                                               float(pp['hod_bisection_search_rtol']), it0, it1, capi.ptr(ws),
+                                               C.c_void_p(mask_d.data_ptr()), capi.stream()), "hmv_hod_bisect")
+            if self._zcomm is not None:
+                self._zcomm.all_reduce_and(mask_d)
         l10_d = self._empty(nz)
         iters_d = torch.zeros(1, dtype=torch.int32, device=self.device)
         capi.check(capi.lib.hmv_hod_pick(nz, capi.ptr(ws), C.c_void_p(mask_d.data_ptr()),

@@ -127,7 +127,7 @@ class GridSix(object):
         self.d["nfw_ws"] = E(int(capi.lib.hmv_uk_nfw_ws_doubles(nz, nm, nk)))
         self.d["tr_ws"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(nz, nm, self.nxs)))
         self.d["pow_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
-        self.d["bis_ws"] = E(nz * (capi.HMV_BISECT_MAXIT + 2))
+        self.d["bis_ws"] = E(nz * (capi.HMV_BISECT_MAXIT + 4))
         self.mask = torch.empty(1, dtype=torch.int64, device=self.device)
         self.iters = torch.zeros(1, dtype=torch.int32, device=self.device)
         # the two cubes: [nz][nm][ldk]; pad columns (if any) zeroed once, never written by the kernels
@@ -156,6 +156,7 @@ class GridSix(object):
             self.h_cl = torch.empty((2, self.nl), dtype=torch.float64).pin_memory()
         self.launches_per_run = 0
         self._ev = None
+        self._Pfull = None
         self.d2h_chunks = 5
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
@@ -228,19 +229,20 @@ class GridSix(object):
                                            ptr(self.ue), st), "hmv_profile_transform")
         n += 7
         self._mark(4)
-        capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]), self.hodp,
-                                    float(p['hod_bisection_search_min_log10mthresh']),
-                                    float(p['hod_bisection_search_max_log10mthresh']),
-                                    float(p['hod_bisection_search_rtol']), ptr(d["bis_ws"]),
-                                    C.c_void_p(self.mask.data_ptr()), st), "hmv_hod_bisect")
-        if self.zcomm is not None:
-            self.zcomm.all_reduce_and(self.mask)
+        for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
+            capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]),
+                                        self.hodp, float(p['hod_bisection_search_min_log10mthresh']),
+                                        float(p['hod_bisection_search_max_log10mthresh']),
+                                        float(p['hod_bisection_search_rtol']), it0, it1, ptr(d["bis_ws"]),
+                                        C.c_void_p(self.mask.data_ptr()), st), "hmv_hod_bisect")
+            if self.zcomm is not None:
+                self.zcomm.all_reduce_and(self.mask)
         capi.check(L.hmv_hod_pick(nz, ptr(d["bis_ws"]), C.c_void_p(self.mask.data_ptr()),
                                   float(p['hod_A_log10mthresh']), ptr(d["l10"]), ptr(self.iters), st), "hmv_hod_pick")
         capi.check(L.hmv_hod(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["l10"]), self.hodp, 0, ptr(d["nzm"]), ptr(d["bh"]),
                              ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NsNsm1"]), ptr(d["NcNs"]), ptr(d["ngal"]), ptr(d["bg"]),
                              st), "hmv_hod")
-        n += 4
+        n += 6
         self._mark(5)
         # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
         nchunk = self.d2h_chunks if overlap_d2h else 1
@@ -287,10 +289,12 @@ class GridSix(object):
         """P = P1h + P2h for mm and gm, all-gathered over z when sharded, then C_kk and C_kg (cosmology.py:536-568)."""
         L, d, ptr = capi.lib, self.d, capi.ptr
         if self.zcomm is not None:
-            # one all-gather of the four [nz_local,nk] slabs (P1h, P2h of mm and gm) -> [4, nz_total, nk]
-            P = self.zcomm.all_gather_z(torch.stack((self.p1[0], self.p2[0], self.p1[4], self.p2[4])))
-            mm1, mm2, gm1, gm2 = P[0], P[1], P[2], P[3]
-            self._Pfull = P
+            # all-gather of the four [nz_local,nk] slabs (P1h, P2h of mm and gm) straight into [4, nz_total, nk]
+            if self._Pfull is None:
+                self._Pfull = torch.empty((4, self.zs_all.numel(), self.nk), dtype=torch.float64, device=self.device)
+            for i, src in enumerate((self.p1[0], self.p2[0], self.p1[4], self.p2[4])):
+                self.zcomm.all_gather_rows(src, self._Pfull[i])
+            mm1, mm2, gm1, gm2 = self._Pfull[0], self._Pfull[1], self._Pfull[2], self._Pfull[3]
         else:
             mm1, mm2, gm1, gm2 = self.p1[0], self.p2[0], self.p1[4], self.p2[4]
         nzt = mm1.shape[0]

@@ -48,6 +48,15 @@ class ZComm(object):
         mask.copy_((bits.to(torch.int64) << sh).sum().reshape(mask.shape))
         return mask
 
+    def all_gather_rows(self, local, out):
+        """local: contiguous [nz_local, n] slab -> out: preallocated contiguous [nz_total, n], in place, no staging
+        copies when every rank owns the same number of redshifts (the usual case); otherwise via all_gather_z."""
+        if self.nz_total == self.world * self.nz_local and local.is_contiguous() and out.is_contiguous():
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        else:
+            out.copy_(self.all_gather_z(local))
+        return out
+
     def all_gather_z(self, local):
         """local: [..., nz_local, n] slab (z is dim -2) -> [..., nz_total, n] on every rank."""
         if local.shape[-2] != self.nz_local:

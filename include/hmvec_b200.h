@@ -99,16 +99,19 @@ int hmv_hod(int nz, int nm, const double* zs_d, const double* ms_d, const double
  * Reproduces the reference's all-z loop exactly: every z bisects independently for HMV_BISECT_MAXIT
  * iterations recording its midpoint and whether |x/x_target - 1| <= rtol (bit `it` of its pass mask); the
  * result is the midpoint of the first iteration at which ALL z pass.
- *   hmv_hod_bisect : runs the iterations; ws_d = nz*(HMV_BISECT_MAXIT+2) doubles (midpoints + per-z masks);
+ *   hmv_hod_bisect : runs iterations [it_begin, it_end) (first call from 0; a continuation call resumes from the
+ *                    interval state kept in ws_d and returns at once when mask_d[0] != 0, i.e. when an earlier round
+ *                    already converged everywhere -- so the usual ~20-iteration solve does not pay for 64);
+ *                    ws_d = nz*(HMV_BISECT_MAXIT+4) doubles (midpoints, per-z masks, bracket state);
  *                    mask_d[0] (uint64, device) = AND of the masks of THIS call's redshifts.
  *   (z-sharded runs AND-reduce mask_d over the ranks here -- the reference's loop condition is global in z.)
  *   hmv_hod_pick   : log10mthresh_d[z] = midpoint(z, first set bit of mask_d[0]) * A_log10mthresh;
  *                    iters_d: int32[1], the iteration count (0 = never converged within HMV_BISECT_MAXIT).
- *   hmv_hod_solve  : both steps on one device. */
+ *   hmv_hod_solve  : both steps on one device (all HMV_BISECT_MAXIT iterations in one round; same ws_d size). */
 #define HMV_BISECT_MAXIT 64
 int hmv_hod_bisect(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,
                    const double* ngal_target_d, const double* hodp_h, double ylo, double yhi, double rtol,
-                   double* ws_d, unsigned long long* mask_d, void* stream);
+                   int it_begin, int it_end, double* ws_d, unsigned long long* mask_d, void* stream);
 int hmv_hod_pick(int nz, const double* ws_d, const unsigned long long* mask_d, double A_log10mthresh,
                  double* log10mthresh_d, int* iters_d, void* stream);
 int hmv_hod_solve(int nz, int nm, const double* zs_d, const double* ms_d, const double* nzm_d,

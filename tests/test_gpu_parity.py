@@ -200,6 +200,21 @@ def test_known_answers(hm, golden_kat):
     np.testing.assert_allclose(ci.cpu().numpy(), Cc, rtol=1e-12, atol=3e-15)
 
 
+def test_bisection_continuation_round(hm, golden_mini):
+    """A tight rtol needs more iterations than the first bisection round (24): the continuation round resumes from
+    the saved brackets and must land on the same iteration count and midpoints as the reference's loop."""
+    from oracle import hmvec_oracle as orc
+    g = golden_mini
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low', skip_nfw=True)
+    h.uk_profiles["nfw"] = np.ones((g["zs"].size, g["ms"].size, g["ks"].size))
+    h.add_hod("gt", ngal=g["g2_ngal_target"], param_override={"hod_bisection_search_rtol": 1e-9})
+    o = orc.OracleHaloModel(g["zs"], g["ks"], g["ms"], params={"hod_bisect_rtol": 1e-9}, skip_nfw=True)
+    l10, iters = orc.hod_solve_mthresh(g["g2_ngal_target"], o.zs, o.ms, o.nzm, o.p)
+    assert iters > 24
+    assert h.hods["gt"]["iterations"] == iters
+    assert_close(h.hods["gt"]["log10mthresh"][:, 0], l10, 1e-12, name="log10mthresh (rtol 1e-9)")
+
+
 def test_two_halo_consistency_invariant(mini):
     """P2h(k->0) -> b1 b2 P_lin by construction of the consistency term (hmvec.py:566-572): at the lowest k the
     matter u(k) -> 1, so I - C -> 0 and P2h_mm -> Pzk."""

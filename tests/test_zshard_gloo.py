@@ -20,6 +20,9 @@ def _worker(rank, world, port, nz, q):
         ok_gather = bool(torch.equal(got, full))
         got2 = zc.all_gather_z(full[0, zc.slab].contiguous())
         ok_gather2 = bool(torch.equal(got2, full[0]))
+        out = torch.empty_like(full[1])
+        zc.all_gather_rows(full[1, zc.slab].contiguous(), out)
+        ok_gather2 = ok_gather2 and bool(torch.equal(out, full[1]))
         # rank 0 passes from iteration 3 on, rank 1 from iteration 5 on -> global first pass = iteration 5
         mask = torch.tensor([(~0) << (3 if rank == 0 else 5)], dtype=torch.int64)
         zc.all_reduce_and(mask)
