@@ -1,16 +1,20 @@
 // k_power.cu -- K5: fused 1-halo + 2-halo mass integrals (reference hmvec.py:469-572).
 //
-// HBM-bound streaming reduction over the mass axis of the u(z,M,k) cubes.  A CTA owns one redshift and a
-// 64-wide k tile (one 512-byte segment per cube row); its 8 warps split the mass axis, each lane carries two
-// adjacent k (16-byte vector loads), partial sums meet in shared memory, and the epilogue applies the
-// trapezoid-in-linear-M weights (folded into per-(z,M) coefficient rows by a small prep kernel), the 1-halo
-// damping, the consistency terms and P_lin.  Algorithmic traffic: 8*nm bytes per (z,k) per distinct cube read.
+// HBM-bound streaming reductions over the mass axis of the u(z,M,k) cubes.  A CTA owns one redshift and a 512-wide
+// k tile and walks the whole mass axis: one producer lane issues 1-D bulk async copies (cp.async.bulk -> TMA unit) of
+// a few rows of every cube it needs plus the rows' 64-byte coefficient records into a shared-memory ring tracked by
+// mbarriers; eight consumer warps read the ring, each thread owning two adjacent k for ALL masses (no cross-thread
+// reduction).  The trapezoid-in-linear-M weights, n(M,z), b(M,z) and the tracer amplitudes are folded into the
+// per-(z,M) records by a small prep kernel; the epilogue applies the 1-halo damping, the consistency terms and
+// P_lin.  Algorithmic traffic: 8*nm bytes per (z,k) per distinct cube read.
+//   power_pair_kernel      any tracer pair (matter / HOD / pressure), up to four distinct cubes
+//   power_six_kernel       {mm, ee, me, gg, gm, ge} in one pass over two cubes
+//   power_six_nfw_kernel   the same with the NFW profile evaluated in-kernel (spectra-only fusion)
 #include "common.cuh"
 #include "nfw_device.cuh"
 
 namespace hmv {
 
-constexpr int PT = 256, PW = PT / 32, KT = 64;   // threads, warps, k per tile
 
 // ---------------------------------------------------------------------------------------------------------
 // prep: per-(z,M) coefficient rows + per-z offsets
@@ -39,8 +43,7 @@ __global__ void __launch_bounds__(256) power_prep_kernel(int nm, const double* _
                                                           const double* __restrict__ nzm,
                                                           const double* __restrict__ bh, double rho_m0,
                                                           TracerArgs A, TracerArgs B, int form,
-                                                          double* __restrict__ coef, long long cstride,
-                                                          double* __restrict__ zoff) {
+                                                          double* __restrict__ coef, double* __restrict__ zoff) {
   __shared__ double red[32];
   const int z = blockIdx.x;
   double cA = 0.0, cB = 0.0, gA = 0.0, gB = 0.0;
@@ -51,17 +54,17 @@ __global__ void __launch_bounds__(256) power_prep_kernel(int nm, const double* _
     double aA, bA, tA0, aB, bB, tB0;
     leg_coeffs(A, z, i, mu, aA, bA, tA0);
     leg_coeffs(B, z, i, mu, aB, bB, tB0);
-    coef[0 * cstride + i] = aA; coef[1 * cstride + i] = bA;
-    coef[2 * cstride + i] = aB; coef[3 * cstride + i] = bB;
-    coef[5 * cstride + i] = w2;
+    double c4 = w1, c6 = 0.0;
     if (form == 1) {            // hmvec.py:477-479
       const double ig = 1.0 / A.ngal[z], ig2 = ig * ig;
-      coef[4 * cstride + i] = w1 * 2.0 * A.NcNs[i] * ig2;
-      coef[6 * cstride + i] = w1 * A.NsNsm1[i] * ig2;
-    } else {
-      coef[4 * cstride + i] = w1;
-      coef[6 * cstride + i] = 0.0;
+      c4 = w1 * 2.0 * A.NcNs[i] * ig2;
+      c6 = w1 * A.NsNsm1[i] * ig2;
     }
+    double2* rec = reinterpret_cast<double2*>(coef + i * 8);     // 64-byte record per (z,M): one bulk copy per stage
+    rec[0] = make_double2(aA, bA);
+    rec[1] = make_double2(aB, bB);
+    rec[2] = make_double2(c4, w2);
+    rec[3] = make_double2(c6, 0.0);
     cA = fma(w2, tA0, cA);      // consistency integrals (hmvec.py:567-568)
     cB = fma(w2, tB0, cB);
     if (A.kind == 1) gA = fma(w2, A.Nc[i] + A.Ns[i], gA);   // get_bg numerator (hmvec.py:465)
@@ -78,71 +81,140 @@ __global__ void __launch_bounds__(256) power_prep_kernel(int nm, const double* _
   }
 }
 
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// producer-side wait: back off between polls so the spinning lane does not eat the consumers' issue slots
+__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Generic tracer pair on the same TMA ring as power_six_kernel: up to four distinct cubes (us_A, uc_A, us_B, uc_B,
+// de-duplicated by pointer) are streamed once; a stage holds PR_R rows of every cube plus the rows' 64-byte records.
+constexpr int PR_K = 512, PR_R = 4, PR_CT = 256;
+
 struct PairArgs {
-  int nm, nk, ldk, form;
-  const double *usA, *ucA, *usB, *ucB;   // cubes (uc may be null => 1)
+  int nm, nk, ldk, form, ncube, nst;
+  const double* cube[4];
+  int rusA, rucA, rusB, rucB;            // index into cube[] of each role; -1 = the profile is identically 1
   const double* coef;
-  long long cstride;
   const double *zoff, *ks, *Pzk;
   double kstar;
   double *p1h, *p2h;
 };
 
-__device__ __forceinline__ double2 ld2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
-
-__global__ void __launch_bounds__(PT) power_pair_kernel(const PairArgs a) {
-  __shared__ double part[PW][3][KT];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int z = blockIdx.y, k0 = blockIdx.x * KT + 2 * lane;
-  const bool active = k0 < a.ldk;      // ldk is even: a full double2 is always in-bounds of the padded row
+__global__ void __launch_bounds__(PR_CT + 32, 1) power_pair_kernel(const PairArgs a) {
+  extern __shared__ __align__(128) unsigned char pair_smem[];
+  const int stage_doubles = a.ncube * PR_R * PR_K + PR_R * 8;
+  double* ring = reinterpret_cast<double*>(pair_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)a.nst * stage_doubles);
+  unsigned long long* empty = full + a.nst;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.y, k0 = blockIdx.x * PR_K;
+  const int segk = min(PR_K, a.ldk - k0);
   const long long zrow = (long long)z * a.nm;
-  const double* cf = a.coef + zrow;
-  const bool sameUS = (a.usB == a.usA), hasUCA = (a.ucA != nullptr), hasUCB = (a.ucB != nullptr);
-  const bool sameUC = (a.ucB == a.ucA);
-  double2 p1 = {0, 0}, iA = {0, 0}, iB = {0, 0};
-  if (active) {
-#pragma unroll 4
-    for (int m = w; m < a.nm; m += PW) {
-      const long long off = (zrow + m) * (long long)a.ldk + k0;
-      const double2 usA = ld2(a.usA + off);
-      double2 ucA = {1.0, 1.0}, usB = usA, ucB = {1.0, 1.0};
-      if (hasUCA) ucA = ld2(a.ucA + off);
-      if (!sameUS) usB = ld2(a.usB + off);
-      if (hasUCB) ucB = sameUC ? ucA : ld2(a.ucB + off);
-      const double aA = __ldg(cf + m), bA = __ldg(cf + a.cstride + m);
-      const double aB = __ldg(cf + 2 * a.cstride + m), bB = __ldg(cf + 3 * a.cstride + m);
-      const double c4 = __ldg(cf + 4 * a.cstride + m), w2 = __ldg(cf + 5 * a.cstride + m);
-      double2 tA, tB;
-      tA.x = fma(aA, ucA.x, bA * usA.x); tA.y = fma(aA, ucA.y, bA * usA.y);
-      tB.x = fma(aB, ucB.x, bB * usB.x); tB.y = fma(aB, ucB.y, bB * usB.y);
-      if (a.form == 0) {
-        p1.x = fma(c4 * tA.x, tB.x, p1.x); p1.y = fma(c4 * tA.y, tB.y, p1.y);
-      } else {
-        const double c6 = __ldg(cf + 6 * a.cstride + m);
-        p1.x = fma(usA.x, fma(c4, ucA.x, c6 * usA.x), p1.x);
-        p1.y = fma(usA.y, fma(c4, ucA.y, c6 * usA.y), p1.y);
-      }
-      iA.x = fma(w2, tA.x, iA.x); iA.y = fma(w2, tA.y, iA.y);
-      iB.x = fma(w2, tB.x, iB.x); iB.y = fma(w2, tB.y, iB.y);
-    }
+  const int nit = (a.nm + PR_R - 1) / PR_R;
+  if (tid == 0) {
+    for (int s = 0; s < a.nst; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, PR_CT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  part[w][0][2 * lane] = p1.x; part[w][0][2 * lane + 1] = p1.y;
-  part[w][1][2 * lane] = iA.x; part[w][1][2 * lane + 1] = iA.y;
-  part[w][2][2 * lane] = iB.x; part[w][2][2 * lane + 1] = iB.y;
   __syncthreads();
-  if (threadIdx.x < KT) {
-    const int k = blockIdx.x * KT + threadIdx.x;
-    if (k < a.nk) {
-      double s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-      for (int ww = 0; ww < PW; ++ww) { s0 += part[ww][0][threadIdx.x]; s1 += part[ww][1][threadIdx.x]; s2 += part[ww][2][threadIdx.x]; }
-      const long long o = (long long)z * a.nk + k;
-      if (a.p1h) {
-        const double r = a.ks[k] / a.kstar;
-        a.p1h[o] = s0 * (1.0 - exp(-r * r));                                   // hmvec.py:526
+
+  if (warp == PR_CT / 32) {            // ---- producer warp ----
+    if (lane == 0) {
+      const unsigned segb = (unsigned)segk * 8u;
+      int s = 0;
+      unsigned ph = 0;
+      for (int it = 0; it < nit; ++it) {
+        mbar_wait(empty + s, ph ^ 1u);
+        const int m0 = it * PR_R, rows = min(PR_R, a.nm - m0);
+        double* st = ring + (size_t)s * stage_doubles;
+        mbar_expect_tx(full + s, (unsigned)rows * ((unsigned)a.ncube * segb + 64u));
+        for (int c = 0; c < a.ncube; ++c)
+          for (int r = 0; r < rows; ++r)
+            bulk_g2s(st + (c * PR_R + r) * PR_K, a.cube[c] + (zrow + m0 + r) * (long long)a.ldk + k0, segb, full + s);
+        bulk_g2s(st + a.ncube * PR_R * PR_K, a.coef + (zrow + m0) * 8, (unsigned)rows * 64u, full + s);
+        if (++s == a.nst) { s = 0; ph ^= 1u; }
       }
-      if (a.p2h) a.p2h[o] = a.Pzk[o] * (s1 + a.zoff[2 * z]) * (s2 + a.zoff[2 * z + 1]);   // hmvec.py:572
     }
+    return;
+  }
+
+  const bool active = 2 * tid < segk;
+  double2 p1 = {0, 0}, iA = {0, 0}, iB = {0, 0};
+  const double2 one = make_double2(1.0, 1.0);
+  int s = 0;
+  unsigned ph = 0;
+  for (int it = 0; it < nit; ++it) {
+    const int rows = min(PR_R, a.nm - it * PR_R);
+    const double* st = ring + (size_t)s * stage_doubles;
+    mbar_wait(full + s, ph);
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < PR_R; ++r) {
+        if (r < rows) {
+          auto ld = [&](int role) { return *reinterpret_cast<const double2*>(st + (role * PR_R + r) * PR_K + 2 * tid); };
+          const double2 usA = ld(a.rusA);
+          const double2 ucA = a.rucA >= 0 ? ld(a.rucA) : one;
+          const double2 usB = a.rusB == a.rusA ? usA : ld(a.rusB);
+          const double2 ucB = a.rucB >= 0 ? (a.rucB == a.rucA ? ucA : ld(a.rucB)) : one;
+          const double2* c = reinterpret_cast<const double2*>(st + a.ncube * PR_R * PR_K + r * 8);
+          const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+          const double aA = c01.x, bA = c01.y, aB = c23.x, bB = c23.y, c4 = c45.x, w2 = c45.y, c6 = c67.x;
+          double2 tA, tB;
+          tA.x = fma(aA, ucA.x, bA * usA.x); tA.y = fma(aA, ucA.y, bA * usA.y);
+          tB.x = fma(aB, ucB.x, bB * usB.x); tB.y = fma(aB, ucB.y, bB * usB.y);
+          if (a.form == 0) {
+            p1.x = fma(c4 * tA.x, tB.x, p1.x); p1.y = fma(c4 * tA.y, tB.y, p1.y);
+          } else {
+            p1.x = fma(usA.x, fma(c4, ucA.x, c6 * usA.x), p1.x);
+            p1.y = fma(usA.y, fma(c4, ucA.y, c6 * usA.y), p1.y);
+          }
+          iA.x = fma(w2, tA.x, iA.x); iA.y = fma(w2, tA.y, iA.y);
+          iB.x = fma(w2, tB.x, iB.x); iB.y = fma(w2, tB.y, iB.y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    if (++s == a.nst) { s = 0; ph ^= 1u; }
+  }
+  if (!active) return;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + 2 * tid + e;
+    if (k >= a.nk) break;
+    const long long o = (long long)z * a.nk + k;
+    if (a.p1h) {
+      const double r = a.ks[k] / a.kstar;
+      a.p1h[o] = (e ? p1.y : p1.x) * (1.0 - exp(-r * r));                                   // hmvec.py:526
+    }
+    if (a.p2h) a.p2h[o] = a.Pzk[o] * ((e ? iA.y : iA.x) + a.zoff[2 * z]) * ((e ? iB.y : iB.x) + a.zoff[2 * z + 1]);   // hmvec.py:572
   }
 }
 
@@ -190,39 +262,6 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
     zoff[2 * z + 0] = 1.0 - cm;
     zoff[2 * z + 1] = gb * ig - cg + gc;   // bias - consistency + the k-independent central part of I_g
   }
-}
-
-// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ----------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-// producer-side wait: back off between polls so the spinning lane does not eat the consumers' issue slots
-__device__ __forceinline__ void mbar_wait_sleep(unsigned long long* bar, unsigned parity) {
-  unsigned ok;
-  for (;;) {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) break;
-    __nanosleep(64);
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 constexpr int SIX_K = 512, SIX_R = 4, SIX_NST = 6, SIX_CT = 256;   // k per CTA, rows per stage, stages, consumers
@@ -536,7 +575,8 @@ extern "C" int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, co
                          const hmv_tracer* A, const hmv_tracer* B, double* ws_d, double* p1h_d, double* p2h_d,
                          void* stream) {
   HMV_REQUIRE(nz > 0 && nm >= 2 && nk > 0 && ldk >= nk, "hmv_power: bad sizes (nz=%d nm=%d nk=%d ldk=%d)", nz, nm, nk, ldk);
-  HMV_REQUIRE((ldk & 1) == 0, "hmv_power: ldk must be even (16-byte vector loads); got %d", ldk);
+  HMV_REQUIRE((ldk & 1) == 0 && ((unsigned long long)ws_d & 15ull) == 0,
+              "hmv_power: ldk must be even and the workspace 16-byte aligned (bulk async copies); ldk=%d", ldk);
   HMV_REQUIRE(nz <= 65535, "hmv_power: nz=%d exceeds grid.y limit 65535", nz);
   HMV_REQUIRE(ms_d && ks_d && nzm_d && bh_d && ws_d, "hmv_power: null pointer");
   HMV_REQUIRE(p2h_d == nullptr || Pzk_d != nullptr, "hmv_power: P2h requested without Pzk");
@@ -551,28 +591,46 @@ extern "C" int hmv_power(int nz, int nm, int nk, int ldk, const double* ms_d, co
   double* zoff = ws_d + 8 * cs;
   int form = 0;
   if (A->kind == 1 && B->kind == 1) form = 1;            // hmvec.py:510-511 (uses leg A's HOD only)
-  power_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, ta, tb, form, coef, cs, zoff);
+  power_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, ta, tb, form, coef, zoff);
   rc = check_launch("power_prep_kernel");
   if (rc) return rc;
   PairArgs a;
   a.nm = nm; a.nk = nk; a.ldk = ldk; a.form = form;
-  a.usA = A->us_d; a.ucA = A->uc_d; a.usB = B->us_d; a.ucB = B->uc_d;
-  a.coef = coef; a.cstride = cs; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar;
+  a.coef = coef; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar;
   a.p1h = p1h_d; a.p2h = p2h_d;
-  dim3 grid(cdiv(nk, KT), nz);
+  auto launch = [&](const double* usA, const double* ucA, const double* usB, const double* ucB, PairArgs q) -> int {
+    q.ncube = 0;
+    auto role = [&](const double* ptr) -> int {
+      if (!ptr) return -1;
+      for (int c = 0; c < q.ncube; ++c)
+        if (q.cube[c] == ptr) return c;
+      q.cube[q.ncube] = ptr;
+      return q.ncube++;
+    };
+    q.rusA = role(usA); q.rucA = role(ucA); q.rusB = role(usB); q.rucB = role(ucB);
+    for (int c = 0; c < q.ncube; ++c)
+      if ((unsigned long long)q.cube[c] & 15ull) return fail(HMV_E_ARG, "hmv_power: cubes must be 16-byte aligned");
+    const size_t stage = ((size_t)q.ncube * PR_R * PR_K + PR_R * 8) * sizeof(double);
+    q.nst = (int)((200 * 1024) / stage);
+    if (q.nst > 6) q.nst = 6;
+    const size_t smem = q.nst * stage + 2 * q.nst * sizeof(unsigned long long);
+    cudaError_t e = cudaFuncSetAttribute(power_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_pair_kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+    dim3 grid(cdiv(ldk, PR_K), nz);
+    power_pair_kernel<<<grid, PR_CT + 32, smem, st>>>(q);
+    return check_launch("power_pair_kernel");
+  };
   if (A->kind == 2 && B->kind == 2 && A->us_d != B->us_d && p1h_d) {
     // both pressure: the 1h integrand is pk_A^2 (hmvec.py:512-513) while the 2h legs stay A and B.
-    // Leg-B coefficient rows equal leg A's for pressure (a=0, b=1), so one prep serves both passes.
+    // Leg-B coefficient records equal leg A's for pressure (a=0, b=1), so one prep serves both passes.
     PairArgs a1 = a;
-    a1.usB = A->us_d; a1.ucB = A->uc_d; a1.p2h = nullptr;
-    power_pair_kernel<<<grid, PT, 0, st>>>(a1);
-    rc = check_launch("power_pair_kernel(1h)");
+    a1.p2h = nullptr;
+    rc = launch(A->us_d, A->uc_d, A->us_d, A->uc_d, a1);
     if (rc) return rc;
     a.p1h = nullptr;
     if (!p2h_d) return HMV_OK;
   }
-  power_pair_kernel<<<grid, PT, 0, st>>>(a);
-  return check_launch("power_pair_kernel");
+  return launch(A->us_d, A->uc_d, B->us_d, B->uc_d, a);
 }
 
 extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d,
