@@ -189,23 +189,23 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
       const int warp = tid >> 5, lane = tid & 31;
       const int ntile = (jn + 7) >> 3;
       for (int t0 = 0; t0 < ntile;) {
-        const int per = (ntile - t0 + NW - 1) / NW;
-        const int jw = 1 + 8 * (t0 + warp * ((per > 4 && MAXNJ >= 8) ? 8 : per > 2 ? 4 : per > 1 ? 2 : 1));
-        if (per > 4 && MAXNJ >= 8) {
-          if constexpr (MAXNJ >= 8) {
-            if (jw <= jn) accum_mma<8>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
+        const int per = (ntile - t0 + NW - 1) / NW;        // tiles each warp still has to take
+        // NT in {1,2,3,4,6,8}: the smallest allowed count >= per (capped by MAXNJ), so that the last pass is not
+        // padded to the next power of two
+        const int nt = per >= 7 ? 8 : per >= 5 ? 6 : per;
+        const int ntc = nt > MAXNJ ? MAXNJ : nt;
+        const int jw = 1 + 8 * (t0 + warp * ntc);
+        if (jw <= jn) {
+          switch (ntc) {
+            case 8: if constexpr (MAXNJ >= 8) accum_mma<8>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
+            case 6: if constexpr (MAXNJ >= 8) accum_mma<6>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
+            case 4: accum_mma<4>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
+            case 3: accum_mma<3>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
+            case 2: accum_mma<2>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
+            default: accum_mma<1>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane); break;
           }
-          t0 += 8 * NW;
-        } else if (per > 2) {
-          if (jw <= jn) accum_mma<4>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
-          t0 += 4 * NW;
-        } else if (per > 1) {
-          if (jw <= jn) accum_mma<2>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
-          t0 += 2 * NW;
-        } else {
-          if (jw <= jn) accum_mma<1>(T, gs, Us, p.JS, p.N, n0, nlen, jw, jn, lane);
-          t0 += NW;
         }
+        t0 += ntc * NW;
       }
     } else {
       for (int j = tid + 1; j <= jn; j += TT) {
