@@ -71,6 +71,10 @@ class DeviceCubes(MutableMapping):
         t[..., :o._nk] = arr.to(o.device)
         self._t[name] = t
 
+    def __contains__(self, name):
+        # Mapping's default would call __getitem__, i.e. download a whole cube, just to test membership
+        return name in self._t
+
     def __delitem__(self, name):
         del self._t[name]
 

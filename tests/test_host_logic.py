@@ -77,3 +77,19 @@ def test_device_ops_fail_loudly_without_gpu(cosmo):
         warnings.simplefilter("ignore")
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             HaloModel(np.array([0.1]), np.geomspace(1e-3, 1, 8), ms=np.geomspace(1e12, 1e14, 4), accuracy='low')
+
+
+def test_profile_dict_membership_does_not_download():
+    """`name in hm.uk_profiles` / `.keys()` are what add_hod and get_power use to classify tracers; they must not
+    trigger DeviceCubes.__getitem__ (a 32 GB device->host copy per test on the LARGE grid)."""
+    from hmvec_b200.hmvec import DeviceCubes
+
+    class Boom(DeviceCubes):
+        def __getitem__(self, name):
+            raise AssertionError("membership test downloaded a cube")
+
+    dc = Boom(owner=None)
+    dc._t["nfw"] = object()
+    assert "nfw" in dc and "electron" not in dc
+    assert "nfw" in dc.keys() and "electron" not in dc.keys()
+    assert list(dc) == ["nfw"] and len(dc) == 1
