@@ -227,7 +227,7 @@ class GridSix(object):
                                            ptr(d["cmax"]), ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]),
                                            ptr(d["oscale"]), self.gamma, self.xmax, self.nxs, 1, ptr(d["tr_ws"]),
                                            ptr(self.ue), st), "hmv_profile_transform")
-        n += 7
+        n += 8    # mdelta, gnfw_params, sine_table, bin_count, four bin-count classes
         self._mark(4)
         for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
             capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]),
@@ -261,7 +261,7 @@ class GridSix(object):
                                                off(d["Nc"], z0, nm), off(d["Ns"], z0, nm), off(d["NcNs"], z0, nm),
                                                off(d["NsNsm1"], z0, nm), off(d["ngal"], z0, 1), ptr(d["pow_ws"]), S,
                                                off(self.p1, z0, nk), off(self.p2, z0, nk), st), "hmv_power_six_nfw")
-                n += 1
+                n += 3
             else:
                 capi.check(L.hmv_power_six(z1 - z0, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), off(d["nzm"], z0, nm),
                                            off(d["bh"], z0, nm), off(d["Pzk"], z0, nk), self.rho_m0,
