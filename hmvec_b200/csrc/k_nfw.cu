@@ -19,15 +19,6 @@ namespace hmv {
 
 constexpr int NFW_T = 256, NFW_E = 8, NFW_CH = 32 * NFW_E;
 
-// ---- per-halo series coefficients A[row][NFW_NMAX] ---------------------------------------------------------
-__global__ void __launch_bounds__(128) nfw_coef_kernel(long long rows, const double* __restrict__ cs,
-                                                        double* __restrict__ coef) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  const double c = cs[row];
-  nfw_series_coefficients(c, log1p(c) - c / (1.0 + c), coef + row * NFW_NMAX);
-}
-
 // max of ks over each NFW_CH-wide chunk: lets both passes classify a chunk with one load
 __global__ void nfw_chunkmax_kernel(int nk, const double* __restrict__ ks, double* __restrict__ kcmax) {
   const int chunk = blockIdx.x, lane = threadIdx.x;
@@ -42,24 +33,19 @@ __global__ void nfw_chunkmax_kernel(int nk, const double* __restrict__ ks, doubl
 // remaining chunks (some element with x c > 16), which need the Si/Ci routines -- a separate instantiation so that
 // their register footprint does not cap the occupancy of the series pass.
 template <bool TAIL>
-__global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nm, int nk, int ldk, const double* __restrict__ zs,
-                                                        const double* __restrict__ ks,
-                                                        const double* __restrict__ cs,
-                                                        const double* __restrict__ rvir,
+__global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nk, int ldk, const double* __restrict__ ks,
                                                         const double* __restrict__ coef,
                                                         const double* __restrict__ kcmax, double kmax,
                                                         double* __restrict__ uk) {
-  __shared__ __align__(16) double A[NFW_NMAX];
+  __shared__ __align__(16) double A[NFW_NREC];
   const long long row = blockIdx.x;                   // row = z*nm + m
-  const int z = (int)(row / nm);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double c = cs[row];
-  const double a = rvir[row] / c * (1.0 + zs[z]);     // x = k * rs * (1+z), hmvec.py:342,349
-  const double ac = a * c;
+  const double* rec = coef + row * NFW_NREC;
+  const double ac = __ldg(rec + 44);
   if (TAIL) {   // rows whose whole k-range is in the series regime have nothing to do here
     if (kmax * ac <= NFW_XC_MAX) return;
   }
-  if (threadIdx.x < NFW_NMAX) A[threadIdx.x] = coef[row * NFW_NMAX + threadIdx.x];
+  if (threadIdx.x < NFW_NREC) A[threadIdx.x] = __ldg(rec + threadIdx.x);
   __syncthreads();
   double* out = uk + row * (long long)ldk;
   const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
@@ -95,8 +81,7 @@ __global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nm, int
     // every warp visits every tail chunk and takes its own 32-wide slice of it: the Si/Ci work of a row is spread
     // evenly over the CTA's warps however few chunks are in the tail
     static_assert(NFW_T / 32 == NFW_E, "one slice per warp");
-    const double ln1pc = log1p(c);
-    const double inv_mc = 1.0 / (ln1pc - c / (1.0 + c));  // hmvec.py:348
+    const double c = A[42], a = A[43], ln1pc = A[45], inv_mc = A[46];
     for (int cb = 0; cb < nchunks; cb += 32) {        // 32 chunks per ballot: visit only the tail chunks
       const int cc = cb + lane;
       unsigned tail = __ballot_sync(0xffffffffu, cc < nchunks && __ldg(kcmax + min(cc, nchunks - 1)) * ac > NFW_XC_MAX);
@@ -124,7 +109,7 @@ using namespace hmv;
 
 extern "C" long long hmv_uk_nfw_ws_doubles(int nz, int nm, int nk) {
   if (nz <= 0 || nm <= 0 || nk <= 0) return 0;
-  return (long long)nz * nm * NFW_NMAX + (nk + NFW_CH - 1) / NFW_CH;   // series coefficients + per-chunk max(k)
+  return (long long)nz * nm * NFW_NREC + (nk + NFW_CH - 1) / NFW_CH;   // per-halo records + per-chunk max(k)
 }
 
 extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
@@ -135,17 +120,17 @@ extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, c
   const long long rows = (long long)nz * nm;
   if (rows > 2147483647LL) return fail(HMV_E_LIMIT, "hmv_uk_nfw: %lld halo rows exceed the 2^31-1 grid limit", rows);
   cudaStream_t st = (cudaStream_t)stream;
-  nfw_coef_kernel<<<cdiv(rows, 128), 128, 0, st>>>(rows, cs_d, ws_d);
-  int rc = check_launch("nfw_coef_kernel");
+  nfw_record_kernel<<<cdiv(rows, 128), 128, 0, st>>>(nz, nm, zs_d, cs_d, rvir_d, ws_d);
+  int rc = check_launch("nfw_record_kernel");
   if (rc) return rc;
-  double* kcmax = ws_d + rows * NFW_NMAX;
+  double* kcmax = ws_d + rows * NFW_NREC;
   nfw_chunkmax_kernel<<<(nk + NFW_CH - 1) / NFW_CH, 32, 0, st>>>(nk, ks_d, kcmax);
   rc = check_launch("nfw_chunkmax_kernel");
   if (rc) return rc;
-  uk_nfw_kernel<false><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kcmax, kmax, uk_d);
+  uk_nfw_kernel<false><<<(unsigned)rows, NFW_T, 0, st>>>(nk, ldk, ks_d, ws_d, kcmax, kmax, uk_d);
   rc = check_launch("uk_nfw_kernel<series>");
   if (rc) return rc;
-  uk_nfw_kernel<true><<<(unsigned)rows, NFW_T, 0, st>>>(nm, nk, ldk, zs_d, ks_d, cs_d, rvir_d, ws_d, kcmax, kmax, uk_d);
+  uk_nfw_kernel<true><<<(unsigned)rows, NFW_T, 0, st>>>(nk, ldk, ks_d, ws_d, kcmax, kmax, uk_d);
   return check_launch("uk_nfw_kernel<tail>");
 }
 

@@ -390,21 +390,7 @@ __global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs
 // Same ring/mbarrier structure as power_six_kernel; stage = SIX_R rows x (4 KB of u_e + 64 B coefficients + 384 B
 // NFW record).  k tiles are the slow grid dimension, highest k first: the Si/Ci-heavy tiles are scheduled first.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NREC = 48;
-
-__global__ void __launch_bounds__(128) nfw_record_kernel(int nz, int nm, const double* __restrict__ zs,
-                                                          const double* __restrict__ cs,
-                                                          const double* __restrict__ rvir, double* __restrict__ rec) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (long long)nz * nm) return;
-  const int z = (int)(row / nm);
-  const double c = cs[row];
-  const double ln1pc = log1p(c), mc = ln1pc - c / (1.0 + c);
-  double* r = rec + row * NREC;
-  nfw_series_coefficients(c, mc, r);
-  const double a = rvir[row] / c * (1.0 + zs[z]);     // x = k * rs * (1+z), hmvec.py:342,349
-  r[42] = c; r[43] = a; r[44] = a * c; r[45] = ln1pc; r[46] = 1.0 / mc; r[47] = 0.0;
-}
+constexpr int NREC = NFW_NREC;
 
 constexpr int FSX_NST = 6;
 constexpr int FSX_STAGE_DOUBLES = SIX_R * SIX_K + SIX_R * 8 + SIX_R * NREC;

@@ -7,7 +7,8 @@
 
 namespace hmv {
 
-constexpr int NFW_NMAX = 42;             // series coefficients per halo (even: 16-byte aligned rows)
+constexpr int NFW_NMAX = 42;             // series coefficients per halo
+constexpr int NFW_NREC = 48;             // doubles per halo record: A[0..42), c, a = r_s (1+z), a*c, ln(1+c), 1/m_c, 0
 constexpr double NFW_XC_MAX = 16.0;      // series regime: x c <= 16
 
 // A[0..NFW_NMAX): u_NFW(x; c) = sum_n A[n] (x c)^(2n), A_n = (-1)^n c^2 Itilde_n / ((2n+1)! m_c)
@@ -50,6 +51,22 @@ __device__ __forceinline__ void nfw_series_coefficients(double c, double mc, dou
       A[n] = pref * sf * acc[n];
     }
   }
+}
+
+// per-halo NFW record rec[row][NFW_NREC] (row = z*nm + m): everything a kernel needs to evaluate u_NFW(k) for that halo
+static __global__ void __launch_bounds__(128) nfw_record_kernel(int nz, int nm, const double* __restrict__ zs,
+                                                                 const double* __restrict__ cs,
+                                                                 const double* __restrict__ rvir,
+                                                                 double* __restrict__ rec) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (long long)nz * nm) return;
+  const int z = (int)(row / nm);
+  const double c = cs[row];
+  const double ln1pc = log1p(c), mc = ln1pc - c / (1.0 + c);        // hmvec.py:348
+  double* r = rec + row * NFW_NREC;
+  nfw_series_coefficients(c, mc, r);
+  const double a = rvir[row] / c * (1.0 + zs[z]);                     // x = k * rs * (1+z), hmvec.py:342,349
+  r[42] = c; r[43] = a; r[44] = a * c; r[45] = ln1pc; r[46] = 1.0 / mc; r[47] = 0.0;
 }
 
 // odd term count n with y^n/(2n+1)! < 1e-19 (y = xc^2): tabulated at the low end, linear bound above

@@ -21,6 +21,29 @@ __device__ __forceinline__ void sici_series(double z, double& S, double& C) {
   C = c;
 }
 
+// sin and cos of 0 <= x < ~1e6 for the Si/Ci tail (x = c k r_s(1+z) reaches ~1e4): two-constant Cody-Waite
+// reduction by pi/2 with FMAs, then the kernels sin r = r PS(r^2), cos r = PC(r^2) on |r| <= pi/4 (own Chebyshev
+// fits, 1.1e-16 absolute; tools/gen_sici_tables.py).  About 30 instructions; CUDA's sincospi costs ~80 here
+// because it also serves huge and special arguments.
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+  const double q = rint(x * 0.63661977236758134308);           // x * 2/pi
+  double r = fma(-q, 1.5707963267948966, x);                   // pi/2 = hi + lo
+  r = fma(-q, 6.123233995736766e-17, r);
+  const int iq = (int)q;
+  const double w = r * r;
+  double ps = c_sin_k[7], pc = c_cos_k[8];
+#pragma unroll
+  for (int i = 6; i >= 0; --i) ps = fma(ps, w, c_sin_k[i]);
+#pragma unroll
+  for (int i = 7; i >= 0; --i) pc = fma(pc, w, c_cos_k[i]);
+  const double sr = r * ps;
+  double s0 = (iq & 1) ? pc : sr;
+  double c0 = (iq & 1) ? -sr : pc;
+  if (iq & 2) { s0 = -s0; c0 = -c0; }
+  sn = s0;
+  cs = c0;
+}
+
 // f(x), g(x) for x > 4 from the reciprocal rx = 1/x:  Si = pi/2 - f cos x - g sin x,  Ci = f sin x - g cos x.
 // s = 16/x^2 in (0,1] is cut into HMV_SICI_NSEG uniform segments (index = one multiply + float->int); each holds
 // degree-HMV_SICI_DEG polynomials for F = x f and G = x^2 g whose coefficient pairs are read as double2 (L1).
@@ -73,8 +96,7 @@ __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) 
     double fX, gX, fx, gx, scx, ccx;
     sici_fg_r(rX, fX, gX);
     sici_fg_r((1.0 + c) * rX, fx, gx);     // 1/x = (1+c)/X: one reciprocal serves both arguments
-    // sincospi: exact mod-2 argument reduction (c x is O(1e3) here; the 1/pi scaling costs ~2 ulp of phase, <1e-12)
-    sincospi(c * x * M_1_PI, &scx, &ccx);
+    sincos_cw(c * x, scx, ccx);
     return fX * scx - gX * ccx + gx - scx * rX;
   }
   double sx, cx, S, C;

@@ -76,6 +76,18 @@ def cheb_monomial(fun, a, b, deg):
     return mono
 
 
+def cheb_to_plain(fun, a, b, deg):
+    """Chebyshev interpolant of fun on [a,b] as plain monomial coefficients in the ORIGINAL variable."""
+    mono_u = cheb_monomial(fun, a, b, deg)            # in u = (w - mid)/half
+    mid, half = (mp.mpf(a) + mp.mpf(b)) / 2, (mp.mpf(b) - mp.mpf(a)) / 2
+    out = [mp.mpf(0)] * (deg + 1)
+    # expand sum_i m_i ((w-mid)/half)^i
+    for i, m in enumerate(mono_u):
+        for k in range(i + 1):
+            out[k] += m * mp.binomial(i, k) * (-mid) ** (i - k) / half ** i
+    return out
+
+
 def horner(co, u):
     r = np.zeros_like(u) + co[-1]
     for c in co[-2::-1]:
@@ -111,6 +123,17 @@ def main():
     worst["Ci"] = np.max(np.abs(ci - cie))  # absolute (Ci crosses zero near 0.6165)
     print("max rel err F %.2e  G %.2e ; Maclaurin Si rel %.2e  Ci abs %.2e" % (worst["F"], worst["G"], worst["Si"], worst["Ci"]))
 
+    # ---- sin/cos kernels on |r| <= pi/4 for the device sincos used by the Si/Ci tail (arguments up to ~1e5):
+    #      sin r = r * PS(r^2), cos r = PC(r^2); Chebyshev interpolants in w = r^2 on [0, (pi/4)^2]
+    wmax = (mp.pi / 4) ** 2 * mp.mpf("1.02")
+    ps = [float(v) for v in cheb_to_plain(lambda w: mp.mpf(1) if w == 0 else mp.sin(mp.sqrt(w)) / mp.sqrt(w), 0, wmax, 7)]
+    pc = [float(v) for v in cheb_to_plain(lambda w: mp.cos(mp.sqrt(w)), 0, wmax, 8)]
+    r = np.linspace(-np.pi / 4, np.pi / 4, 2001)
+    w = r * r
+    es = np.max(np.abs(r * horner(ps, w) - np.array([float(mp.sin(mp.mpf(float(v)))) for v in r])))
+    ec = np.max(np.abs(horner(pc, w) - np.array([float(mp.cos(mp.mpf(float(v)))) for v in r])))
+    print("sin/cos kernel abs err %.2e %.2e" % (es, ec))
+
     def arr(name, vals):
         return "static __device__ __constant__ double %s[%d] = {\n  %s\n};\n" % (
             name, len(vals), ",\n  ".join(repr(float(v)) for v in vals))
@@ -118,6 +141,8 @@ def main():
     with open(OUT, "w") as fh:
         fh.write("// GENERATED by tools/gen_sici_tables.py -- do not edit.  See that script for the derivation.\n")
         fh.write("#define HMV_SICI_NMAC %d\n#define HMV_SICI_DEG %d\n#define HMV_SICI_NSEG %d\n" % (NMAC, DEG, nseg))
+        fh.write(arr("c_sin_k", ps))
+        fh.write(arr("c_cos_k", pc))
         fh.write(arr("c_si_mac", a))
         fh.write(arr("c_ci_mac", b))
         fh.write("// (F,G) monomial coefficients in u = 2 (s NSEG - seg) - 1, interleaved: g_sici_FG[seg*(DEG+1)+i] = {F_i, G_i}\n")
