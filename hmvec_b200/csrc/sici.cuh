@@ -100,13 +100,13 @@ __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) 
     return fX * scx - gX * ccx + gx - scx * rX;
   }
   double sx, cx, S, C;
-  sincos(x, &sx, &cx);
+  sincos_cw(x, sx, cx);
   const double z = x * x;
   sici_series(z, S, C);
   if (X > 4.0) {
     double fX, gX, sX, cX;
     sici_fg_r(rX, fX, gX);
-    sincos(X, &sX, &cX);
+    sincos_cw(X, sX, cX);
     const double siX = M_PI_2 - fX * cX - gX * sX, ciX = fX * sX - gX * cX;
     const double six = x * S, cix = HMV_EULER + log(x) + z * C;
     const double scx = sX * cx - cX * sx;  // sin(X - x) = sin(c x)
