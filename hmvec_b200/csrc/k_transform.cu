@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
             v = 0.0;
           } else {
             const double* U = Us + (size_t)h * p.JS;
-            const int j = min((int)t, p.J - 1);
+            const int j = min(min((int)t, p.J - 1), jn);   // <= jn: stays inside the bins this CTA computed
             const double u0 = U[j];
             v = fma(t - (double)j, U[j + 1] - u0, u0);
           }
