@@ -10,8 +10,8 @@
 // Truncation + cancellation error of the series is < 1e-11 relative (worst at x c = 16).  Beyond x c = 16 the
 // Si/Ci form is evaluated directly with the device routines in sici.cuh.
 //
-// One CTA per halo row (z,M); each warp walks 128-wide k chunks (4 elements per lane, warp-uniform term count)
-// and writes the row once, coalesced: 8 B/element of algorithmic traffic.
+// One CTA per halo row (z,M); each warp walks 256-wide k chunks (8 elements per lane sharing every coefficient load,
+// warp-uniform term count) and writes the row once, coalesced: 8 B/element of algorithmic traffic.
 #include "common.cuh"
 #include "nfw_device.cuh"
 
@@ -29,11 +29,11 @@ __global__ void nfw_chunkmax_kernel(int nk, const double* __restrict__ ks, doubl
   if (lane == 0) kcmax[chunk] = m;
 }
 
-// TAIL=false: chunks that lie entirely in the series regime (lean: few registers, high occupancy).  TAIL=true: the
-// remaining chunks (some element with x c > 16), which need the Si/Ci routines -- a separate instantiation so that
-// their register footprint does not cap the occupancy of the series pass.
-template <bool TAIL>
-__global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nk, int ldk, const double* __restrict__ ks,
+// A CTA first sweeps the chunks that lie entirely in the series regime, then the remaining ones (some element with
+// x c > 16), which need the Si/Ci routines.  MODE 0/1 run only one of the two parts (kept for profiling them apart);
+// the library launches MODE 2, both in one kernel, so that the store-bound and the FP64-bound halves overlap.
+template <int MODE>   // 0 series only, 1 tail only, 2 both in one launch
+__global__ void __launch_bounds__(NFW_T, MODE ? 3 : 4) uk_nfw_kernel(int nk, int ldk, const double* __restrict__ ks,
                                                         const double* __restrict__ coef,
                                                         const double* __restrict__ kcmax, double kmax,
                                                         double* __restrict__ uk) {
@@ -42,14 +42,14 @@ __global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nk, int
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* rec = coef + row * NFW_NREC;
   const double ac = __ldg(rec + 44);
-  if (TAIL) {   // rows whose whole k-range is in the series regime have nothing to do here
+  if (MODE == 1) {   // rows whose whole k-range is in the series regime have nothing to do here
     if (kmax * ac <= NFW_XC_MAX) return;
   }
   if (threadIdx.x < NFW_NREC) A[threadIdx.x] = __ldg(rec + threadIdx.x);
   __syncthreads();
   double* out = uk + row * (long long)ldk;
   const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
-  if (!TAIL) {
+  if (MODE != 1) {
     for (int chunk = warp; chunk < nchunks; chunk += NFW_T / 32) {
       const double xcm = __ldg(kcmax + chunk) * ac;
       if (xcm > NFW_XC_MAX) continue;                 // left to the tail pass
@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(NFW_T, TAIL ? 3 : 4) uk_nfw_kernel(int nk, int
         if (k < nk) out[k] = u[e];
       }
     }
-  } else {
+  }
+  if (MODE != 0 && kmax * ac > NFW_XC_MAX) {
     // every warp visits every tail chunk and takes its own 32-wide slice of it: the Si/Ci work of a row is spread
     // evenly over the CTA's warps however few chunks are in the tail
     static_assert(NFW_T / 32 == NFW_E, "one slice per warp");
@@ -127,11 +128,8 @@ extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, c
   nfw_chunkmax_kernel<<<(nk + NFW_CH - 1) / NFW_CH, 32, 0, st>>>(nk, ks_d, kcmax);
   rc = check_launch("nfw_chunkmax_kernel");
   if (rc) return rc;
-  uk_nfw_kernel<false><<<(unsigned)rows, NFW_T, 0, st>>>(nk, ldk, ks_d, ws_d, kcmax, kmax, uk_d);
-  rc = check_launch("uk_nfw_kernel<series>");
-  if (rc) return rc;
-  uk_nfw_kernel<true><<<(unsigned)rows, NFW_T, 0, st>>>(nk, ldk, ks_d, ws_d, kcmax, kmax, uk_d);
-  return check_launch("uk_nfw_kernel<tail>");
+  uk_nfw_kernel<2><<<(unsigned)rows, NFW_T, 0, st>>>(nk, ldk, ks_d, ws_d, kcmax, kmax, uk_d);
+  return check_launch("uk_nfw_kernel<both>");
 }
 
 // test hook: elementwise Si/Ci of the device routine (x > 0)

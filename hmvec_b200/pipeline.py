@@ -215,7 +215,7 @@ class GridSix(object):
         if not self.fused_nfw:
             capi.check(L.hmv_uk_nfw(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["cs"]),
                                     ptr(d["rvir"]), ptr(d["nfw_ws"]), ptr(self.um), st), "hmv_uk_nfw")
-            n += 4
+            n += 3
         self._mark(3)
         capi.check(L.hmv_mdelta(nz, nm, ptr(d["ms"]), ptr(d["cs"]), ptr(d["drho1"]), ptr(d["drho2"]), ptr(d["m200c"]),
                                 st), "hmv_mdelta")
