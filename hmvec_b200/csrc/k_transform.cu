@@ -34,7 +34,10 @@ struct TParams {
   double* uk;
 };
 
-constexpr int NCH = 256;   // samples evaluated per chunk
+// samples evaluated per chunk: the tensor-core path holds 704 (every Battaglia/README halo has <= 690 samples inside
+// its theta-cut, so one chunk = one evaluation phase, one seeding of the sine recurrences per pass and no shared-
+// memory read-modify-write of the bin table); longer profiles simply take more chunks.  The DFMA fallback keeps 256.
+constexpr int NCH_MMA = 704, NCH_ROT = 256;
 
 // {sin, cos}(2 pi m/N) for m < N: seeds of the tensor-core path (read with __ldg, 16 bytes per entry)
 __global__ void sine_table_kernel(int N, double2* __restrict__ tab) {
@@ -106,7 +109,7 @@ __device__ __forceinline__ void accum_mma(const double2* __restrict__ tab, const
 
 template <int HB, int TT, bool TABLE, int MAXNJ>
 __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
-  static_assert(TT % NCH == 0 && HB % (TT / NCH) == 0, "threads must tile the (sample, halo) chunk");
+  constexpr int NCH = TABLE ? NCH_MMA : NCH_ROT;
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
   double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
@@ -159,25 +162,26 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
   for (int h = 0; h < HB; ++h) msum[h] = 0.0;
 
   for (int n0 = 0; n0 < nb; n0 += NCH) {
-    {  // ---- evaluate x*y for sample n0 + (tid % NCH) of this thread's share of the halos (theta-cut, fft.py:79-81)
-      constexpr int HPT = HB / (TT / NCH);      // halos per thread
-      const int sn = tid % NCH, hb = (tid / NCH) * HPT;
-      const int n = n0 + sn;
-      const double x = (double)(n + 1) * p.dx;
-      const double lx = log(x);
-      const double w = (n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx;  // np.trapz weights on xs (fft.py:84)
+    {  // ---- evaluate x*y for the chunk's samples, all HB halos per sample (theta-cut: x <= cmax, fft.py:79-81);
+       //      samples up to the next multiple of 4 past the chunk's end are zero-filled for the 4-sample MMA steps
+      const int nfill = min(NCH, ((nb - n0) + 3) & ~3);
+      for (int sn = tid; sn < nfill; sn += TT) {
+        const int n = n0 + sn;
+        const double x = (double)(n + 1) * p.dx;
+        const double lx = log(x);
+        const double w = (n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx;  // np.trapz weights on xs (fft.py:84)
 #pragma unroll
-      for (int hh = 0; hh < HPT; ++hh) {
-        const int h = hb + hh;
-        double v = 0.0;
-        if (n < p.N && x <= h_cmax[h]) {
-          const double lt = lx - h_lxc[h];
-          // amp * t^gamma * (1+t^alpha)^(-expo)
-          const double rho = h_amp[h] * exp(p.gamma * lt - h_expo[h] * log1p(exp(h_alpha[h] * lt)));
-          v = x * rho;
-          msum[hh] = fma(w * x, v, msum[hh]);
+        for (int h = 0; h < HB; ++h) {
+          double v = 0.0;
+          if (n < p.N && x <= h_cmax[h]) {
+            const double lt = lx - h_lxc[h];
+            // amp * t^gamma * (1+t^alpha)^(-expo)
+            const double rho = h_amp[h] * exp(p.gamma * lt - h_expo[h] * log1p(exp(h_alpha[h] * lt)));
+            v = x * rho;
+            msum[h] = fma(w * x, v, msum[h]);
+          }
+          gs[sn * HB + h] = v;
         }
-        gs[sn * HB + h] = v;
       }
     }
     __syncthreads();
@@ -232,17 +236,10 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 
   // ---- mass norm (fft.py:83-87) and u_j = U_j / kt_j / mnorm (fft.py:91) ----
   double scale[HB];
-  {
-    constexpr int HPT = HB / (TT / NCH);
-    const int hb = (tid / NCH) * HPT;
 #pragma unroll
-    for (int h = 0; h < HB; ++h) {
-      double mine = 0.0;
-#pragma unroll
-      for (int hh = 0; hh < HPT; ++hh) mine = (hb + hh == h) ? msum[hh] : mine;
-      const double mn = p.do_mass_norm ? block_sum(mine, red) : 1.0;
-      scale[h] = p.step / mn * h_oscale[h];
-    }
+  for (int h = 0; h < HB; ++h) {
+    const double mn = p.do_mass_norm ? block_sum(msum[h], red) : 1.0;
+    scale[h] = p.step / mn * h_oscale[h];
   }
   for (int j = tid + 1; j <= jn; j += TT) {
     const double ikt = 1.0 / ((double)j * p.kt1);
@@ -288,7 +285,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 
 template <int HB, int TT, bool TABLE>
 static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)NCH * HB + 32 + (size_t)0 * (TABLE ? N : 0)) * sizeof(double);
+  return ((size_t)HB * JS + (size_t)(TABLE ? NCH_MMA : NCH_ROT) * HB + 32) * sizeof(double);
 }
 
 template <int HB, int TT, bool TABLE, int MAXNJ>
