@@ -107,9 +107,8 @@ __device__ __forceinline__ void accum_mma(const double2* __restrict__ tab, const
   }
 }
 
-template <int HB, int TT, bool TABLE, int MAXNJ>
-__global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
-  constexpr int NCH = TABLE ? NCH_MMA : NCH_ROT;
+template <int HB, int TT, bool TABLE, int MAXNJ, int NCH>
+__global__ void __launch_bounds__(TT, (TABLE && TT <= 256) ? (TT == 128 ? 6 : MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
   double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
@@ -283,15 +282,15 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
   }
 }
 
-template <int HB, int TT, bool TABLE>
-static size_t transform_smem(int JS, int N) {
-  return ((size_t)HB * JS + (size_t)(TABLE ? NCH_MMA : NCH_ROT) * HB + 32) * sizeof(double);
+template <int HB, int NCH>
+static size_t transform_smem(int JS) {
+  return ((size_t)HB * JS + (size_t)NCH * HB + 32) * sizeof(double);
 }
 
-template <int HB, int TT, bool TABLE, int MAXNJ>
+template <int HB, int TT, bool TABLE, int MAXNJ, int NCH>
 static int launch_transform(const TParams& p, int jlo, int jhi, int JS, cudaStream_t st) {
-  const size_t smem = transform_smem<HB, TT, TABLE>(JS, p.N);
-  auto kern = profile_transform_kernel<HB, TT, TABLE, MAXNJ>;
+  const size_t smem = transform_smem<HB, NCH>(JS);
+  auto kern = profile_transform_kernel<HB, TT, TABLE, MAXNJ, NCH>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
@@ -342,7 +341,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   };
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
-  if (transform_smem<8, 512, true>(J + 2, nxs) <= budget) {
+  if (transform_smem<8, NCH_MMA>(J + 2) <= budget) {
     // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
     sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d));
     int rc = check_launch("sine_table_kernel");
@@ -352,27 +351,27 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
     const int jA = 254, jB = 510, jC = 1022;           // class upper bounds: 4 / 3 / 2 / 1 CTAs fit per SM
     auto hi = [&](int j) { return j < J ? j : J; };
     if (J > jC) {
-      rc = launch_transform<8, 512, true, 8>(p, jC, J, J + 2, st);            // heavy CTAs first
+      rc = launch_transform<8, 512, true, 8, NCH_MMA>(p, jC, J, J + 2, st);            // heavy CTAs first
       if (rc) return rc;
     }
     if (J > jB) {
-      rc = launch_transform<8, 256, true, 8>(p, jB, hi(jC), hi(jC) + 2, st);
+      rc = launch_transform<8, 256, true, 8, NCH_MMA>(p, jB, hi(jC), hi(jC) + 2, st);
       if (rc) return rc;
     }
     if (J > jA) {
-      rc = launch_transform<8, 256, true, 4>(p, jA, hi(jB), hi(jB) + 2, st);
+      rc = launch_transform<8, 256, true, 4, NCH_MMA>(p, jA, hi(jB), hi(jB) + 2, st);
       if (rc) return rc;
     }
-    return launch_transform<8, 256, true, 4>(p, 0, hi(jA), hi(jA) + 2, st);
+    return launch_transform<8, 128, true, 4, NCH_ROT>(p, 0, hi(jA), hi(jA) + 2, st);
   }
   // large N: rotation recurrence, widest halo batch whose bin table fits
 #define HMV_ROT(HBV)                                                                   \
-  if (transform_smem<HBV, 256, false>(J + 2, nxs) <= budget) {                         \
+  if (transform_smem<HBV, NCH_ROT>(J + 2) <= budget) {                                 \
     const int rc = bin_counts(HBV);                                                    \
-    return rc ? rc : launch_transform<HBV, 256, false, 1>(p, 0, J, J + 2, st);            \
+    return rc ? rc : launch_transform<HBV, 256, false, 1, NCH_ROT>(p, 0, J, J + 2, st);            \
   }
   HMV_ROT(8) HMV_ROT(4) HMV_ROT(2) HMV_ROT(1)
 #undef HMV_ROT
   return fail(HMV_E_LIMIT, "hmv_profile_transform: nxs=%d needs %zu B of shared memory per halo (limit %zu)", nxs,
-              transform_smem<1, 256, false>(J + 2, nxs), budget);
+              transform_smem<1, NCH_ROT>(J + 2), budget);
 }
