@@ -34,9 +34,10 @@ struct TParams {
   double* uk;
 };
 
-// samples evaluated per chunk: the tensor-core path holds 704 (every Battaglia/README halo has <= 690 samples inside
-// its theta-cut, so one chunk = one evaluation phase, one seeding of the sine recurrences per pass and no shared-
-// memory read-modify-write of the bin table); longer profiles simply take more chunks.  The DFMA fallback keeps 256.
+// samples evaluated per chunk.  The two large bin-count classes hold 704 (every Battaglia/README halo has <= 690
+// samples inside its theta-cut, so one chunk = one evaluation phase and one seeding of the sine recurrences per
+// pass); longer profiles simply take more chunks.  The two small classes and the DFMA fallback use 256, which keeps
+// their shared-memory footprint at 3 CTAs per SM (measured: 704 was slower for them).
 constexpr int NCH_MMA = 704, NCH_ROT = 256;
 
 // {sin, cos}(2 pi m/N) for m < N: seeds of the tensor-core path (read with __ldg, 16 bytes per entry)
@@ -108,7 +109,7 @@ __device__ __forceinline__ void accum_mma(const double2* __restrict__ tab, const
 }
 
 template <int HB, int TT, bool TABLE, int MAXNJ, int NCH>
-__global__ void __launch_bounds__(TT, (TABLE && TT <= 256) ? (TT == 128 ? 6 : MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
+__global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2) : 1) profile_transform_kernel(const TParams p) {
   extern __shared__ double smem[];
   double* Us = smem;                          // [HB][JS]
   double* gs = Us + (size_t)HB * p.JS;        // [NCH][HB]
@@ -359,10 +360,10 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
       if (rc) return rc;
     }
     if (J > jA) {
-      rc = launch_transform<8, 256, true, 4, NCH_MMA>(p, jA, hi(jB), hi(jB) + 2, st);
+      rc = launch_transform<8, 256, true, 4, NCH_ROT>(p, jA, hi(jB), hi(jB) + 2, st);
       if (rc) return rc;
     }
-    return launch_transform<8, 128, true, 4, NCH_ROT>(p, 0, hi(jA), hi(jA) + 2, st);
+    return launch_transform<8, 256, true, 4, NCH_ROT>(p, 0, hi(jA), hi(jA) + 2, st);
   }
   // large N: rotation recurrence, widest halo batch whose bin table fits
 #define HMV_ROT(HBV)                                                                   \

@@ -26,17 +26,22 @@ def launches(path):
     txt = open(path).read()
     rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
     agg = collections.OrderedDict()
+    scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
+    byts = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows:
         n = r['Kernel Name'].split('(')[0][:80]
-        a = agg.setdefault(n, [0, 0.0])
-        a[0] += 1
-        a[1] += float(r['Metric Value']) / 1e6
+        a = agg.setdefault(n, [0, 0.0, 0.0])
+        if r['Metric Name'] == 'gpu__time_duration.sum':
+            a[0] += 1
+            a[1] += float(r['Metric Value']) * scale.get(r['Metric Unit'], 1e-6)
+        elif r['Metric Name'] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+            a[2] += float(r['Metric Value']) * byts.get(r['Metric Unit'], 1.0)
     tot = sum(v[1] for v in agg.values())
     print("# per-launch device time from: ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised)")
-    print("# source: %s ; %d launches, %.3f ms total" % (path, len(rows), tot))
-    print("%-82s %5s %11s %10s %7s" % ("kernel", "n", "total_ms", "avg_ms", "share"))
-    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("%-82s %5d %11.3f %10.3f %6.1f%%" % (n, c, t, t / c, 100 * t / tot))
+    print("# source: %s ; %d launches, %.3f ms total" % (path, sum(v[0] for v in agg.values()), tot))
+    print("%-82s %5s %11s %10s %7s %12s" % ("kernel", "n", "total_ms", "avg_ms", "share", "dram_GB/launch"))
+    for n, (c, t, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("%-82s %5d %11.3f %10.3f %6.1f%% %12.3f" % (n, c, t, t / max(c, 1), 100 * t / tot, b / max(c, 1) / 1e9))
 
 
 def full(path):
