@@ -188,6 +188,8 @@ def run_b200(a):
     sl = zc.slab if zc is not None else slice(0, a.nz)
     g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs,
                          fused_nfw=a.fused_nfw)
+    capi.check(capi.lib.hmv_set_transform_mode(a.transform_mode), "hmv_set_transform_mode")
+    g.transform_mode = a.transform_mode
     g.upload()
     torch.cuda.synchronize()
 
@@ -294,7 +296,7 @@ def run_b200(a):
         pass
     dom = max(alg_bytes, key=lambda n: kernels[n]["ms"])
     if dom == "uk_electron":
-        roof = {"kernel": "profile_transform_kernel (K1, FP64 mma.sync m8n8k4)", "bound": "tensor",
+        roof = {"kernel": "%s (K1, FP64 mma.sync m8n8k4)" % ("profile_transform_ws_kernel" if g.transform_mode == 0 else "profile_transform_kernel"), "bound": "tensor",
                 "achieved": k1["tflops"], "peak": dmma_tf, "unit": "TFLOP/s", "frac": k1["frac_fp64_tensor"],
                 "peak_source": "FP64 DMMA peak measured in this run (hmv_bench_dmma); MEASURED_PEAKS.json has no FP64 figure",
                 "alg_flop_per_launch": k1_flop, "hbm_store_frac": k1["frac_hbm"]}
@@ -347,6 +349,8 @@ def main():
     ap.add_argument("--nl", type=int, default=1000)
     ap.add_argument("--cpu-nz", type=int, default=2, help="redshifts in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--transform-mode", type=int, default=0, choices=[0, 1],
+                    help="K1 launch plan: 0 = persistent warp-specialised kernel (default), 1 = bin-count-class kernels")
     ap.add_argument("--fused-nfw", action="store_true",
                     help="evaluate the NFW profile inside the mass reduction (hmv_power_six_nfw) instead of writing "
                          "its cube to HBM and reading it back (hmv_uk_nfw + hmv_power_six, the faster default)")

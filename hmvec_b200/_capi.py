@@ -53,6 +53,7 @@ _SIGS = {
     "hmv_gnfw_params": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _d,
                              _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
+    "hmv_set_transform_mode": (_i, [_i]),
     "hmv_profile_transform": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_hod": (_i, [_i, _i, _p, _p, _p, C.POINTER(_d), _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_hod_bisect": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _i, _i, _p, _p, _p]),

@@ -53,8 +53,9 @@ __global__ void sine_table_kernel(int N, double2* __restrict__ tab) {
 // bins needed by each CTA (group of HB halos): jn = floor(kmax * max_h(rs (1+z)) / kt_1) + 2, capped at N/2
 __global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double kmax, double kt1,
                                  const double* __restrict__ zs, const double* __restrict__ rs,
-                                 int* __restrict__ jn_cta) {
+                                 int* __restrict__ jn_cta, int* __restrict__ work_counter) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *work_counter = 0;                // queue head of the persistent kernel
   if (b >= nz * nmg) return;
   const int z = b / nmg, mg = nmg - 1 - (b - z * nmg);
   double amax = 0.0;
@@ -283,6 +284,398 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
   }
 }
 
+
+// =====================================================================================================================
+// Warp-specialised persistent form of the same transform (the default path).
+//
+// The class kernels above run their three phases -- GNFW evaluation, tensor-core sine sums, interpolation + store --
+// one after the other inside a CTA, and the heavy classes fit one CTA per SM, so the FP64 pipe idles while the rows are
+// stored and the store path idles while the pipe works (ncu: 48 % tensor-pipe active, 8 % DRAM in the heaviest class).
+// Here ONE 512-thread CTA per SM splits into two roles that overlap:
+//   * 8 producer warps pull (z, 16-halo group) items from a global atomic queue, evaluate the samples into shared
+//     memory, run the DMMA sine sums and write the finished, normalised bin table u_j of the group into one slot of a
+//     per-CTA ring in global memory (WS_NSLOT x 16 x (N/2+2) doubles; only the bins a group needs are touched, so the
+//     ring lives in the 126 MB L2 and the consumer's re-reads hit L1);
+//   * 8 consumer warps wait for a slot, interpolate its 16 rows onto the target ks (one row per warp at a time, four
+//     16-byte streaming stores per lane and trip, a warp-vote fast path where a whole 256-k span is below the first
+//     bin) and release the slot.
+// full/empty mbarriers hand the slots over (producer: named barrier among its 256 threads, then one release-arrive;
+// consumer: acquire-wait), so the FP64-pipe-bound work of one group overlaps the HBM-bound stores of the previous ones.
+// Sixteen halos per item = two 8-row M tiles per B fragment: every sine value the recurrence produces feeds two DMMAs
+// (tools/micro/dmma_sweep.cu: one recurrence DFMA per DMMA caps the loop at 28 of 36 TFLOP/s), and a warp with 4 bin
+// tiles runs 8 independent accumulator chains (DMMA dependent-issue latency ~49 cycles, 16 cycles of pipe each).
+// Items are issued in an order that strides through the mass axis (golden-ratio step), so light (store-bound) and heavy
+// (DMMA-bound) groups alternate in every SM's queue instead of arriving as one heavy and one light phase; the last
+// redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
+// registers while the current one is being transformed.
+// Shared memory is only the 90 KB sample chunk, so there are no bin-count classes and no limit on N from the bin table.
+constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256, WS_CT = 256;
+
+struct WsSlotMeta {
+  int z, m0, jn, nvalid;
+  double inv[WS_HB], u1[WS_HB];
+};
+
+// sum over the lanes of the caller's parity (even lanes hold halos 0-7, odd lanes halos 8-15)
+__device__ __forceinline__ double warp_sum_parity(double v) {
+#pragma unroll
+  for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// sample n of halo h inside a chunk: [n/4][h%8][n%4][h/8] -- the A fragments (sample kq of halo nq, both M tiles) of a
+// 4-sample MMA step are 32 consecutive 16-byte words, one conflict-free LDS.128 per lane
+__device__ __forceinline__ int ws_gs_index(int sn, int h) {
+  return ((sn >> 2) << 6) + ((h & 7) << 3) + ((sn & 3) << 1) + (h >> 3);
+}
+
+// D[16 halos][8 bins] += A[16][4 samples] B[4][8] as two m8n8k4 DMMAs sharing the B fragment; NT bin tiles per warp.
+// First chunk stores, later chunks add; when the whole profile fits one chunk (fuse) the mass norm and 1/kt_j are
+// applied on the way out and bin 1 is published as u1.
+template <int NT>
+__device__ __forceinline__ void accum_mma_ws(const double2* __restrict__ tab, const double* __restrict__ gs, double* U,
+                                             int JS, int N, int n0, int nlen, int jw, int jn, int lane, bool first,
+                                             bool fuse, double scale0, double scale1, double kt1, double* u1_out) {
+  const int kq = lane & 3, nq = lane >> 2;
+  double bc[NT], bp[NT], tc[NT], c[NT][2][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int jj = jw + 8 * t + nq;
+    const unsigned j = (jj <= jn) ? (unsigned)jj : 0u;          // bin 0: sin == 0, contributes nothing
+    const unsigned ph = (j * (unsigned)(n0 + kq)) % (unsigned)N;  // j*n < 2^31 (checked on the host)
+    const unsigned st = (4u * j) % (unsigned)N;                   // phase advance per 4 samples
+    const unsigned pp = ph >= st ? ph - st : ph + (unsigned)N - st;
+    bc[t] = __ldg(tab + ph).x;
+    bp[t] = __ldg(tab + pp).x;
+    tc[t] = 2.0 * __ldg(tab + st).y;
+    c[t][0][0] = 0.0; c[t][0][1] = 0.0; c[t][1][0] = 0.0; c[t][1][1] = 0.0;
+  }
+  const double2* ga = reinterpret_cast<const double2*>(gs) + (nq << 2) + kq;
+#pragma unroll 2
+  for (int nn = 0; nn < nlen; nn += 4) {
+    const double2 a = ga[nn << 3];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][0][0]), "+d"(c[t][0][1]) : "d"(a.x), "d"(bc[t]));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][1][0]), "+d"(c[t][1][1]) : "d"(a.y), "d"(bc[t]));
+      const double bn = fma(tc[t], bc[t], -bp[t]);
+      bp[t] = bc[t];
+      bc[t] = bn;
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    double* Uh = U + (size_t)(nq + 8 * mt) * JS;
+    const double sc = mt ? scale1 : scale0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = jw + 8 * t + 2 * kq + e;
+        if (b <= jn) {
+          double v = c[t][mt][e];
+          if (!first) v += Uh[b];
+          if (fuse) {
+            v *= sc / ((double)b * kt1);
+            if (b == 1) u1_out[nq + 8 * mt] = v;
+          }
+          Uh[b] = v;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ double ws_interp(const double* U, double t, double u1, double tJ, int jcap) {
+  const int j = min(max((int)fmin(t, tJ), 1), jcap);       // always inside the bins the producer wrote
+  const double ua = U[j], ub = U[j + 1];
+  double v = fma(t - (double)j, ub - ua, ua);
+  v = (t > tJ) ? 0.0 : v;                                    // np.interp right=0
+  return (t >= 1.0) ? v : u1;                                // np.interp left=puks[0]
+}
+
+// queue position -> (z, mass-group index counted from the heavy end)
+__device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
+  z = item / nmg;
+  const int r = item - z * nmg;
+  q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
+}
+
+__global__ void __launch_bounds__(WS_PT + WS_CT, 1)
+profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride) {
+  extern __shared__ double smem[];
+  double* gs = smem;                          // [NCH_MMA/4][8][4][2]
+  __shared__ unsigned long long full[WS_NSLOT], empty[WS_NSLOT];
+  __shared__ WsSlotMeta meta[WS_NSLOT];
+  __shared__ double h_cmax[WS_HB], h_lxc[WS_HB], h_alpha[WS_HB], h_expo[WS_HB], h_amp[WS_HB], h_oscale[WS_HB],
+      h_inv[WS_HB];
+  __shared__ double redm[WS_PT / 32][WS_HB];
+  __shared__ int nxt_item;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < WS_NSLOT; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WS_CT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    nxt_item = atomicAdd(work_counter, 1);
+  }
+  __syncthreads();
+  const int JS = p.JS;
+  double* slots = ring + (size_t)blockIdx.x * WS_NSLOT * WS_HB * JS;
+
+  if (tid < WS_PT) {
+    // =============================== producers: samples -> sine sums -> bin table ================================
+    const double2* T = reinterpret_cast<const double2*>(p.sintab);
+    const int warp = tid >> 5, lane = tid & 31, hoff = (tid & 1) << 3;
+    // parameters of halo `tid` (tid < 16) of an item, fetched one item ahead
+    double f_cmax = -1.0, f_xc = 1.0, f_alpha = 0.0, f_expo = 0.0, f_amp = 0.0, f_oscale = 1.0, f_inv = 0.0;
+    int f_jn = 0;
+    auto fetch = [&](int item) {
+      if (item >= nitems) return;
+      int z, q;
+      ws_item(item, p.nz, p.nmg, stride, z, q);
+      f_jn = p.jn_cta[z * p.nmg + q];
+      if (tid < WS_HB) {
+        const int m = (p.nmg - 1 - q) * WS_HB + tid;
+        const bool ok = m < p.nm;
+        const long long rr = (long long)z * p.nm + (ok ? m : p.nm - 1);
+        f_cmax = ok ? p.cmax[rr] : -1.0;
+        f_xc = p.xc[rr];
+        f_alpha = p.alpha[rr];
+        f_expo = p.expo[rr];
+        f_amp = p.amp[rr];
+        f_oscale = p.outscale ? p.outscale[rr] : 1.0;
+        f_inv = p.rs[rr] * (1.0 + p.zs[z]) / p.kt1;            // k -> fractional bin index   (fft.py:92)
+      }
+    };
+    auto publish = [&]() {
+      if (tid < WS_HB) {
+        h_cmax[tid] = f_cmax; h_lxc[tid] = log(f_xc); h_alpha[tid] = f_alpha; h_expo[tid] = f_expo;
+        h_amp[tid] = f_amp; h_oscale[tid] = f_oscale; h_inv[tid] = f_inv;
+      }
+    };
+    int item = nxt_item;
+    fetch(item);
+    publish();
+    producer_bar();
+    for (unsigned it = 0;; ++it) {
+      const int s = (int)(it % WS_NSLOT);
+      const unsigned ph = (it / WS_NSLOT) & 1u;
+      if (tid == 0) nxt_item = atomicAdd(work_counter, 1);
+      mbar_wait(empty + s, ph ^ 1u);           // the consumers are done with this slot (first lap passes at once)
+      if (item >= nitems) {                    // queue drained: hand the consumers a stop marker
+        if (tid == 0) { meta[s].jn = -1; mbar_arrive(full + s); }
+        break;
+      }
+      int z, q;
+      ws_item(item, p.nz, p.nmg, stride, z, q);
+      const int jn = f_jn;
+      const int m0 = (p.nmg - 1 - q) * WS_HB;
+      double* U = slots + (size_t)s * WS_HB * JS;
+      if (tid < WS_HB) meta[s].inv[tid] = h_inv[tid];
+      if (tid == 0) { meta[s].z = z; meta[s].m0 = m0; meta[s].jn = jn; meta[s].nvalid = min(WS_HB, p.nm - m0); }
+      producer_bar();                          // h_* of this item and nxt_item are visible
+      const int nxt = nxt_item;
+      fetch(nxt);                              // loads in flight behind the whole transform of this item
+
+      double cmx = -1.0;
+#pragma unroll
+      for (int h = 0; h < WS_HB; ++h) cmx = fmax(cmx, h_cmax[h]);
+      const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
+      const bool single = nb > 0 && nb <= NCH_MMA;
+      if (nb == 0)
+        for (int i = tid; i < WS_HB * (jn + 1); i += WS_PT) U[(size_t)(i / (jn + 1)) * JS + 1 + i % (jn + 1)] = 0.0;
+
+      double msum[8];                          // this lane's half of the halos (hoff ...)
+#pragma unroll
+      for (int h = 0; h < 8; ++h) msum[h] = 0.0;
+      double scale0 = 1.0, scale1 = 1.0;
+
+      for (int n0 = 0; n0 < nb; n0 += NCH_MMA) {
+        const int nfill = min(NCH_MMA, ((nb - n0) + 3) & ~3);
+        // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15
+        for (int sn = tid >> 1; sn < nfill; sn += WS_PT / 2) {
+          const int n = n0 + sn;
+          const double x = (double)(n + 1) * p.dx;
+          const double lx = log(x);
+          const double w = (n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx;   // np.trapz weights on xs (fft.py:84)
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) {
+            const int h = hh + hoff;
+            double v = 0.0;
+            if (n < p.N && x <= h_cmax[h]) {
+              const double lt = lx - h_lxc[h];
+              // amp * t^gamma * (1+t^alpha)^(-expo)
+              const double rho = h_amp[h] * exp(p.gamma * lt - h_expo[h] * log1p(exp(h_alpha[h] * lt)));
+              v = x * rho;
+              msum[hh] = fma(w * x, v, msum[hh]);
+            }
+            gs[ws_gs_index(sn, h)] = v;
+          }
+        }
+        if (single && p.do_mass_norm) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const double v = warp_sum_parity(msum[h]);
+            if (lane < 2) redm[warp][h + hoff] = v;
+          }
+        }
+        producer_bar();
+        if (single) {
+          const int nq = lane >> 2;
+          double mn0 = 1.0, mn1 = 1.0;
+          if (p.do_mass_norm) {
+            mn0 = 0.0; mn1 = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < WS_PT / 32; ++w8) { mn0 += redm[w8][nq]; mn1 += redm[w8][nq + 8]; }
+          }
+          scale0 = p.step / mn0 * h_oscale[nq];
+          scale1 = p.step / mn1 * h_oscale[nq + 8];
+        }
+        const int nlen = min(NCH_MMA, nb - n0);
+        constexpr int NW = WS_PT / 32;
+        const int ntile = (jn + 7) >> 3;
+        const bool first = n0 == 0;
+        for (int t0 = 0; t0 < ntile;) {
+          const int per = (ntile - t0 + NW - 1) / NW;        // tiles each warp still has to take
+          const int ntc = per >= 4 ? 4 : per;
+          const int jw = 1 + 8 * (t0 + warp * ntc);
+          if (jw <= jn) {
+#define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.kt1, meta[s].u1)
+            switch (ntc) {
+              case 4: HMV_WS_ACC(4); break;
+              case 3: HMV_WS_ACC(3); break;
+              case 2: HMV_WS_ACC(2); break;
+              default: HMV_WS_ACC(1); break;
+            }
+#undef HMV_WS_ACC
+          }
+          t0 += ntc * NW;
+        }
+        producer_bar();                        // the chunk's samples are consumed, its sums are in the table
+      }
+
+      if (!single) {
+        // profile longer than one chunk (or empty): normalise the finished table in a separate pass
+        if (p.do_mass_norm) {
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const double v = warp_sum_parity(msum[h]);
+            if (lane < 2) redm[warp][h + hoff] = v;
+          }
+        }
+        producer_bar();
+        for (int i = tid; i < WS_HB * jn; i += WS_PT) {
+          const int h = i / jn, j = 1 + (i - h * jn);
+          double mn = 1.0;
+          if (p.do_mass_norm) {
+            mn = 0.0;
+            for (int w8 = 0; w8 < WS_PT / 32; ++w8) mn += redm[w8][h];
+          }
+          const double v = U[(size_t)h * JS + j] * (p.step / mn * h_oscale[h]) / ((double)j * p.kt1);
+          U[(size_t)h * JS + j] = v;
+          if (j == 1) meta[s].u1[h] = v;
+        }
+      }
+      if (tid < WS_HB) U[(size_t)tid * JS + jn + 1] = 0.0;   // guard bin behind the last computed one
+      producer_bar();                          // table complete; nobody reads this item's h_* any more
+      if (tid == 0) mbar_arrive(full + s);     // release: the table and its meta record are visible to the consumers
+      publish();                               // next item's parameters (ordered by the next trip's first barrier)
+      item = nxt;
+    }
+  } else {
+    // =============================== consumers: interpolate onto ks, store the rows ==============================
+    const int ct = tid - WS_PT, lane = ct & 31, cw = ct >> 5;
+    const int npair = p.nk >> 1;
+    const double2* ks2 = reinterpret_cast<const double2*>(p.ks);
+    const double tJ = (double)p.J;
+    for (unsigned it = 0;; ++it) {
+      const int s = (int)(it % WS_NSLOT);
+      const unsigned ph = (it / WS_NSLOT) & 1u;
+      mbar_wait(full + s, ph);
+      const int jn = meta[s].jn;
+      if (jn < 0) break;
+      const int nvalid = meta[s].nvalid;
+      const double* U = slots + (size_t)s * WS_HB * JS;
+      double* out0 = p.uk + ((long long)meta[s].z * p.nm + meta[s].m0) * (long long)p.ldk;
+      const int jcap = min(p.J - 1, jn);
+      for (int row = cw; row < nvalid; row += WS_CT / 32) {
+        const double inv = meta[s].inv[row], u1 = meta[s].u1[row];
+        const double* Uh = U + (size_t)row * JS;
+        double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk);
+        for (int base = 0; base < npair; base += 128) {          // warp-uniform trip count (the vote below)
+          double2 kk[4];
+          bool lt1 = true;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int k2 = base + lane + 32 * u;
+            kk[u] = (k2 < npair) ? __ldg(ks2 + k2) : make_double2(0.0, 0.0);
+            kk[u].x *= inv; kk[u].y *= inv;
+            lt1 = lt1 && kk[u].x < 1.0 && kk[u].y < 1.0;
+          }
+          if (__all_sync(0xffffffffu, lt1)) {
+            const double2 v = make_double2(u1, u1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k2 = base + lane + 32 * u;
+              if (k2 < npair) __stcs(orow + k2, v);
+            }
+          } else {
+            double2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              v[u].x = ws_interp(Uh, kk[u].x, u1, tJ, jcap);
+              v[u].y = ws_interp(Uh, kk[u].y, u1, tJ, jcap);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int k2 = base + lane + 32 * u;
+              if (k2 < npair) __stcs(orow + k2, v[u]);
+            }
+          }
+        }
+        if ((p.nk & 1) && lane == 0) {         // odd nk: the last wavenumber
+          const int k = p.nk - 1;
+          out0[(long long)row * p.ldk + k] = ws_interp(Uh, __ldg(p.ks + k) * inv, u1, tJ, jcap);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+  }
+}
+
+static bool ws_ring_fits(int nxs) {
+  return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)1 << 30);
+}
+
+static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
+
+static int launch_transform_ws(const TParams& p, double* ring, int* counter, cudaStream_t st) {
+  int dev = 0, nsm = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform: %s", cudaGetErrorString(e));
+  TParams q = p;
+  q.nmg = cdiv(p.nm, WS_HB);
+  q.jlo = 0; q.jhi = p.J; q.JS = p.J + 2;
+  const int nitems = q.nz * q.nmg;
+  const int grid = nitems < nsm ? nitems : (nsm < WS_MAXCTA ? nsm : WS_MAXCTA);
+  // stride through the mass groups with a step near nmg/phi^2 that is coprime to nmg (a permutation of 0..nmg-1)
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  int stride = (int)(0.381966 * q.nmg);
+  if (stride < 1) stride = 1;
+  while (gcd(stride, q.nmg) != 1) ++stride;
+  const size_t smem = (size_t)NCH_MMA * WS_HB * sizeof(double);
+  e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  profile_transform_ws_kernel<<<grid, WS_PT + WS_CT, smem, st>>>(q, ring, counter, nitems, stride);
+  return check_launch("profile_transform_ws_kernel");
+}
+
 template <int HB, int NCH>
 static size_t transform_smem(int JS) {
   return ((size_t)HB * JS + (size_t)NCH * HB + 32) * sizeof(double);
@@ -309,7 +702,15 @@ using namespace hmv;
 extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
   // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
-  return 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2;
+  long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2;
+  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NSLOT * WS_HB * (nxs / 2 + 2);   // bin-table ring of the persistent kernel
+  return n;
+}
+
+extern "C" int hmv_set_transform_mode(int mode) {
+  HMV_REQUIRE(mode == 0 || mode == 1, "hmv_set_transform_mode: mode must be 0 (persistent) or 1 (bin-count classes)");
+  g_transform_mode = mode;
+  return HMV_OK;
 }
 
 extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
@@ -334,12 +735,26 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
   int* jn_cta = reinterpret_cast<int*>(ws_d + 2 * (size_t)nxs + 2);
   p.jn_cta = jn_cta;
+  double* after_jn = ws_d + 2 * (size_t)nxs + 2 + ((size_t)nz * nm + 1) / 2 + 2;
+  int* counter = reinterpret_cast<int*>(after_jn);
+  double* ring = after_jn + 2;
   cudaStream_t st = (cudaStream_t)stream;
   auto bin_counts = [&](int HB) {
     const int nmg = cdiv(nm, HB);
-    bin_count_kernel<<<cdiv((long long)nz * nmg, 256), 256, 0, st>>>(nz, nm, nmg, HB, p.J, kmax, p.kt1, zs_d, rs_d, jn_cta);
+    bin_count_kernel<<<cdiv((long long)nz * nmg, 256), 256, 0, st>>>(nz, nm, nmg, HB, p.J, kmax, p.kt1, zs_d, rs_d, jn_cta,
+                                                                     counter);
     return check_launch("bin_count_kernel");
   };
+  const bool aligned16 = (((size_t)ks_d | (size_t)uk_d | (size_t)ws_d) & 15) == 0 && (ldk & 1) == 0;
+  if (g_transform_mode == 0 && ws_ring_fits(nxs) && aligned16) {
+    // persistent warp-specialised kernel: sine table, bin counts, one launch
+    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d));
+    int rc = check_launch("sine_table_kernel");
+    if (rc) return rc;
+    rc = bin_counts(WS_HB);
+    if (rc) return rc;
+    return launch_transform_ws(p, ring, counter, st);
+  }
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
   if (transform_smem<8, NCH_MMA>(J + 2) <= budget) {

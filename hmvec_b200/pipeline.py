@@ -155,6 +155,7 @@ class GridSix(object):
             self.cl = E(2, self.nl)
             self.h_cl = torch.empty((2, self.nl), dtype=torch.float64).pin_memory()
         self.launches_per_run = 0
+        self.transform_mode = 0
         self._ev = None
         self._Pfull = None
         self.d2h_chunks = 5
@@ -227,7 +228,8 @@ class GridSix(object):
                                            ptr(d["cmax"]), ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]),
                                            ptr(d["oscale"]), self.gamma, self.xmax, self.nxs, 1, ptr(d["tr_ws"]),
                                            ptr(self.ue), st), "hmv_profile_transform")
-        n += 8    # mdelta, gnfw_params, sine_table, bin_count, four bin-count classes
+        # mdelta, gnfw_params, sine_table, bin_count + one persistent kernel (or the four bin-count classes)
+        n += 5 if self.transform_mode == 0 else 8
         self._mark(4)
         for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
             capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]),

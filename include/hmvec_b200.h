@@ -80,8 +80,13 @@ int hmv_gnfw_params(int kind, int nz, int nm, const double* zs_d, const double* 
  * sums U_j = step sum_n x_n y_n sin(2 pi j n/N), u_j = U_j/kt_j/mnorm, kout_j = kt_j/rs/(1+z), then linear
  * interpolation onto ks (hold u_1 below the first bin, 0 above the last).  The (z,M,x) cube is never stored.
  * outscale_d may be NULL (=1).  do_mass_norm as in generic_profile_fft.  ks need not be sorted.
- * ws_d: workspace of hmv_profile_transform_ws_doubles(nz,nm,nxs) doubles (sine table + per-CTA bin counts). */
+ * ws_d: workspace of hmv_profile_transform_ws_doubles(nz,nm,nxs) doubles (sine table, per-CTA bin counts, work-queue
+ * head and the per-CTA ring of bin tables), 16-byte aligned. */
 long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs);
+/* Process-wide choice of the transform's launch plan: 0 (default) = one persistent, warp-specialised kernel (producer
+ * warps: samples + tensor-core sine sums; consumer warps: interpolation + row stores, overlapped through a ring of bin
+ * tables); 1 = the earlier four bin-count-class kernels (kept for A/B measurements).  Same results either way. */
+int hmv_set_transform_mode(int mode);
 int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                           double kmax /* = max(ks): bounds the bins computed */, const double* rs_d,
                           const double* cmax_d, const double* xc_d, const double* alpha_d, const double* expo_d,
