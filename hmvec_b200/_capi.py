@@ -79,6 +79,10 @@ for _name, (_res, _args) in _SIGS.items():
 
 EXPORTS = tuple(_SIGS)
 
+if os.environ.get("HMV_TRANSFORM_MODE"):       # A/B measurements of the transform's launch plan (see the header)
+    if lib.hmv_set_transform_mode(int(os.environ["HMV_TRANSFORM_MODE"])) != 0:
+        raise ImportError("hmvec_b200: bad HMV_TRANSFORM_MODE=%r" % os.environ["HMV_TRANSFORM_MODE"])
+
 
 def last_error():
     return lib.hmv_last_error().decode("utf-8", "replace")

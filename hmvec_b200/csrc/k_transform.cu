@@ -23,6 +23,7 @@
 // (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints (33 / 49 / 82 / 176 KB)
 // let the many small halos run several CTAs per SM instead of all being sized for the largest one.
 #include "common.cuh"
+#include "gnfw_eval.cuh"
 
 namespace hmv {
 
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
 // registers while the current one is being transformed.
 // Shared memory is only the 90 KB sample chunk, so there are no bin-count classes and no limit on N from the bin table.
-constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256, WS_CT = 256;
+constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256;   // 8 producer warps; consumer warps: template
 
 struct WsSlotMeta {
   int z, m0, jn, nvalid;
@@ -398,6 +399,38 @@ __device__ __forceinline__ double ws_interp(const double* U, double t, double u1
   return (t >= 1.0) ? v : u1;                                // np.interp left=puks[0]
 }
 
+// The same interpolation with 5 FP64-pipe instructions (the pipe is shared with the producers' DMMAs, so every FP64
+// compare, min or conversion here is taken from the sine sums): rint(t) by the 2^52 magic-number add, the offset
+// from the nearest bin by an exact fma, classification (t < 1, t > J) and clamping on integer registers, and
+// v = U[jn] + |t - jn| (U[jn +- 1] - U[jn]), the line through the two bins around t.  Split in two steps so that a
+// lane can issue the table loads of all its elements before the first use (one L2 round trip per block, not eight).
+struct WsLerp {
+  int jc, jo;         // nearest bin and its neighbour on t's side, clamped to the computed bins
+  int cls;            // 0: interpolate, 1: below the first bin (hold u_1), 2: above the last bin (zero)
+  double af;          // |t - rint(t)|
+};
+__device__ __forceinline__ WsLerp ws_lerp_setup(double k, double inv, int J, int jcap) {
+  const double MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
+  const double tm = fma(k, inv, MAGIC);
+  const unsigned jr = (unsigned)__double2loint(tm);          // rint(t) for t < 2^32
+  const int huge = __double2hiint(tm) != 0x43380000;         // t >= 2^32 (or negative / NaN)
+  const double frac = fma(k, inv, -(tm - MAGIC));            // t - rint(t), exact
+  const int fh = __double2hiint(frac), fl = __double2loint(frac);
+  const int neg = fh < 0, pos = (fh >= 0) & ((fh | fl) != 0);
+  const int below = (huge ^ 1) & ((jr < 1u) | ((jr == 1u) & neg));                  // t < 1
+  const int above = huge | (jr > (unsigned)J) | ((jr == (unsigned)J) & pos);        // t > J
+  WsLerp r;
+  r.jc = min(max((int)min(jr, (unsigned)(jcap + 1)), 1), jcap + 1);
+  r.jo = min(r.jc + 1 - 2 * neg, jcap + 1);
+  r.cls = below | (above << 1);
+  r.af = __hiloint2double(fh & 0x7fffffff, fl);
+  return r;
+}
+__device__ __forceinline__ double ws_lerp_finish(const WsLerp& r, double ua, double uo, double u1) {
+  const double v = fma(r.af, uo - ua, ua);
+  return (r.cls & 1) ? u1 : ((r.cls & 2) ? 0.0 : v);
+}
+
 // queue position -> (z, mass-group index counted from the heavy end)
 __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
   z = item / nmg;
@@ -405,16 +438,19 @@ __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, i
   q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
 }
 
+template <int WS_CT>
 __global__ void __launch_bounds__(WS_PT + WS_CT, 1)
-profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride) {
+profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride, int ks_smem) {
   extern __shared__ double smem[];
   double* gs = smem;                          // [NCH_MMA/4][8][4][2]
+  double* kss = smem + NCH_MMA * WS_HB;       // [nk] copy of the target wavenumbers (when it fits: ks_smem)
   __shared__ unsigned long long full[WS_NSLOT], empty[WS_NSLOT];
   __shared__ WsSlotMeta meta[WS_NSLOT];
   __shared__ double h_cmax[WS_HB], h_lxc[WS_HB], h_alpha[WS_HB], h_expo[WS_HB], h_amp[WS_HB], h_oscale[WS_HB],
       h_inv[WS_HB];
   __shared__ double redm[WS_PT / 32][WS_HB];
   __shared__ int nxt_item;
+  __shared__ GnfwTables tabs;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -422,11 +458,22 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     nxt_item = atomicAdd(work_counter, 1);
   }
-  __syncthreads();
+  gnfw_tables_init(tabs, tid, WS_PT + WS_CT);
+  int ascending = 1;
+  for (int k = tid; k < p.nk; k += WS_PT + WS_CT) {
+    const double kv = __ldg(p.ks + k);
+    if (ks_smem) kss[k] = kv;
+    if (k + 1 < p.nk && !(kv <= __ldg(p.ks + k + 1))) ascending = 0;
+  }
+  const int sorted = __syncthreads_and(ascending);     // also publishes the mbarriers and kss
   const int JS = p.JS;
   double* slots = ring + (size_t)blockIdx.x * WS_NSLOT * WS_HB * JS;
 
+  // more than 8 consumer warps: the launch allocation (96 / 80 registers per thread) is re-split so the producers
+  // keep the 128 registers the 8-chain DMMA loop needs and the consumers run on 72 / 56
+  constexpr int CREG = WS_CT == 384 ? 72 : 56;
   if (tid < WS_PT) {
+    if constexpr (WS_CT > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // =============================== producers: samples -> sine sums -> bin table ================================
     const double2* T = reinterpret_cast<const double2*>(p.sintab);
     const int warp = tid >> 5, lane = tid & 31, hoff = (tid & 1) << 3;
@@ -496,23 +543,30 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
 
       for (int n0 = 0; n0 < nb; n0 += NCH_MMA) {
         const int nfill = min(NCH_MMA, ((nb - n0) + 3) & ~3);
-        // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15
+        // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15, the eight
+        // chains of a thread in lock-step (gnfw_eval.cuh); samples outside a halo's theta-cut are masked afterwards
         for (int sn = tid >> 1; sn < nfill; sn += WS_PT / 2) {
           const int n = n0 + sn;
           const double x = (double)(n + 1) * p.dx;
-          const double lx = log(x);
-          const double w = (n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx;   // np.trapz weights on xs (fft.py:84)
+          const double wx = ((n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx) * x;   // np.trapz weights on xs (fft.py:84)
+          double lt[8], y[8], f[8];
+          {
+            const double xv[1] = {x};
+            double lxv[1];
+            log_lockstep<1>(tabs, xv, 0.0, lxv);
+#pragma unroll
+            for (int hh = 0; hh < 8; ++hh) { lt[hh] = lxv[0] - h_lxc[hh + hoff]; y[hh] = h_alpha[hh + hoff] * lt[hh]; }
+          }
+          exp_lockstep<8>(tabs, y, f);                       // t^alpha
+          log_lockstep<8>(tabs, f, 1.0, y);                  // log(1 + t^alpha)
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) y[hh] = fma(-h_expo[hh + hoff], y[hh], p.gamma * lt[hh]);
+          exp_lockstep<8>(tabs, y, f);                       // t^gamma (1 + t^alpha)^(-expo)
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const int h = hh + hoff;
-            double v = 0.0;
-            if (n < p.N && x <= h_cmax[h]) {
-              const double lt = lx - h_lxc[h];
-              // amp * t^gamma * (1+t^alpha)^(-expo)
-              const double rho = h_amp[h] * exp(p.gamma * lt - h_expo[h] * log1p(exp(h_alpha[h] * lt)));
-              v = x * rho;
-              msum[hh] = fma(w * x, v, msum[hh]);
-            }
+            const double v = (n < p.N && x <= h_cmax[h]) ? (x * h_amp[h]) * f[hh] : 0.0;   // x * rho(x) inside the cut
+            msum[hh] = fma(wx, v, msum[hh]);
             gs[ws_gs_index(sn, h)] = v;
           }
         }
@@ -587,10 +641,13 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       item = nxt;
     }
   } else {
+    if constexpr (WS_CT > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CREG));
     // =============================== consumers: interpolate onto ks, store the rows ==============================
     const int ct = tid - WS_PT, lane = ct & 31, cw = ct >> 5;
     const int npair = p.nk >> 1;
-    const double2* ks2 = reinterpret_cast<const double2*>(p.ks);
+    // wavenumbers come from shared memory when the grid fits there (generic pointer: LDS or LDG)
+    const double* ks1 = ks_smem ? kss : p.ks;
+    const double2* ks2 = reinterpret_cast<const double2*>(ks1);
     const double tJ = (double)p.J;
     for (unsigned it = 0;; ++it) {
       const int s = (int)(it % WS_NSLOT);
@@ -606,40 +663,57 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
         const double inv = meta[s].inv[row], u1 = meta[s].u1[row];
         const double* Uh = U + (size_t)row * JS;
         double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk);
-        for (int base = 0; base < npair; base += 128) {          // warp-uniform trip count (the vote below)
-          double2 kk[4];
-          bool lt1 = true;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int k2 = base + lane + 32 * u;
-            kk[u] = (k2 < npair) ? __ldg(ks2 + k2) : make_double2(0.0, 0.0);
-            kk[u].x *= inv; kk[u].y *= inv;
-            lt1 = lt1 && kk[u].x < 1.0 && kk[u].y < 1.0;
-          }
-          if (__all_sync(0xffffffffu, lt1)) {
-            const double2 v = make_double2(u1, u1);
+        // sorted ks: [0, eA) is below the first bin (hold u_1), [eB, nk) is above the last one (zero); whole blocks
+        // inside those spans are plain fills.  Unsorted ks: every block takes the general path.
+        int pA = 0, pB = npair;
+        if (sorted) {
+          int lo = 0, hi = p.nk;                       // first element with k*inv >= 1
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv >= 1.0) hi = mid; else lo = mid + 1; }
+          pA = lo >> 1;
+          lo = 0; hi = p.nk;                           // first element with k*inv > J
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv > tJ) hi = mid; else lo = mid + 1; }
+          pB = (lo + 1) >> 1;
+        }
+        for (int base = 0; base < npair; base += 128) {
+          if (base + 128 <= pA || base >= pB) {
+            const double c = (base >= pB) ? 0.0 : u1;
+            const double2 v = make_double2(c, c);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int k2 = base + lane + 32 * u;
               if (k2 < npair) __stcs(orow + k2, v);
             }
           } else {
-            double2 v[4];
+            {  // pull the table lines the NEXT block will read into L1 while this one is interpolated (sorted ks:
+               // the bins between its first and last wavenumber, one 128-byte line per lane; a hint otherwise)
+              const int e0 = min(2 * (base + 128), p.nk - 1), e1 = min(2 * (base + 256) - 1, p.nk - 1);
+              const int j0 = (int)fmin(ks1[e0] * inv, (double)jcap), j1 = (int)fmin(ks1[e1] * inv, (double)(jcap + 1));
+              for (int j = (j0 & ~15) + 16 * lane; j <= j1; j += 512)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
+            }
+            WsLerp e[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              v[u].x = ws_interp(Uh, kk[u].x, u1, tJ, jcap);
-              v[u].y = ws_interp(Uh, kk[u].y, u1, tJ, jcap);
+              const int k2 = min(base + lane + 32 * u, npair - 1);
+              const double2 kk = ks2[k2];
+              e[2 * u] = ws_lerp_setup(kk.x, inv, p.J, jcap);
+              e[2 * u + 1] = ws_lerp_setup(kk.y, inv, p.J, jcap);
             }
+            double ua[8], uo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ua[i] = Uh[e[i].jc]; uo[i] = Uh[e[i].jo]; }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int k2 = base + lane + 32 * u;
-              if (k2 < npair) __stcs(orow + k2, v[u]);
+              const double2 v = make_double2(ws_lerp_finish(e[2 * u], ua[2 * u], uo[2 * u], u1),
+                                             ws_lerp_finish(e[2 * u + 1], ua[2 * u + 1], uo[2 * u + 1], u1));
+              if (k2 < npair) __stcs(orow + k2, v);
             }
           }
         }
         if ((p.nk & 1) && lane == 0) {         // odd nk: the last wavenumber
           const int k = p.nk - 1;
-          out0[(long long)row * p.ldk + k] = ws_interp(Uh, __ldg(p.ks + k) * inv, u1, tJ, jcap);
+          out0[(long long)row * p.ldk + k] = ws_interp(Uh, ks1[k] * inv, u1, tJ, jcap);
         }
       }
       __syncwarp();
@@ -652,6 +726,7 @@ static bool ws_ring_fits(int nxs) {
   return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)1 << 30);
 }
 
+static int g_ws_consumer_warps = 8, g_ws_ks_smem = 1;
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
 
 static int launch_transform_ws(const TParams& p, double* ring, int* counter, cudaStream_t st) {
@@ -669,11 +744,20 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int stride = (int)(0.381966 * q.nmg);
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
-  const size_t smem = (size_t)NCH_MMA * WS_HB * sizeof(double);
-  e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  profile_transform_ws_kernel<<<grid, WS_PT + WS_CT, smem, st>>>(q, ring, counter, nitems, stride);
-  return check_launch("profile_transform_ws_kernel");
+  size_t smem = (size_t)NCH_MMA * WS_HB * sizeof(double);
+  const int ks_smem = g_ws_ks_smem && smem + (size_t)(p.nk + 1) * sizeof(double) <= (size_t)220 * 1024;
+  if (ks_smem) smem += (size_t)(p.nk + 1) * sizeof(double);
+  auto go = [&](auto kern, int ct) {
+    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e2));
+    kern<<<grid, WS_PT + ct, smem, st>>>(q, ring, counter, nitems, stride, ks_smem);
+    return check_launch("profile_transform_ws_kernel");
+  };
+  switch (g_ws_consumer_warps) {
+    case 12: return go(profile_transform_ws_kernel<384>, 384);
+    case 16: return go(profile_transform_ws_kernel<512>, 512);
+    default: return go(profile_transform_ws_kernel<256>, 256);
+  }
 }
 
 template <int HB, int NCH>
@@ -708,6 +792,14 @@ extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
 }
 
 extern "C" int hmv_set_transform_mode(int mode) {
+  if (mode >= 100) {   // tuning hook: 108 / 112 / 116 = persistent kernel with 8 / 12 / 16 consumer warps
+    g_ws_ks_smem = mode < 200;
+    if (mode >= 200) mode -= 100;               // 2xx: wavenumbers read from global memory instead of shared
+    HMV_REQUIRE(mode == 108 || mode == 112 || mode == 116, "hmv_set_transform_mode: bad tuning mode %d", mode);
+    g_ws_consumer_warps = mode - 100;
+    g_transform_mode = 0;
+    return HMV_OK;
+  }
   HMV_REQUIRE(mode == 0 || mode == 1, "hmv_set_transform_mode: mode must be 0 (persistent) or 1 (bin-count classes)");
   g_transform_mode = mode;
   return HMV_OK;

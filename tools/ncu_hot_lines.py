@@ -36,15 +36,21 @@ def main():
             ins = int(r[hdr.index("Instructions Executed")] or 0)
         except ValueError:
             continue
-        kernels[-1][2][(int(r[0]), r[1].strip()[:110])] = (smp, ins)
+        st = {}
+        for i, h in enumerate(hdr):
+            if h.startswith("stall_") and "Not Issued" not in h and r[i].strip().isdigit() and int(r[i]):
+                st[h[6:]] = int(r[i])
+        kernels[-1][2][(int(r[0]), r[1].strip()[:90])] = (smp, ins, st)
     for name, hdr, agg in kernels:
         if not agg:
             continue
         tot = sum(v[0] for v in agg.values()) or 1
         toti = sum(v[1] for v in agg.values()) or 1
         print("=== %s   (samples %d, warp-instructions %d)" % (name[:90], tot, toti))
-        for (ln, src), (smp, ins) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-            print("  %5.1f%% smp %5.1f%% inst  L%-4d %s" % (100.0 * smp / tot, 100.0 * ins / toti, ln, src))
+        for (ln, src), (smp, ins, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+            why = " ".join("%s:%d%%" % (k, round(100.0 * v / max(1, sum(st.values()))))
+                           for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
+            print("  %5.1f%% smp %5.1f%% inst  L%-4d %-90s | %s" % (100.0 * smp / tot, 100.0 * ins / toti, ln, src, why))
 
 
 if __name__ == "__main__":
