@@ -431,6 +431,17 @@ __device__ __forceinline__ double ws_lerp_finish(const WsLerp& r, double ua, dou
   return (r.cls & 1) ? u1 : ((r.cls & 2) ? 0.0 : v);
 }
 
+// Interior of a sorted row (every t of the block inside [1, J], bins inside the computed range): no classification.
+__device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned jmax, unsigned& jc, unsigned& jo, double& af) {
+  const double MAGIC = 6755399441055744.0;
+  const double tm = fma(k, inv, MAGIC);
+  const double frac = fma(k, inv, -(tm - MAGIC));
+  const int fh = __double2hiint(frac);
+  jc = min((unsigned)__double2loint(tm), jmax);
+  jo = jc + 1u + (unsigned)((fh >> 31) << 1);                // +1, or -1 when t is left of its nearest bin
+  af = __hiloint2double(fh & 0x7fffffff, __double2loint(frac));
+}
+
 // queue position -> (z, mass-group index counted from the heavy end)
 __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
   z = item / nmg;
@@ -665,14 +676,16 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
         double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk);
         // sorted ks: [0, eA) is below the first bin (hold u_1), [eB, nk) is above the last one (zero); whole blocks
         // inside those spans are plain fills.  Unsorted ks: every block takes the general path.
-        int pA = 0, pB = npair;
+        int pA = 0, pB = npair, pA1 = npair, pB0 = 0;   // (unsorted: no interior blocks)
         if (sorted) {
           int lo = 0, hi = p.nk;                       // first element with k*inv >= 1
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv >= 1.0) hi = mid; else lo = mid + 1; }
           pA = lo >> 1;
+          pA1 = (lo + 1) >> 1;
           lo = 0; hi = p.nk;                           // first element with k*inv > J
           while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv > tJ) hi = mid; else lo = mid + 1; }
           pB = (lo + 1) >> 1;
+          pB0 = lo >> 1;                               // pairs [pA1, pB0) lie entirely inside [eA, eB)
         }
         for (int base = 0; base < npair; base += 128) {
           if (base + 128 <= pA || base >= pB) {
@@ -683,6 +696,29 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
               const int k2 = base + lane + 32 * u;
               if (k2 < npair) __stcs(orow + k2, v);
             }
+          } else if (base >= pA1 && base + 128 <= pB0) {
+            // whole block strictly inside [eA, eB): 1 <= t <= J for all of its 256 wavenumbers
+            {
+              const int e0 = min(2 * (base + 128), p.nk - 1), e1 = min(2 * (base + 256) - 1, p.nk - 1);
+              const int j0 = (int)fmin(ks1[e0] * inv, (double)jcap), j1 = (int)fmin(ks1[e1] * inv, (double)(jcap + 1));
+              for (int j = (j0 & ~15) + 16 * lane; j <= j1; j += 512)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
+            }
+            unsigned jc[8], jo[8];
+            double af[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const double2 kk = ks2[base + lane + 32 * u];
+              ws_lerp_interior(kk.x, inv, (unsigned)(jcap + 1), jc[2 * u], jo[2 * u], af[2 * u]);
+              ws_lerp_interior(kk.y, inv, (unsigned)(jcap + 1), jc[2 * u + 1], jo[2 * u + 1], af[2 * u + 1]);
+            }
+            double ua[8], uo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ua[i] = Uh[jc[i]]; uo[i] = Uh[jo[i]]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              __stcs(orow + base + lane + 32 * u, make_double2(fma(af[2 * u], uo[2 * u] - ua[2 * u], ua[2 * u]),
+                                                               fma(af[2 * u + 1], uo[2 * u + 1] - ua[2 * u + 1], ua[2 * u + 1])));
           } else {
             {  // pull the table lines the NEXT block will read into L1 while this one is interpolated (sorted ks:
                // the bins between its first and last wavenumber, one 128-byte line per lane; a hint otherwise)
