@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhmvec_b200.so")
+LIB_PATH = os.environ.get("HMV_LIB") or os.path.join(_HERE, "libhmvec_b200.so")   # HMV_LIB: A/B builds of the same ABI
 
 HMV_BISECT_MAXIT = 64
 HMV_BISECT_ROUND1 = 24      # iterations of the first bisection round (rtol 1e-4 on [7,14] needs ~19)

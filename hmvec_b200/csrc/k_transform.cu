@@ -30,7 +30,7 @@ namespace hmv {
 struct TParams {
   int nz, nm, nk, ldk, N, J, JS, nmg, do_mass_norm, jlo, jhi;
   double gamma, dx, step, kt1, kmax;
-  const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab;
+  const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab, *rkt;
   const int* jn_cta;
   double* uk;
 };
@@ -42,12 +42,13 @@ struct TParams {
 constexpr int NCH_MMA = 704, NCH_ROT = 256;
 
 // {sin, cos}(2 pi m/N) for m < N: seeds of the tensor-core path (read with __ldg, 16 bytes per entry)
-__global__ void sine_table_kernel(int N, double2* __restrict__ tab) {
+__global__ void sine_table_kernel(int N, double2* __restrict__ tab, double kt1, double* __restrict__ rkt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) {
     double sn, cs;
     sincospi(2.0 * (double)i / (double)N, &sn, &cs);
     tab[i] = make_double2(sn, cs);
+    if (rkt && i <= N / 2 + 1) rkt[i] = i ? 1.0 / ((double)i * kt1) : 0.0;   // 1/kt_j  (fft.py:91)
   }
 }
 
@@ -328,8 +329,11 @@ __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;"
 
 // sample n of halo h inside a chunk: [n/4][h%8][n%4][h/8] -- the A fragments (sample kq of halo nq, both M tiles) of a
 // 4-sample MMA step are 32 consecutive 16-byte words, one conflict-free LDS.128 per lane
+// (WS_GSB = doubles per 4-sample block; padding it to 72 to spread the evaluation's stores over more banks was
+// measured: no gain, the A-fragment loads then straddle an extra bank row)
+constexpr int WS_GSB = 64;
 __device__ __forceinline__ int ws_gs_index(int sn, int h) {
-  return ((sn >> 2) << 6) + ((h & 7) << 3) + ((sn & 3) << 1) + (h >> 3);
+  return (sn >> 2) * WS_GSB + ((h & 7) << 3) + ((sn & 3) << 1) + (h >> 3);
 }
 
 // D[16 halos][8 bins] += A[16][4 samples] B[4][8] as two m8n8k4 DMMAs sharing the B fragment; NT bin tiles per warp.
@@ -338,7 +342,8 @@ __device__ __forceinline__ int ws_gs_index(int sn, int h) {
 template <int NT>
 __device__ __forceinline__ void accum_mma_ws(const double2* __restrict__ tab, const double* __restrict__ gs, double* U,
                                              int JS, int N, int n0, int nlen, int jw, int jn, int lane, bool first,
-                                             bool fuse, double scale0, double scale1, double kt1, double* u1_out) {
+                                             bool fuse, double scale0, double scale1, const double* __restrict__ rkt,
+                                             double* u1_out) {
   const int kq = lane & 3, nq = lane >> 2;
   double bc[NT], bp[NT], tc[NT], c[NT][2][2];
 #pragma unroll
@@ -356,7 +361,7 @@ __device__ __forceinline__ void accum_mma_ws(const double2* __restrict__ tab, co
   const double2* ga = reinterpret_cast<const double2*>(gs) + (nq << 2) + kq;
 #pragma unroll 2
   for (int nn = 0; nn < nlen; nn += 4) {
-    const double2 a = ga[nn << 3];
+    const double2 a = ga[(nn >> 2) * (WS_GSB / 2)];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -381,7 +386,7 @@ __device__ __forceinline__ void accum_mma_ws(const double2* __restrict__ tab, co
           double v = c[t][mt][e];
           if (!first) v += Uh[b];
           if (fuse) {
-            v *= sc / ((double)b * kt1);
+            v *= sc * __ldg(rkt + b);
             if (b == 1) u1_out[nq + 8 * mt] = v;
           }
           Uh[b] = v;
@@ -442,6 +447,17 @@ __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned 
   af = __hiloint2double(fh & 0x7fffffff, __double2loint(frac));
 }
 
+// pairs [lo, hi) of a row <- (c, c): the spans of a sorted row that need no interpolation
+__device__ __forceinline__ void ws_fill(double2* orow, int lo, int hi, double c, int lane) {
+  const double2 v = make_double2(c, c);
+  int k2 = lo + lane;
+  for (; k2 + 96 < hi; k2 += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) __stcs(orow + k2 + 32 * u, v);
+  }
+  for (; k2 < hi; k2 += 32) __stcs(orow + k2, v);
+}
+
 // queue position -> (z, mass-group index counted from the heavy end)
 __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
   z = item / nmg;
@@ -454,7 +470,7 @@ __global__ void __launch_bounds__(WS_PT + WS_CT, 1)
 profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride, int ks_smem) {
   extern __shared__ double smem[];
   double* gs = smem;                          // [NCH_MMA/4][8][4][2]
-  double* kss = smem + NCH_MMA * WS_HB;       // [nk] copy of the target wavenumbers (when it fits: ks_smem)
+  double* kss = smem + (NCH_MMA / 4) * WS_GSB;       // [nk] copy of the target wavenumbers (when it fits: ks_smem)
   __shared__ unsigned long long full[WS_NSLOT], empty[WS_NSLOT];
   __shared__ WsSlotMeta meta[WS_NSLOT];
   __shared__ double h_cmax[WS_HB], h_lxc[WS_HB], h_alpha[WS_HB], h_expo[WS_HB], h_amp[WS_HB], h_oscale[WS_HB],
@@ -603,23 +619,25 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
         const int nlen = min(NCH_MMA, nb - n0);
         constexpr int NW = WS_PT / 32;
         const int ntile = (jn + 7) >> 3;
+#define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.rkt, meta[s].u1)
         const bool first = n0 == 0;
-        for (int t0 = 0; t0 < ntile;) {
-          const int per = (ntile - t0 + NW - 1) / NW;        // tiles each warp still has to take
-          const int ntc = per >= 4 ? 4 : per;
-          const int jw = 1 + 8 * (t0 + warp * ntc);
-          if (jw <= jn) {
-#define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.kt1, meta[s].u1)
-            switch (ntc) {
-              case 4: HMV_WS_ACC(4); break;
-              case 3: HMV_WS_ACC(3); break;
-              case 2: HMV_WS_ACC(2); break;
-              default: HMV_WS_ACC(1); break;
-            }
-#undef HMV_WS_ACC
+        // bin tiles split evenly over the warps (counts differ by at most one), each warp's share in passes of up to
+        // four tiles of equal size (5 tiles: 3 + 2, not 4 + 1, so that no pass runs on two accumulator chains)
+        int rem = ntile / NW + (warp < ntile % NW);
+        int tb = warp * (ntile / NW) + min(warp, ntile % NW);
+        for (int passes = (rem + 3) >> 2; passes > 0; --passes) {
+          const int ntc = (rem + passes - 1) / passes;
+          const int jw = 1 + 8 * tb;
+          switch (ntc) {
+            case 4: HMV_WS_ACC(4); break;
+            case 3: HMV_WS_ACC(3); break;
+            case 2: HMV_WS_ACC(2); break;
+            default: HMV_WS_ACC(1); break;
           }
-          t0 += ntc * NW;
+          tb += ntc;
+          rem -= ntc;
         }
+#undef HMV_WS_ACC
         producer_bar();                        // the chunk's samples are consumed, its sums are in the table
       }
 
@@ -640,7 +658,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             mn = 0.0;
             for (int w8 = 0; w8 < WS_PT / 32; ++w8) mn += redm[w8][h];
           }
-          const double v = U[(size_t)h * JS + j] * (p.step / mn * h_oscale[h]) / ((double)j * p.kt1);
+          const double v = U[(size_t)h * JS + j] * (p.step / mn * h_oscale[h]) * __ldg(p.rkt + j);
           U[(size_t)h * JS + j] = v;
           if (j == 1) meta[s].u1[h] = v;
         }
@@ -687,23 +705,19 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
           pB = (lo + 1) >> 1;
           pB0 = lo >> 1;                               // pairs [pA1, pB0) lie entirely inside [eA, eB)
         }
-        for (int base = 0; base < npair; base += 128) {
-          if (base + 128 <= pA || base >= pB) {
-            const double c = (base >= pB) ? 0.0 : u1;
-            const double2 v = make_double2(c, c);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int k2 = base + lane + 32 * u;
-              if (k2 < npair) __stcs(orow + k2, v);
-            }
-          } else if (base >= pA1 && base + 128 <= pB0) {
+        const int pA0 = pA & ~127;                                   // blocks stay aligned to 2 KB of the row
+        ws_fill(orow, 0, pA0, u1, lane);                             // below the first bin: hold u_1
+        for (int base = pA0; base < pB; base += 128) {
+          {  // table lines the NEXT block reads go to L1 while this one is interpolated: the bins between its first
+             // and last wavenumber, one 128-byte line per lane (sorted ks; merely a hint otherwise)
+            const double MAGIC = 6755399441055744.0;
+            const unsigned j0 = min((unsigned)__double2loint(fma(ks1[min(2 * (base + 128), p.nk - 1)], inv, MAGIC)), (unsigned)jcap);
+            const unsigned j1 = min((unsigned)__double2loint(fma(ks1[min(2 * (base + 256) - 1, p.nk - 1)], inv, MAGIC)), (unsigned)(jcap + 1));
+            for (unsigned j = (max(j0, 1u) - 1u & ~15u) + 16u * lane; j <= j1; j += 512u)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
+          }
+          if (base >= pA1 && base + 128 <= pB0) {
             // whole block strictly inside [eA, eB): 1 <= t <= J for all of its 256 wavenumbers
-            {
-              const int e0 = min(2 * (base + 128), p.nk - 1), e1 = min(2 * (base + 256) - 1, p.nk - 1);
-              const int j0 = (int)fmin(ks1[e0] * inv, (double)jcap), j1 = (int)fmin(ks1[e1] * inv, (double)(jcap + 1));
-              for (int j = (j0 & ~15) + 16 * lane; j <= j1; j += 512)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
-            }
             unsigned jc[8], jo[8];
             double af[8];
 #pragma unroll
@@ -720,13 +734,6 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
               __stcs(orow + base + lane + 32 * u, make_double2(fma(af[2 * u], uo[2 * u] - ua[2 * u], ua[2 * u]),
                                                                fma(af[2 * u + 1], uo[2 * u + 1] - ua[2 * u + 1], ua[2 * u + 1])));
           } else {
-            {  // pull the table lines the NEXT block will read into L1 while this one is interpolated (sorted ks:
-               // the bins between its first and last wavenumber, one 128-byte line per lane; a hint otherwise)
-              const int e0 = min(2 * (base + 128), p.nk - 1), e1 = min(2 * (base + 256) - 1, p.nk - 1);
-              const int j0 = (int)fmin(ks1[e0] * inv, (double)jcap), j1 = (int)fmin(ks1[e1] * inv, (double)(jcap + 1));
-              for (int j = (j0 & ~15) + 16 * lane; j <= j1; j += 512)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
-            }
             WsLerp e[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -743,10 +750,11 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
               const int k2 = base + lane + 32 * u;
               const double2 v = make_double2(ws_lerp_finish(e[2 * u], ua[2 * u], uo[2 * u], u1),
                                              ws_lerp_finish(e[2 * u + 1], ua[2 * u + 1], uo[2 * u + 1], u1));
-              if (k2 < npair) __stcs(orow + k2, v);
+              if (k2 < pB) __stcs(orow + k2, v);
             }
           }
         }
+        ws_fill(orow, pB, npair, 0.0, lane);                         // above the last bin: zero
         if ((p.nk & 1) && lane == 0) {         // odd nk: the last wavenumber
           const int k = p.nk - 1;
           out0[(long long)row * p.ldk + k] = ws_interp(Uh, ks1[k] * inv, u1, tJ, jcap);
@@ -780,7 +788,7 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int stride = (int)(0.381966 * q.nmg);
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
-  size_t smem = (size_t)NCH_MMA * WS_HB * sizeof(double);
+  size_t smem = (size_t)(NCH_MMA / 4) * WS_GSB * sizeof(double);
   const int ks_smem = g_ws_ks_smem && smem + (size_t)(p.nk + 1) * sizeof(double) <= (size_t)220 * 1024;
   if (ks_smem) smem += (size_t)(p.nk + 1) * sizeof(double);
   auto go = [&](auto kern, int ct) {
@@ -822,7 +830,7 @@ using namespace hmv;
 extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
   // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
-  long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2;
+  long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2 + (nxs / 2 + 2);   // ..., queue head, 1/kt_j
   if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NSLOT * WS_HB * (nxs / 2 + 2);   // bin-table ring of the persistent kernel
   return n;
 }
@@ -865,7 +873,9 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.jn_cta = jn_cta;
   double* after_jn = ws_d + 2 * (size_t)nxs + 2 + ((size_t)nz * nm + 1) / 2 + 2;
   int* counter = reinterpret_cast<int*>(after_jn);
-  double* ring = after_jn + 2;
+  double* rkt = after_jn + 2;
+  double* ring = rkt + (nxs / 2 + 2);
+  p.rkt = rkt;
   cudaStream_t st = (cudaStream_t)stream;
   auto bin_counts = [&](int HB) {
     const int nmg = cdiv(nm, HB);
@@ -876,7 +886,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   const bool aligned16 = (((size_t)ks_d | (size_t)uk_d | (size_t)ws_d) & 15) == 0 && (ldk & 1) == 0;
   if (g_transform_mode == 0 && ws_ring_fits(nxs) && aligned16) {
     // persistent warp-specialised kernel: sine table, bin counts, one launch
-    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d));
+    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d), p.kt1, rkt);
     int rc = check_launch("sine_table_kernel");
     if (rc) return rc;
     rc = bin_counts(WS_HB);
@@ -887,7 +897,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   const int J = p.J;
   if (transform_smem<8, NCH_MMA>(J + 2) <= budget) {
     // table path, three bin-count classes (a CTA whose bin count is outside (jlo, jhi] exits immediately)
-    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d));
+    sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d), p.kt1, nullptr);
     int rc = check_launch("sine_table_kernel");
     if (rc) return rc;
     rc = bin_counts(8);

@@ -256,3 +256,33 @@ def test_unsorted_wavenumbers(hm, golden_mini):
     for tag, a, b in SPECTRA:
         assert_close(h.get_power_1halo(a, b), g["P1h_" + tag][:, perm], 1e-6, name="P1h_" + tag)
         assert_close(h.get_power_2halo(a, b), g["P2h_" + tag][:, perm], 1e-6, name="P2h_" + tag)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_transform_ragged_grid_and_long_profile(hm, mode):
+    """Shapes the golden grids do not hold, against the CPU oracle, for both launch plans of the transform
+    (0: persistent warp-specialised kernel, 1: bin-count-class kernels): a mass axis that is not a multiple of the
+    16-halo item (last item partly empty), an odd number of wavenumbers (scalar tail behind the 16-byte pairs),
+    a k-range that starts above some halos' first bin and ends beyond the last bin of the big ones (all three
+    interpolation zones), and a profile of ~2000 samples inside the theta-cut (three 704-sample chunks: the
+    accumulate-then-normalise path)."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle.hmvec_oracle import OracleHaloModel
+    from hmvec_b200 import _capi as capi
+    zs = np.array([0.0, 0.7, 2.5])
+    ms = np.geomspace(3e10, 8e16, 37)
+    ks = np.geomspace(2e-3, 4e3, 333)
+    try:
+        capi.check(capi.lib.hmv_set_transform_mode(mode), "hmv_set_transform_mode")
+        h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+        o = OracleHaloModel(zs, ks, ms)
+        for name, kw in (("e5", dict(xmax=20, nxs=5000)), ("elong", dict(xmax=20, nxs=14000)), ("eodd", dict(xmax=15, nxs=3001))):
+            h.add_battaglia_profile(name, family="AGN", **kw)
+            o.add_battaglia_profile(name, family="AGN", **kw)
+            assert_close(h.uk_profiles[name], o.uk_profiles[name], 1e-6, OSC, "uk_%s (mode %d)" % (name, mode))
+        h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+        o.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+        assert_close(h.pk_profiles["y"], o.pk_profiles["y"], 1e-6, OSC, "pk_y (mode %d)" % mode)
+    finally:
+        capi.lib.hmv_set_transform_mode(0)
