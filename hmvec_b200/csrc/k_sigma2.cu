@@ -27,6 +27,9 @@ __global__ void w2_table_kernel(int nm, int nks, const double* __restrict__ ks, 
 // CTA tile 32 (z) x 64 (m), k staged 16 at a time through shared memory; warp w owns the 8 x 32 strip
 // (rows 8 (w&3), columns 32 (w>>2)) as four mma.sync m8n8k4 tiles.  Split-k across blockIdx.z.
 constexpr int BM = 32, BN = 64, BK = 16, GT = 256;
+#ifndef HMV_SIGMA2_CTAS
+#define HMV_SIGMA2_CTAS (16 * 148)
+#endif
 
 __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks, int kchunk,
                                                          const double* __restrict__ sPzk,
@@ -91,7 +94,7 @@ __global__ void splitk_reduce_kernel(long long n, int nsplit, const double* __re
 
 static int sigma2_splits(int nz, int nm, int nks) {
   const long long tiles = (long long)cdiv(nm, BN) * cdiv(nz, BM);
-  long long s = (2 * 148 + tiles - 1) / tiles;
+  long long s = (HMV_SIGMA2_CTAS + tiles - 1) / tiles;   // enough resident CTAs per SM to hide the un-pipelined loads
   if (s < 1) s = 1;
   if (s > 32) s = 32;
   const long long maxs = (nks + BK - 1) / BK;
