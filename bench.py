@@ -189,7 +189,7 @@ def run_b200(a):
     g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs,
                          fused_nfw=a.fused_nfw)
     capi.check(capi.lib.hmv_set_transform_mode(a.transform_mode), "hmv_set_transform_mode")
-    g.transform_mode = 1 if a.transform_mode == 1 else 0
+    g.transform_mode = a.transform_mode
     g.upload()
     torch.cuda.synchronize()
 
@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--nl", type=int, default=1000)
     ap.add_argument("--cpu-nz", type=int, default=2, help="redshifts in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--transform-mode", type=int, default=0, choices=[0, 1, 108, 112, 116, 208, 212, 216],
+    ap.add_argument("--transform-mode", type=int, default=0, choices=[0, 1],
                     help="K1 launch plan: 0 = persistent warp-specialised kernel (default), 1 = bin-count-class kernels")
     ap.add_argument("--fused-nfw", action="store_true",
                     help="evaluate the NFW profile inside the mass reduction (hmv_power_six_nfw) instead of writing "

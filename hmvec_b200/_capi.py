@@ -66,6 +66,7 @@ _SIGS = {
     "hmv_power_six_nfw": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll,
                                _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "hmv_bench_dfma": (_d, [_i, _p]),
     "hmv_bench_dmma": (_d, [_i, _p]),
     "hmv_bench_copy": (_d, [_p, _p, _ll, _i, _p]),

@@ -198,9 +198,18 @@ class Cosmology(object):
         return 3. * (Hz ** 2.) / 8. / np.pi / G * 1.477543e37
 
     # ------------------------------------------------------------------ linear power (host input)
+    def _pk_grid(self, PK, zs, ks):
+        """PK.P(zs, ks, grid=True) of a RectBivariateSpline-based interpolator, evaluated on the GPU (hmv_pk_spline)."""
+        from .utils import PKInterpolatorDevice
+        if not isinstance(PK, PKInterpolatorDevice):
+            if not hasattr(PK, "tck"):                   # single-redshift interp1d objects: tiny, host
+                return PK.P(zs, ks, grid=True)
+            PK = PKInterpolatorDevice.from_spline(PK, device=self.device)
+        return PK.P(np.atleast_1d(zs), np.atleast_1d(ks), grid=True)
+
     def _get_matter_power(self, zs, ks, nonlinear=False):
         PK = self.get_pk_interpolator(zs, kmax=np.max(ks), var='total', nonlinear=nonlinear)
-        return (self.as8 ** 2.) * PK.P(zs, ks, grid=True)
+        return (self.as8 ** 2.) * self._pk_grid(PK, zs, ks)
 
     def get_pk_interpolator(self, zs, kmax, var='total', nonlinear=False):
         if not hasattr(self, '_camb_pars'):
@@ -257,7 +266,7 @@ class Cosmology(object):
         if knorm >= kmax:
             raise ValueError
         PK = self.get_pk_interpolator(zs, kmax=kmax, var='total', nonlinear=False)
-        pnorm = PK.P(zs, knorm, grid=True)
+        pnorm = self._pk_grid(PK, zs, knorm)
         tnorm = self.Tk(knorm, 'eisenhu_osc') * knorm ** (self.params['ns'])
         return (self.as8 ** 2.) * (pnorm / tnorm) * tk ** 2. * ks ** (self.params['ns'])
 
@@ -266,7 +275,7 @@ class Cosmology(object):
         if kmax is None:
             kmax = ks.max()
         PK = self.get_pk_interpolator(zs, kmax=kmax, var='total', nonlinear=False)
-        return (self.as8 ** 2.) * PK.P(zs, ks, grid=True)
+        return (self.as8 ** 2.) * self._pk_grid(PK, zs, ks)
 
     # ------------------------------------------------------------------ sigma^2 (device, K3)
     def _sigma2_inputs(self, zs, kmin=None, kmax=None, numks=None):

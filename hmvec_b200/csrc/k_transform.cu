@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
 // registers while the current one is being transformed.
 // Shared memory is only the 90 KB sample chunk, so there are no bin-count classes and no limit on N from the bin table.
-constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256;   // 8 producer warps; consumer warps: template
+constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256, WS_CT = 256;   // 8 producer + 8 consumer warps
 
 struct WsSlotMeta {
   int z, m0, jn, nvalid;
@@ -465,7 +465,6 @@ __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, i
   q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
 }
 
-template <int WS_CT>
 __global__ void __launch_bounds__(WS_PT + WS_CT, 1)
 profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride, int ks_smem) {
   extern __shared__ double smem[];
@@ -496,11 +495,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   const int JS = p.JS;
   double* slots = ring + (size_t)blockIdx.x * WS_NSLOT * WS_HB * JS;
 
-  // more than 8 consumer warps: the launch allocation (96 / 80 registers per thread) is re-split so the producers
-  // keep the 128 registers the 8-chain DMMA loop needs and the consumers run on 72 / 56
-  constexpr int CREG = WS_CT == 384 ? 72 : 56;
   if (tid < WS_PT) {
-    if constexpr (WS_CT > 256) asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
     // =============================== producers: samples -> sine sums -> bin table ================================
     const double2* T = reinterpret_cast<const double2*>(p.sintab);
     const int warp = tid >> 5, lane = tid & 31, hoff = (tid & 1) << 3;
@@ -670,7 +665,6 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       item = nxt;
     }
   } else {
-    if constexpr (WS_CT > 256) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CREG));
     // =============================== consumers: interpolate onto ks, store the rows ==============================
     const int ct = tid - WS_PT, lane = ct & 31, cw = ct >> 5;
     const int npair = p.nk >> 1;
@@ -770,7 +764,6 @@ static bool ws_ring_fits(int nxs) {
   return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)1 << 30);
 }
 
-static int g_ws_consumer_warps = 8, g_ws_ks_smem = 1;
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
 
 static int launch_transform_ws(const TParams& p, double* ring, int* counter, cudaStream_t st) {
@@ -789,19 +782,12 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
   size_t smem = (size_t)(NCH_MMA / 4) * WS_GSB * sizeof(double);
-  const int ks_smem = g_ws_ks_smem && smem + (size_t)(p.nk + 1) * sizeof(double) <= (size_t)220 * 1024;
+  const int ks_smem = smem + (size_t)(p.nk + 1) * sizeof(double) <= (size_t)220 * 1024;
   if (ks_smem) smem += (size_t)(p.nk + 1) * sizeof(double);
-  auto go = [&](auto kern, int ct) {
-    cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e2 != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e2));
-    kern<<<grid, WS_PT + ct, smem, st>>>(q, ring, counter, nitems, stride, ks_smem);
-    return check_launch("profile_transform_ws_kernel");
-  };
-  switch (g_ws_consumer_warps) {
-    case 12: return go(profile_transform_ws_kernel<384>, 384);
-    case 16: return go(profile_transform_ws_kernel<512>, 512);
-    default: return go(profile_transform_ws_kernel<256>, 256);
-  }
+  e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  profile_transform_ws_kernel<<<grid, WS_PT + WS_CT, smem, st>>>(q, ring, counter, nitems, stride, ks_smem);
+  return check_launch("profile_transform_ws_kernel");
 }
 
 template <int HB, int NCH>
@@ -836,14 +822,6 @@ extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
 }
 
 extern "C" int hmv_set_transform_mode(int mode) {
-  if (mode >= 100) {   // tuning hook: 108 / 112 / 116 = persistent kernel with 8 / 12 / 16 consumer warps
-    g_ws_ks_smem = mode < 200;
-    if (mode >= 200) mode -= 100;               // 2xx: wavenumbers read from global memory instead of shared
-    HMV_REQUIRE(mode == 108 || mode == 112 || mode == 116, "hmv_set_transform_mode: bad tuning mode %d", mode);
-    g_ws_consumer_warps = mode - 100;
-    g_transform_mode = 0;
-    return HMV_OK;
-  }
   HMV_REQUIRE(mode == 0 || mode == 1, "hmv_set_transform_mode: mode must be 0 (persistent) or 1 (bin-count classes)");
   g_transform_mode = mode;
   return HMV_OK;

@@ -179,6 +179,16 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
                const double* P_d, const double* P2_d, int ngz, const double* gzs_d, const double* pref_d,
                const double* chis_d, double* cl_d, void* stream);
 
+/* ---- next row: P(z,k) from a matter-power interpolator  (cosmology.py:227-229, 353-382;
+ *      utils.py:95-103 `PKInterpolator.P`; CAMB get_matter_power_interpolator) -------------------------------
+ * out[z][k] = scale * (islog ? exp(s) : s),  s = the tensor-product B-spline (knots tx[nx], ty[ny], degrees kx, ky,
+ * coefficients c[(nx-kx-1)(ny-ky-1)], as in scipy RectBivariateSpline.tck) evaluated at (zs[z], ln ks[k]) with
+ * FITPACK bispev's conventions (arguments clamped to the knot range).  The fit itself stays on the host.
+ * scale carries logsign * as8^2. */
+int hmv_pk_spline(int nz, int nk, const double* zs_d, const double* ks_d, int nx, int ny, int kx, int ky,
+                  const double* tx_d, const double* ty_d, const double* c_d, int islog, double scale, double* out_d,
+                  void* stream);
+
 /* ---- test hook: elementwise Si(x), Ci(x) of the device routine used by hmv_uk_nfw (x > 0) -----------*/
 int hmv_sici_test(int n, const double* x_d, double* si_d, double* ci_d, void* stream);
 

@@ -561,6 +561,42 @@ def limber(ells, zs, ks, Pzk, gzs, W1, W2, hzs, chis, use_fitpack=True):
 
 
 # ----------------------------------------------------------------------------------------------
+# P(z,k) interpolator in front of the path: utils.py:53-182, cosmology.py:227-229,353-382
+# ----------------------------------------------------------------------------------------------
+class PKOracle(object):
+    """RectBivariateSpline in (z, ln k) of log|P| (or of P when it changes sign), bicubic when the table allows,
+    with the optional two-node power-law extension to extrap_kmax; P(z,k) = sign*exp(spline) (utils.py:95-103)."""
+
+    def __init__(self, ks, zs, pk, log_interp=True, extrap_kmax=None):
+        from scipy.interpolate import RectBivariateSpline
+        ks, zs, pk = (np.asarray(a, dtype=np.float64) for a in (ks, zs, pk))
+        self.sign = 1
+        if log_interp and np.any(pk <= 0):                                               # utils.py:139-144
+            if np.all(pk < 0):
+                self.sign = -1
+            else:
+                log_interp = False
+        vals = np.log(self.sign * pk) if log_interp else pk
+        logk = np.log(ks)
+        if extrap_kmax and extrap_kmax > ks[-1]:                                         # utils.py:150-169
+            top = np.log(extrap_kmax)
+            delta = top - logk[-1]
+            ext = np.empty((vals.shape[0], vals.shape[1] + 2))
+            ext[:, :-2] = vals
+            dlog = (ext[:, -3] - ext[:, -4]) / (logk[-1] - logk[-2])
+            ext[:, -1] = ext[:, -3] + dlog * delta
+            ext[:, -2] = ext[:, -3] + dlog * delta * 0.9
+            logk = np.hstack((logk, top - delta * 0.1, top))
+            vals = ext
+        self.islog = bool(log_interp)
+        self.spl = RectBivariateSpline(zs, logk, vals, kx=min(len(zs) - 1, 3), ky=min(len(logk) - 1, 3))   # :171-172
+
+    def P(self, z, k, grid=True):
+        v = self.spl(z, np.log(k), grid=grid)
+        return self.sign * np.exp(v) if self.islog else v
+
+
+# ----------------------------------------------------------------------------------------------
 # A small driver object so parity tests and the CPU baseline read like reference usage
 # ----------------------------------------------------------------------------------------------
 class OracleHaloModel(object):

@@ -48,6 +48,14 @@ def golden_kat():
     return load_golden("kat")
 
 
+PKSPLINE_CASES = [  # (golden key, table key, query-z key, query-k key, redshift-table key, builder kwargs)
+    ("P_log", "pk_tab", "zq", "kq", "zs_tab", {}),
+    ("P_extrap", "pk_tab", "zq", "kq_x", "zs_tab", {"extrap_kmax": 200.0}),
+    ("P_signchange", "pk_tab_sc", "zq", "kq", "zs_tab", {}),
+    ("P_negative", "-pk_tab", "zq", "kq", "zs_tab", {}),
+]
+
+
 def assert_close(got, want, rtol=1e-6, atol_frac=0.0, name=""):
     """rtol parity with an optional absolute floor expressed as a fraction of max|want|.
 
@@ -58,3 +66,8 @@ def assert_close(got, want, rtol=1e-6, atol_frac=0.0, name=""):
     finite = np.isfinite(want)
     scale = np.max(np.abs(want[finite])) if finite.any() else 0.0
     np.testing.assert_allclose(got, want, rtol=rtol, atol=atol_frac * scale, equal_nan=True, err_msg=name)
+
+
+@pytest.fixture(scope="session")
+def golden_pkspline():
+    return load_golden("pkspline")

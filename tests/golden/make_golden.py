@@ -230,7 +230,37 @@ def case_kat(hm):
     return out
 
 
-CASES = dict(readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
+def case_pkspline(hm):
+    """P(z,k) through the reference's own interpolator builder (utils.py:53-182) on a synthetic CLASS-like table:
+    the reference's EH98 P_lin_approx on a coarse (z,k) grid.  Variants: bicubic log-interpolation, the power-law
+    extension beyond kmax, a sign-changing table (linear interpolation of P itself) and a 3-redshift table (kx=2)."""
+    from hmvec import utils as rutils
+    zs_t = np.linspace(0., 4., 25)
+    ks_t = np.geomspace(5e-5, 30., 140)
+    h = hm.HaloModel(np.array([0.5]), np.geomspace(1e-3, 1., 8), ms=np.geomspace(1e11, 1e15, 8), accuracy='low')
+    pk = h.P_lin_approx(ks_t, zs_t)
+    zq = np.linspace(0., 4., 57)
+    kq = np.geomspace(5e-5, 30., 411)
+    out = dict(zs_tab=zs_t, ks_tab=ks_t, pk_tab=pk, zq=zq, kq=kq)
+    PK = rutils.get_matter_power_interpolator_generic(ks_t, zs_t, pk, silent=True)
+    out["P_log"] = PK.P(zq, kq, grid=True)
+    out["P_log_scalar_z"] = PK.P(1.2345, kq)
+    kq_x = np.geomspace(1e-4, 200., 300)
+    PKx = rutils.get_matter_power_interpolator_generic(ks_t, zs_t, pk, extrap_kmax=200., silent=True)
+    out["kq_x"], out["P_extrap"] = kq_x, PKx.P(zq, kq_x, grid=True)
+    pk_sc = pk * np.cos(3.0 * np.log(ks_t))[None, :]                 # crosses zero: log_interp is dropped
+    PKs = rutils.get_matter_power_interpolator_generic(ks_t, zs_t, pk_sc, silent=True)
+    out["pk_tab_sc"], out["P_signchange"] = pk_sc, PKs.P(zq, kq, grid=True)
+    PKn = rutils.get_matter_power_interpolator_generic(ks_t, zs_t, -pk, silent=True)
+    out["P_negative"] = PKn.P(zq, kq, grid=True)
+    z3 = np.array([0., 1., 2.5])
+    PK3 = rutils.get_matter_power_interpolator_generic(ks_t, z3, h.P_lin_approx(ks_t, z3), silent=True)
+    zq3 = np.linspace(0., 2.5, 11)
+    out["zs_tab3"], out["zq3"], out["P_kx2"] = z3, zq3, PK3.P(zq3, kq, grid=True)
+    return out
+
+
+CASES = dict(pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
 
 if __name__ == "__main__":
     hm = _import_reference()

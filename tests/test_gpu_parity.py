@@ -286,3 +286,33 @@ def test_transform_ragged_grid_and_long_profile(hm, mode):
         assert_close(h.pk_profiles["y"], o.pk_profiles["y"], 1e-6, OSC, "pk_y (mode %d)" % mode)
     finally:
         capi.lib.hmv_set_transform_mode(0)
+
+
+def test_pk_spline_device(hm, golden_pkspline):
+    """hmv_pk_spline (P(z,k) from a matter-power interpolator) against the reference's own
+    get_matter_power_interpolator_generic(...).P(z, k, grid=True): bicubic log-interpolation, power-law extension,
+    sign-changing and negative tables, a 3-redshift (kx=2) table, scalar arguments, and a scipy spline handed over
+    as CAMB's interpolator would be."""
+    from conftest import PKSPLINE_CASES
+    g = golden_pkspline
+    gen = hm.utils.get_matter_power_interpolator_generic
+    for key, tab, zq, kq, zt, kw in PKSPLINE_CASES:
+        pk = -g[tab[1:]] if tab.startswith("-") else g[tab]
+        PK = gen(g["ks_tab"], g[zt], pk, silent=True, **kw)
+        assert_close(PK.P(g[zq], g[kq], grid=True), g[key], 1e-11, name=key)
+    PK = gen(g["ks_tab"], g["zs_tab"], g["pk_tab"])
+    assert (PK.kmin, PK.kmax, PK.zmin, PK.zmax) == (g["ks_tab"].min(), g["ks_tab"][-1], 0.0, 4.0) and PK.islog
+    assert_close(PK.P(1.2345, g["kq"]), g["P_log_scalar_z"], 1e-11, name="P(z scalar, k)")
+    assert np.isclose(PK.P(1.2345, 0.1), g["P_log_scalar_z"][np.argmin(np.abs(g["kq"] - 0.1))], rtol=0.2)
+    # unsorted query points are fine on the device (scipy's grid=True refuses them)
+    perm = np.random.default_rng(1).permutation(g["kq"].size)
+    assert_close(PK.P(g["zq"][::-1], g["kq"][perm]), g["P_log"][::-1][:, perm], 1e-11, name="shuffled grid")
+    # a scipy interpolator object (what camb.get_matter_power_interpolator returns) goes through from_spline
+    from scipy.interpolate import RectBivariateSpline
+    spl = RectBivariateSpline(g["zs_tab"], np.log(g["ks_tab"]), np.log(g["pk_tab"]))
+    spl.islog, spl.logsign = True, 1
+    c = hm.Cosmology(accuracy='low')
+    assert_close(c._pk_grid(spl, g["zq"], g["kq"]), g["P_log"], 1e-11, name="from_spline")
+    z3 = g["zs_tab3"]
+    PK3 = gen(g["ks_tab"], z3, c.P_lin_approx(g["ks_tab"], z3))
+    assert_close(PK3.P(g["zq3"], g["kq"]), g["P_kx2"], 1e-9, name="P_kx2")

@@ -176,3 +176,19 @@ def test_known_answers(golden_kat):
     y, _ = orc.bisect_all(g["bisect_x"], np.sqrt, 1.0, 40.0, 1e-4, decreasing=False)
     assert_close(y, g["bisect_y"], 1e-14)
     assert np.all(np.isclose(y, [4.0, 16.0, 36.0], rtol=1e-3))
+
+
+def test_pk_interpolator(golden_pkspline):
+    """The P(z,k) interpolator in front of the path (utils.py:53-182) against the reference's own builder."""
+    from conftest import PKSPLINE_CASES
+    g = golden_pkspline
+    for key, tab, zq, kq, zt, kw in PKSPLINE_CASES:
+        pk = -g[tab[1:]] if tab.startswith("-") else g[tab]
+        PK = orc.PKOracle(g["ks_tab"], g[zt], pk, **kw)
+        assert_close(PK.P(g[zq], g[kq]), g[key], 1e-12, name=key)
+    z3 = g["zs_tab3"]
+    bg = orc.Background()
+    PK3 = orc.PKOracle(g["ks_tab"], z3, orc.plin_approx(bg, g["ks_tab"], z3))
+    assert_close(PK3.P(g["zq3"], g["kq"]), g["P_kx2"], 1e-9, name="P_kx2")
+    assert_close(orc.PKOracle(g["ks_tab"], g["zs_tab"], g["pk_tab"]).P(1.2345, g["kq"])[0], g["P_log_scalar_z"], 1e-12,
+                 name="P_log_scalar_z")
