@@ -158,9 +158,10 @@ class GridSix(object):
         self.transform_mode = 0
         self._ev = None
         self._Pfull = None
-        self.d2h_chunks = 5
+        self.d2h_chunks = 10      # the download (192 MB) takes about as long as the reduction: start it early, end it small
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
+        self.ev_pzk = torch.cuda.Event()
 
     # ------------------------------------------------------------------ host <-> device
     def h2d_bytes(self):
@@ -171,8 +172,15 @@ class GridSix(object):
         return int(n + (self.h_cl.numel() * 8 if self.has_limber else 0))
 
     def upload(self):
+        """Pinned host -> HBM.  Pzk is first needed by the spectra at the end of the step, so it travels on the copy
+        stream behind the kernels (run() waits for it in front of hmv_power_six); everything else is needed at once."""
+        self.copy_stream.wait_stream(torch.cuda.current_stream())      # the previous step no longer reads Pzk
+        with torch.cuda.stream(self.copy_stream):
+            self.d["Pzk"].copy_(self.h_in["Pzk"], non_blocking=True)
+            self.ev_pzk.record()
         for k in _PER_STEP:
-            self.d[k].copy_(self.h_in[k], non_blocking=True)
+            if k != "Pzk":
+                self.d[k].copy_(self.h_in[k], non_blocking=True)
 
     def download(self):
         self.h_p1.copy_(self.p1, non_blocking=True)
@@ -247,6 +255,7 @@ class GridSix(object):
         n += 6
         self._mark(5)
         # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
+        torch.cuda.current_stream().wait_event(self.ev_pzk)            # Pzk of this step has arrived (see upload)
         nchunk = self.d2h_chunks if overlap_d2h else 1
         zb = np.linspace(0, nz, nchunk + 1).round().astype(int)
         S = nz * nk
