@@ -24,6 +24,21 @@ inline int check_launch(const char* what) {
     if (!(cond)) return hmv::fail(HMV_E_ARG, __VA_ARGS__); \
   } while (0)
 
+// device-side bounds checks of the debug build (make EXTRA=-DHMV_DEBUG; compute-sanitizer is not available on the pool):
+// a failed check prints its location and traps, which the next CUDA call reports as an error
+#ifdef HMV_DEBUG
+#define HMV_DEV_ASSERT(cond)                                                                         \
+  do {                                                                                               \
+    if (!(cond)) {                                                                                   \
+      printf("HMV_DEV_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+             (int)blockIdx.x, (int)threadIdx.x);                                                     \
+      __trap();                                                                                      \
+    }                                                                                                \
+  } while (0)
+#else
+#define HMV_DEV_ASSERT(cond) ((void)0)
+#endif
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ double warp_sum(double v) {

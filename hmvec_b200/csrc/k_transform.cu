@@ -384,6 +384,7 @@ __device__ __forceinline__ void accum_mma_ws(const double2* __restrict__ tab, co
         const int b = jw + 8 * t + 2 * kq + e;
         if (b <= jn) {
           double v = c[t][mt][e];
+          HMV_DEV_ASSERT(b >= 1 && b < JS - 1);
           if (!first) v += Uh[b];
           if (fuse) {
             v *= sc * __ldg(rkt + b);
@@ -543,6 +544,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       ws_item(item, p.nz, p.nmg, stride, z, q);
       const int jn = f_jn;
       const int m0 = (p.nmg - 1 - q) * WS_HB;
+      HMV_DEV_ASSERT(jn >= 2 && jn <= p.J && m0 >= 0 && m0 < p.nm && z >= 0 && z < p.nz);
       double* U = slots + (size_t)s * WS_HB * JS;
       if (tid < WS_HB) meta[s].inv[tid] = h_inv[tid];
       if (tid == 0) { meta[s].z = z; meta[s].m0 = m0; meta[s].jn = jn; meta[s].nvalid = min(WS_HB, p.nm - m0); }
@@ -589,6 +591,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             const int h = hh + hoff;
             const double v = (n < p.N && x <= h_cmax[h]) ? (x * h_amp[h]) * f[hh] : 0.0;   // x * rho(x) inside the cut
             msum[hh] = fma(wx, v, msum[hh]);
+            HMV_DEV_ASSERT(ws_gs_index(sn, h) >= 0 && ws_gs_index(sn, h) < (NCH_MMA / 4) * WS_GSB);
             gs[ws_gs_index(sn, h)] = v;
           }
         }
@@ -722,7 +725,10 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             }
             double ua[8], uo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ua[i] = Uh[jc[i]]; uo[i] = Uh[jo[i]]; }
+            for (int i = 0; i < 8; ++i) {
+              HMV_DEV_ASSERT(jc[i] >= 1u && jc[i] <= (unsigned)(jn + 1) && jo[i] <= (unsigned)(JS - 1));
+              ua[i] = Uh[jc[i]]; uo[i] = Uh[jo[i]];
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               __stcs(orow + base + lane + 32 * u, make_double2(fma(af[2 * u], uo[2 * u] - ua[2 * u], ua[2 * u]),
@@ -738,7 +744,10 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             }
             double ua[8], uo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { ua[i] = Uh[e[i].jc]; uo[i] = Uh[e[i].jo]; }
+            for (int i = 0; i < 8; ++i) {
+              HMV_DEV_ASSERT(e[i].jc >= 1 && e[i].jc <= jn + 1 && e[i].jo >= 0 && e[i].jo <= jn + 1);
+              ua[i] = Uh[e[i].jc]; uo[i] = Uh[e[i].jo];
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int k2 = base + lane + 32 * u;
