@@ -439,11 +439,13 @@ __device__ __forceinline__ double ws_lerp_finish(const WsLerp& r, double ua, dou
 
 // Interior of a sorted row (every t of the block inside [1, J], bins inside the computed range): no classification.
 __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned jmax, unsigned& jc, unsigned& jo, double& af) {
-  const double MAGIC = 6755399441055744.0;
-  const double tm = fma(k, inv, MAGIC);
-  const double frac = fma(k, inv, -(tm - MAGIC));
+  // four FP64-pipe instructions (t, t - rint t, and the two of the lerp); the rounding and its way back to FP64 are
+  // conversion instructions, which do not queue behind the producers' DMMAs
+  const double t = k * inv;
+  const int jr = __double2int_rn(t);
+  const double frac = t - (double)jr;
   const int fh = __double2hiint(frac);
-  jc = min((unsigned)__double2loint(tm), jmax);
+  jc = min((unsigned)jr, jmax);
   jo = jc + 1u + (unsigned)((fh >> 31) << 1);                // +1, or -1 when t is left of its nearest bin
   af = __hiloint2double(fh & 0x7fffffff, __double2loint(frac));
 }
