@@ -743,6 +743,11 @@ class OracleHaloModel(object):
         w = np.asarray(gdndz) / _trapz(gdndz, gzs)
         return limber(ells, zs, ks, Pgg, gzs, w, w, self.bg.h_of_z(gzs), self.bg.chi(gzs))
 
+    def C_ky(self, ells, zs, ks, Pym, lzs1=None, ldndz1=None):
+        """cosmology.py:585-589"""
+        w1 = lensing_window(self.bg, zs, lzs1, ldndz1)
+        return limber(ells, zs, ks, Pym, zs, w1, np.ones(np.size(zs)), self.bg.h_of_z(zs), self.bg.chi(zs))
+
     def C_yy(self, ells, zs, ks, Ppp):
         """cosmology.py:591-597"""
         one = np.ones(np.size(zs))

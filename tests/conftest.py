@@ -71,3 +71,8 @@ def assert_close(got, want, rtol=1e-6, atol_frac=0.0, name=""):
 @pytest.fixture(scope="session")
 def golden_pkspline():
     return load_golden("pkspline")
+
+
+@pytest.fixture(scope="session")
+def golden_cky():
+    return load_golden("cky")

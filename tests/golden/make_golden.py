@@ -230,6 +230,25 @@ def case_kat(hm):
     return out
 
 
+def case_cky(hm):
+    """The one Limber wrapper the mini fixture does not hold: C_ky = tSZ x CMB lensing (cosmology.py:585-589) from the
+    pressure x matter spectrum, delta-function and dn/dz lensing sources."""
+    zs, ms, ks = MINI_ZS, MINI_MS, MINI_KS
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    out = dict(zs=zs, ms=ms, ks=ks)
+    out["P1h_ym"], out["P2h_ym"] = h.get_power_1halo("y", "nfw"), h.get_power_2halo("y", "nfw")
+    ells = np.geomspace(10, 1e4, 40)
+    Pym = out["P1h_ym"] + out["P2h_ym"]
+    out["ells"] = ells
+    out["C_ky"] = h.C_ky(ells, zs, ks, Pym, lzs1=2.5)
+    lz = np.linspace(0.2, 2.8, 30)
+    ldn = lz ** 2 * np.exp(-(lz / 0.9) ** 1.5)
+    out["lz"], out["ldndz"] = lz, ldn
+    out["C_ky_dndz"] = h.C_ky(ells, zs, ks, Pym, lzs1=lz, ldndz1=ldn)
+    return out
+
+
 def case_pkspline(hm):
     """P(z,k) through the reference's own interpolator builder (utils.py:53-182) on a synthetic CLASS-like table:
     the reference's EH98 P_lin_approx on a coarse (z,k) grid.  Variants: bicubic log-interpolation, the power-law
@@ -260,7 +279,7 @@ def case_pkspline(hm):
     return out
 
 
-CASES = dict(pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
+CASES = dict(cky=case_cky, pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
 
 if __name__ == "__main__":
     hm = _import_reference()

@@ -316,3 +316,15 @@ def test_pk_spline_device(hm, golden_pkspline):
     z3 = g["zs_tab3"]
     PK3 = gen(g["ks_tab"], z3, c.P_lin_approx(g["ks_tab"], z3))
     assert_close(PK3.P(g["zq3"], g["kq"]), g["P_kx2"], 1e-9, name="P_kx2")
+
+
+def test_c_ky(hm, golden_cky):
+    """tSZ x CMB lensing through the drop-in API (cosmology.py:585-589)."""
+    g = golden_cky
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    assert_close(h.get_power_1halo("y", "nfw"), g["P1h_ym"], 1e-6, name="P1h_ym")
+    assert_close(h.get_power_2halo("y", "nfw"), g["P2h_ym"], 1e-6, name="P2h_ym")
+    Pym = h.get_power("y", "nfw")
+    assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=2.5), g["C_ky"], 1e-6)
+    assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=g["lz"], ldndz1=g["ldndz"]), g["C_ky_dndz"], 1e-6)

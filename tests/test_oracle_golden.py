@@ -192,3 +192,15 @@ def test_pk_interpolator(golden_pkspline):
     assert_close(PK3.P(g["zq3"], g["kq"]), g["P_kx2"], 1e-9, name="P_kx2")
     assert_close(orc.PKOracle(g["ks_tab"], g["zs_tab"], g["pk_tab"]).P(1.2345, g["kq"])[0], g["P_log_scalar_z"], 1e-12,
                  name="P_log_scalar_z")
+
+
+def test_c_ky(golden_cky):
+    """tSZ x lensing (cosmology.py:585-589): pressure x matter spectra and both lensing-source forms."""
+    g = golden_cky
+    o = orc.OracleHaloModel(g["zs"], g["ks"], g["ms"])
+    o.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    assert_close(o.get_power_1halo("y", "nfw"), g["P1h_ym"], 1e-6, name="P1h_ym")
+    assert_close(o.get_power_2halo("y", "nfw"), g["P2h_ym"], 1e-6, name="P2h_ym")
+    Pym = g["P1h_ym"] + g["P2h_ym"]
+    assert_close(o.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=2.5), g["C_ky"], 1e-9)
+    assert_close(o.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=g["lz"], ldndz1=g["ldndz"]), g["C_ky_dndz"], 1e-9)
