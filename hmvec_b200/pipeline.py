@@ -158,7 +158,10 @@ class GridSix(object):
         self.transform_mode = 0
         self._ev = None
         self._Pfull = None
-        self.d2h_chunks = 10      # the download (192 MB) takes about as long as the reduction: start it early, end it small
+        self._Ppack = None
+        # the download (192 MB on the full grid) takes about as long as the reduction: start it early, end it small --
+        # but keep >= 20 redshifts (400 CTAs, 2.7 waves) per reduction launch
+        self.d2h_chunks = int(min(10, max(1, self.nz // 20)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
         self.ev_pzk = torch.cuda.Event()
@@ -299,21 +302,35 @@ class GridSix(object):
     def _limber(self, st):
         """P = P1h + P2h for mm and gm, all-gathered over z when sharded, then C_kk and C_kg (cosmology.py:536-568)."""
         L, d, ptr = capi.lib, self.d, capi.ptr
-        if self.zcomm is not None:
-            # all-gather of the four [nz_local,nk] slabs (P1h, P2h of mm and gm) straight into [4, nz_total, nk]
+        nk = self.nk
+        if self.zcomm is not None and getattr(self.zcomm, "nz_total", -1) == getattr(self.zcomm, "world", 0) * self.nz:
+            # ONE all-gather: the four [nz_local,nk] slabs Limber needs (P1h, P2h of mm and gm) are packed z-major as
+            # [nz_local][4][nk]; rank order is z order, so the gathered buffer is [nz_total][4][nk] and each spectrum is
+            # a table with row stride 4 nk (hmv_limber's ldp)
             if self._Pfull is None:
-                self._Pfull = torch.empty((4, self.zs_all.numel(), self.nk), dtype=torch.float64, device=self.device)
-            for i, src in enumerate((self.p1[0], self.p2[0], self.p1[4], self.p2[4])):
-                self.zcomm.all_gather_rows(src, self._Pfull[i])
-            mm1, mm2, gm1, gm2 = self._Pfull[0], self._Pfull[1], self._Pfull[2], self._Pfull[3]
+                self._Ppack = torch.empty((self.nz, 4, nk), dtype=torch.float64, device=self.device)
+                self._Pfull = torch.empty((self.zs_all.numel(), 4, nk), dtype=torch.float64, device=self.device)
+            torch.stack((self.p1[0], self.p2[0], self.p1[4], self.p2[4]), dim=1, out=self._Ppack)
+            self.zcomm.all_gather_rows(self._Ppack.view(self.nz, 4 * nk), self._Pfull.view(-1, 4 * nk))
+            base, ldp = self._Pfull.data_ptr(), 4 * nk
+            mm1, mm2, gm1, gm2 = (C.c_void_p(base + 8 * q * nk) for q in range(4))
+            nzt = self._Pfull.shape[0]
         else:
-            mm1, mm2, gm1, gm2 = self.p1[0], self.p2[0], self.p1[4], self.p2[4]
-        nzt = mm1.shape[0]
-        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, self.nk, self.nk, ptr(self.zs_all), ptr(d["ks"]),
-                                ptr(mm1), ptr(mm2), nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
+            if self.zcomm is not None:          # unequal slabs: one all-gather per spectrum into [4, nz_total, nk]
+                if self._Pfull is None:
+                    self._Pfull = torch.empty((4, self.zs_all.numel(), nk), dtype=torch.float64, device=self.device)
+                for i, src in enumerate((self.p1[0], self.p2[0], self.p1[4], self.p2[4])):
+                    self.zcomm.all_gather_rows(src, self._Pfull[i])
+                t = [self._Pfull[i] for i in range(4)]
+            else:
+                t = [self.p1[0], self.p2[0], self.p1[4], self.p2[4]]
+            mm1, mm2, gm1, gm2 = (ptr(x) for x in t)
+            nzt, ldp = t[0].shape[0], nk
+        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
+                                mm1, mm2, nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
                                 ptr(self.cl[0]), st), "hmv_limber(kk)")
-        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, self.nk, self.nk, ptr(self.zs_all), ptr(d["ks"]),
-                                ptr(gm1), ptr(gm2), 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
+        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
+                                gm1, gm2, 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
                                 st), "hmv_limber(kg)")
         return 2
 

@@ -38,11 +38,14 @@ class ZComm(object):
         self.bounds = slab_bounds(self.nz_total, self.world)
         self.slab = slice(int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
         self.nz_local = self.slab.stop - self.slab.start
+        self._shifts = {}
 
     def all_reduce_and(self, mask):
         """In-place bitwise AND of a 1-element int64 tensor over the ranks (the global bisection stop condition).
         NCCL has no bitwise reductions, so the 64 bits travel as 64 int32 flags reduced with MIN."""
-        sh = torch.arange(64, dtype=torch.int64, device=mask.device)
+        sh = self._shifts.get(mask.device)
+        if sh is None:
+            sh = self._shifts.setdefault(mask.device, torch.arange(64, dtype=torch.int64, device=mask.device))
         bits = ((mask.reshape(1) >> sh) & 1).to(torch.int32)
         dist.all_reduce(bits, op=dist.ReduceOp.MIN, group=self.group)
         mask.copy_((bits.to(torch.int64) << sh).sum().reshape(mask.shape))
