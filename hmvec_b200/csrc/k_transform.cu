@@ -772,7 +772,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
 }
 
 static bool ws_ring_fits(int nxs) {
-  return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)1 << 30);
+  return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)4 << 30);   // only the bins a group needs are ever touched; covers every N the phase index allows (N < 65536)
 }
 
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels

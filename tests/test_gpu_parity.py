@@ -284,6 +284,11 @@ def test_transform_ragged_grid_and_long_profile(hm, mode):
         h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
         o.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
         assert_close(h.pk_profiles["y"], o.pk_profiles["y"], 1e-6, OSC, "pk_y (mode %d)" % mode)
+        # numeric NFW at the package defaults (nxs=40000, xmax=200; params.py:59-60): a 20000-bin table per halo,
+        # ~2000 samples inside the cut
+        h.add_nfw_profile("nfwnum", numeric=True)
+        o.add_nfw_profile("nfwnum", numeric=True)
+        assert_close(h.uk_profiles["nfwnum"], o.uk_profiles["nfwnum"], 1e-6, OSC, "uk_nfwnum default (mode %d)" % mode)
     finally:
         capi.lib.hmv_set_transform_mode(0)
 
