@@ -2,26 +2,32 @@
 // interpolation onto the target wavenumbers.  Replaces generic_profile_fft + fft_integral + _interp_loop
 // (reference fft.py:35-115) and rho_gas_generic_x / P_e_generic_x (hmvec.py:856-860, 918-927).
 //
-// One CTA owns HB consecutive-mass halos of one redshift.  The (z,M,x) profile cube never exists: samples are
-// evaluated chunk by chunk into shared memory, the sine sums
+// The (z,M,x) profile cube never exists: samples are evaluated chunk by chunk into shared memory, the sine sums
 //        U_j = step * sum_n x_n y_n sin(2 pi j n / N)          ( == -Im rfft(x*y) * step, fft.py:49 )
 // are accumulated only for the bins j the target k-range needs (bin skipping; the theta-cut bounds n), then
-// u_j = U_j/kt_j/mnorm is linearly interpolated onto ks from shared memory (direct index j=floor(k/kout_1), no
-// search) and written once, coalesced.
+// u_j = U_j/kt_j/mnorm is linearly interpolated onto ks (direct index j = floor(k/kout_1), no search) and written
+// once, coalesced.
 //
 // The sine matrix S[n][j] = sin(2 pi n j/N) is halo independent, so the sums are a dense contraction
-// [8 halos x samples] x [samples x bins] and run on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
+// [halos x samples] x [samples x bins] and run on the FP64 tensor cores (mma.sync m8n8k4 -> SASS DMMA.8x8x4).
 // A lane's B-operand element is sin(phi_j (s + 4 i)) for its fixed (bin j, sample offset): an arithmetic sequence of
-// angles, advanced with the three-term recurrence  b_{i+1} = 2 cos(4 phi_j) b_i - b_{i-1}  (one DFMA per DMMA) and
-// re-seeded exactly from a {sin,cos} table (global memory, L1-resident) at every 256-sample chunk, which bounds the
-// recurrence round-off at 64^2 ulp/2 ~ 5e-13.  Why tensor cores: DMMA has the DFMA pipe's peak on B200 (36.9 vs 35.0
-// TFLOP/s, tools/micro/dmma_bench.cu) but takes ONE issue slot per 256 FMAs; the per-thread DFMA form was issue-bound
-// on phase-index arithmetic and a DMMA form fed from a shared-memory sine table was shared-memory bandwidth bound
+// angles, advanced with the three-term recurrence  b_{i+1} = 2 cos(4 phi_j) b_i - b_{i-1}  and re-seeded exactly from
+// a {sin,cos} table (global memory) at every sample chunk, which bounds the recurrence round-off at (chunk/4)^2 ulp/2
+// (3e-12 for 704 samples).  Why tensor cores: DMMA has the DFMA pipe's peak on B200 (36.9 vs 35.0 TFLOP/s,
+// tools/micro/dmma_bench.cu) but takes ONE issue slot per 256 FMAs; the per-thread DFMA form was issue-bound on
+// phase-index arithmetic and a DMMA form fed from a shared-memory sine table was shared-memory bandwidth bound
 // (0.74 wavefronts/cycle/SM: the 32 table addresses of a B fragment are effectively random, ~6 wavefronts per
-// fragment) -- ncu evidence in profiles/.  nxs too large for 8 halos' bin tables in shared memory (> ~6400) or odd
-// falls back to a DFMA rotation recurrence.  Because the number of bins a halo needs grows like M^(1/3)
-// (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints (33 / 49 / 82 / 176 KB)
-// let the many small halos run several CTAs per SM instead of all being sized for the largest one.
+// fragment) -- ncu evidence in profiles/.
+//
+// Two launch plans (hmv_set_transform_mode):
+//   0 (default)  profile_transform_ws_kernel: ONE persistent, warp-specialised kernel (second half of this file) --
+//                producer warps evaluate + transform 16 halos at a time, consumer warps interpolate + store, the two
+//                overlapped through a ring of bin tables in L2;
+//   1            profile_transform_kernel: one CTA owns 8 halos and runs evaluation, sums and interpolation one after
+//                the other with the bin table in shared memory; because the number of bins a halo needs grows like
+//                M^(1/3) (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints
+//                (33 / 49 / 82 / 176 KB) let the many small halos run several CTAs per SM.  N too large for 8 halos'
+//                bin tables in shared memory (> ~6400) falls back to a DFMA rotation recurrence.
 #include "common.cuh"
 #include "gnfw_eval.cuh"
 
@@ -298,9 +304,10 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 //     memory, run the DMMA sine sums and write the finished, normalised bin table u_j of the group into one slot of a
 //     per-CTA ring in global memory (WS_NSLOT x 16 x (N/2+2) doubles; only the bins a group needs are touched, so the
 //     ring lives in the 126 MB L2 and the consumer's re-reads hit L1);
-//   * 8 consumer warps wait for a slot, interpolate its 16 rows onto the target ks (one row per warp at a time, four
-//     16-byte streaming stores per lane and trip, a warp-vote fast path where a whole 256-k span is below the first
-//     bin) and release the slot.
+//   * 8 consumer warps wait for a slot and interpolate its 16 rows onto the target ks, one row per warp at a time: two
+//     binary searches split a sorted k axis into hold-u_1 / interpolate / zero spans (an unsorted axis is one
+//     general span), fills are plain 16-byte streaming stores, interpolated blocks load the table values of a lane's
+//     eight wavenumbers before the first use and prefetch the next block's table lines to L1; then release the slot.
 // full/empty mbarriers hand the slots over (producer: named barrier among its 256 threads, then one release-arrive;
 // consumer: acquire-wait), so the FP64-pipe-bound work of one group overlaps the HBM-bound stores of the previous ones.
 // Sixteen halos per item = two 8-row M tiles per B fragment: every sine value the recurrence produces feeds two DMMAs
@@ -310,7 +317,8 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // (DMMA-bound) groups alternate in every SM's queue instead of arriving as one heavy and one light phase; the last
 // redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
 // registers while the current one is being transformed.
-// Shared memory is only the 90 KB sample chunk, so there are no bin-count classes and no limit on N from the bin table.
+// Shared memory is the 90 KB sample chunk plus a copy of ks (when it fits), so there are no bin-count classes and no
+// limit on N from the bin table.
 constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256, WS_CT = 256;   // 8 producer + 8 consumer warps
 
 struct WsSlotMeta {
