@@ -333,3 +333,26 @@ def test_c_ky(hm, golden_cky):
     Pym = h.get_power("y", "nfw")
     assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=2.5), g["C_ky"], 1e-6)
     assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=g["lz"], ldndz1=g["ldndz"]), g["C_ky_dndz"], 1e-6)
+
+
+@pytest.mark.parametrize("nz,nm,nk", [(1, 2, 1), (1, 16, 2), (2, 17, 31), (3, 33, 100), (5, 5, 257), (1, 48, 3)])
+def test_small_and_degenerate_grids(hm, nz, nm, nk):
+    """Edge shapes through the whole drop-in path against the CPU oracle: a single redshift, two masses (the minimum
+    numpy.gradient accepts), one or two wavenumbers (no 16-byte pair / a single pair), mass counts around the 16-halo
+    item size, and k grids shorter than one interpolation block."""
+    from oracle.hmvec_oracle import OracleHaloModel
+    zs = np.linspace(0.2, 2.2, nz) if nz > 1 else np.array([0.7])
+    ms = np.geomspace(5e11, 3e15, nm)
+    ks = np.geomspace(3e-3, 40.0, nk) if nk > 1 else np.array([0.5])
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+    o = OracleHaloModel(zs, ks, ms)
+    assert_close(h.nzm, o.nzm, 1e-6, name="nzm")
+    assert_close(h.uk_profiles["nfw"], o.uk_profiles["nfw"], 1e-6, OSC, "uk_nfw")
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    o.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    assert_close(h.uk_profiles["electron"], o.uk_profiles["electron"], 1e-6, OSC, "uk_e")
+    h.add_hod("g", mthresh=10 ** 11.0 + zs * 0.0)
+    o.add_hod("g", mthresh=10 ** 11.0 + zs * 0.0)
+    for a, b in (("nfw", "nfw"), ("g", "electron"), ("electron", "electron")):
+        assert_close(h.get_power_1halo(a, b), o.get_power_1halo(a, b), 1e-6, name="P1h %s %s" % (a, b))
+        assert_close(h.get_power_2halo(a, b), o.get_power_2halo(a, b), 1e-6, name="P2h %s %s" % (a, b))
