@@ -47,18 +47,28 @@ __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks
   // loader indices
   const int az = tid >> 3, ak = (tid & 7) * 2;     // A: 32 z x 16 k, 2 k per thread
   const int bk = tid >> 4, bm = (tid & 15) * 4;    // B: 16 k x 64 m, 4 m per thread
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+  // software pipeline: the next k-step's operands are fetched into registers while the current one is multiplied
+  double ra[2], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int z = z0 + az, k = k0 + ak + i;
-      As[ak + i][az] = (z < nz && k < kend) ? sPzk[(long long)z * nks + k] * kw[k] : 0.0;
+      ra[i] = (z < nz && k < kend) ? sPzk[(long long)z * nks + k] * kw[k] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + bk, m = m0 + bm + i;
-      Bs[bk][bm + i] = (k < kend && m < nm) ? W2T[(long long)k * nm + m] : 0.0;
+      rb[i] = (k < kend && m < nm) ? W2T[(long long)k * nm + m] : 0.0;
     }
+  };
+  fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) As[ak + i][az] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[bk][bm + i] = rb[i];
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       const double a = As[kk + kq][wz + nq];
