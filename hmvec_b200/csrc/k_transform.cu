@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // registers while the current one is being transformed.
 // Shared memory is the 90 KB sample chunk plus a copy of ks (when it fits), so there are no bin-count classes and no
 // limit on N from the bin table.
-constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = 256, WS_CT = 256;   // 8 producer + 8 consumer warps
+#ifndef HMV_WS_PT
+#define HMV_WS_PT 256      // producer threads: 256 (default) or 384 (with the register re-split below; measured +0.6 %)
+#endif
+constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = HMV_WS_PT, WS_CT = 256;   // 8 producer + 8 consumer warps
 
 struct WsSlotMeta {
   int z, m0, jn, nvalid;
@@ -333,7 +336,7 @@ __device__ __forceinline__ double warp_sum_parity(double v) {
   return v;
 }
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(HMV_WS_PT) : "memory"); }
 
 // sample n of halo h inside a chunk: [n/4][h%8][n%4][h/8] -- the A fragments (sample kq of halo nq, both M tiles) of a
 // 4-sample MMA step are 32 consecutive 16-byte words, one conflict-free LDS.128 per lane
@@ -507,6 +510,11 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   double* slots = ring + (size_t)blockIdx.x * WS_NSLOT * WS_HB * JS;
 
   if (tid < WS_PT) {
+#if HMV_WS_PT == 384
+    // 640 threads are launched with 96 registers each (61440); the producers take 112 and the consumers give back down
+    // to 72 (384*112 + 256*72 = 61440: the increase can only complete because the sum fits the CTA's allocation)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+#endif
     // =============================== producers: samples -> sine sums -> bin table ================================
     const double2* T = reinterpret_cast<const double2*>(p.sintab);
     const int warp = tid >> 5, lane = tid & 31, hoff = (tid & 1) << 3;
@@ -678,6 +686,9 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       item = nxt;
     }
   } else {
+#if HMV_WS_PT == 384
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+#endif
     // =============================== consumers: interpolate onto ks, store the rows ==============================
     const int ct = tid - WS_PT, lane = ct & 31, cw = ct >> 5;
     const int npair = p.nk >> 1;
