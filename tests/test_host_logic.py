@@ -93,3 +93,25 @@ def test_profile_dict_membership_does_not_download():
     assert "nfw" in dc and "electron" not in dc
     assert "nfw" in dc.keys() and "electron" not in dc.keys()
     assert list(dc) == ["nfw"] and len(dc) == 1
+
+
+def test_pk_table_preparation_matches_oracle():
+    """Host half of the P(z,k) interpolator (utils.py:139-170): log|P| / sign / extension nodes handed to the spline
+    fit are the oracle's, for a positive, a negative and a sign-changing table, with and without extrap_kmax."""
+    import numpy as np
+    from hmvec_b200.utils import _table_for_spline
+    from oracle import hmvec_oracle as orc
+    zs = np.linspace(0.0, 3.0, 9)
+    ks = np.geomspace(1e-4, 20.0, 60)
+    pk = orc.plin_approx(orc.Background(), ks, zs)
+    for tab, kw in ((pk, {}), (pk, {"extrap_kmax": 150.0}), (-pk, {}), (pk * np.cos(2.0 * np.log(ks))[None, :], {})):
+        z_t, logk, vals, islog, sign = _table_for_spline(ks, zs, tab, True, kw.get("extrap_kmax"))
+        o = orc.PKOracle(ks, zs, tab, **kw)
+        tx, ty, _ = o.spl.tck
+        assert islog == o.islog and sign == o.sign
+        assert logk.size == ty.size - 4 and np.isclose(logk[-1], ty[-1]) and np.isclose(logk[0], ty[0])
+        # the oracle's spline interpolates exactly the table the product prepares
+        np.testing.assert_allclose(o.spl(z_t, logk), vals, rtol=1e-10, atol=1e-12)
+    import pytest
+    with pytest.raises(ValueError):
+        _table_for_spline(ks, zs, pk * np.cos(2.0 * np.log(ks))[None, :], True, 150.0)
