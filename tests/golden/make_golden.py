@@ -14,6 +14,10 @@ hmvec.py / fft.py / utils.py / params.py / cosmology.py execute the whole hot pa
 `scipy.interpolate.interp2d` and `dfitpack.bispeu` are shimmed for the duration of this script
 with RectBivariateSpline(kx=ky=1) -- SciPy's documented bug-for-bug replacement; the reference's
 own limber_integral body (cosmology.py:867-904) is what executes.
+
+Cases: readme, mini, mini_mean, largeslab (the path on four grids), kat (the reference's two known-answer ideas),
+cky (C_ky: tSZ x lensing), pkspline (utils.get_matter_power_interpolator_generic on an EH98 table: the P(z,k)
+ingestion in front of the path).
 """
 import os
 import sys
