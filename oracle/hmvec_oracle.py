@@ -737,11 +737,16 @@ class OracleHaloModel(object):
         w2 = np.asarray(gdndz) / _trapz(gdndz, gzs) if gzs.size > 1 else np.ones(1)
         return limber(ells, zs, ks, Pgm, gzs, w1, w2, self.bg.h_of_z(gzs), self.bg.chi(gzs))
 
-    def C_gg(self, ells, zs, ks, Pgg, gzs, gdndz):
-        """cosmology.py:549-561 (dn/dz branch)"""
-        gzs = np.asarray(gzs, dtype=np.float64)
-        w = np.asarray(gdndz) / _trapz(gdndz, gzs)
-        return limber(ells, zs, ks, Pgg, gzs, w, w, self.bg.h_of_z(gzs), self.bg.chi(gzs))
+    def C_gg(self, ells, zs, ks, Pgg, gzs, gdndz=None, zmin=None, zmax=None):
+        """cosmology.py:549-561: dn/dz branch, or one effective redshift with a top-hat [zmin, zmax]"""
+        gzs = np.asarray(gzs, dtype=np.float64).reshape(-1)
+        hz, chis = self.bg.h_of_z(gzs), self.bg.chi(gzs)
+        if gzs.size > 1:
+            w1 = w2 = np.asarray(gdndz) / _trapz(gdndz, gzs)
+        else:
+            dchi = self.bg.chi(np.atleast_1d(zmax))[0] - self.bg.chi(np.atleast_1d(zmin))[0]
+            w1, w2 = np.ones(1), 1.0 / dchi / hz
+        return limber(ells, zs, ks, Pgg, gzs, w1, w2, hz, chis)
 
     def C_ky(self, ells, zs, ks, Pym, lzs1=None, ldndz1=None):
         """cosmology.py:585-589"""

@@ -250,6 +250,10 @@ def case_cky(hm):
     ldn = lz ** 2 * np.exp(-(lz / 0.9) ** 1.5)
     out["lz"], out["ldndz"] = lz, ldn
     out["C_ky_dndz"] = h.C_ky(ells, zs, ks, Pym, lzs1=lz, ldndz1=ldn)
+    # C_gg with a single effective redshift and a top-hat [zmin, zmax] (cosmology.py:556-560)
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    out["Pgg"] = h.get_power("g", "g")
+    out["C_gg_tophat"] = h.C_gg(ells, zs, ks, out["Pgg"], gzs=np.array([0.8]), zmin=0.7, zmax=0.9)
     return out
 
 

@@ -333,6 +333,9 @@ def test_c_ky(hm, golden_cky):
     Pym = h.get_power("y", "nfw")
     assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=2.5), g["C_ky"], 1e-6)
     assert_close(h.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=g["lz"], ldndz1=g["ldndz"]), g["C_ky_dndz"], 1e-6)
+    h.add_hod("g", mthresh=10 ** 10.5 + g["zs"] * 0.0)
+    assert_close(h.get_power("g", "g"), g["Pgg"], 1e-6, name="Pgg")
+    assert_close(h.C_gg(g["ells"], g["zs"], g["ks"], g["Pgg"], 0.8, zmin=0.7, zmax=0.9), g["C_gg_tophat"], 1e-6)
 
 
 @pytest.mark.parametrize("nz,nm,nk", [(1, 2, 1), (1, 16, 2), (2, 17, 31), (3, 33, 100), (5, 5, 257), (1, 48, 3)])

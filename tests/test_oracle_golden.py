@@ -204,3 +204,4 @@ def test_c_ky(golden_cky):
     Pym = g["P1h_ym"] + g["P2h_ym"]
     assert_close(o.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=2.5), g["C_ky"], 1e-9)
     assert_close(o.C_ky(g["ells"], g["zs"], g["ks"], Pym, lzs1=g["lz"], ldndz1=g["ldndz"]), g["C_ky_dndz"], 1e-9)
+    assert_close(o.C_gg(g["ells"], g["zs"], g["ks"], g["Pgg"], 0.8, zmin=0.7, zmax=0.9), g["C_gg_tophat"], 1e-9)
