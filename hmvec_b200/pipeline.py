@@ -165,6 +165,9 @@ class GridSix(object):
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
         self.ev_pzk = torch.cuda.Event()
+        self.hod_stream = torch.cuda.Stream(device=self.device)
+        self.ev_mf, self.ev_hod = torch.cuda.Event(), torch.cuda.Event()
+        self.hod_overlap = True
 
     # ------------------------------------------------------------------ host <-> device
     def h2d_bytes(self):
@@ -224,6 +227,8 @@ class GridSix(object):
                                        self.duffy[2], self.h, ptr(d["cs"]), ptr(d["rvir"]), st), "hmv_halo_geometry")
         n += 2
         self._mark(2)
+        if self.hod_overlap:
+            self._hod_stage(torch.cuda.current_stream())      # side stream, concurrent with the cube kernels
         if not self.fused_nfw:
             capi.check(L.hmv_uk_nfw(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["cs"]),
                                     ptr(d["rvir"]), ptr(d["nfw_ws"]), ptr(self.um), st), "hmv_uk_nfw")
@@ -242,23 +247,14 @@ class GridSix(object):
         # mdelta, gnfw_params, sine_table, bin_count + one persistent kernel (or the four bin-count classes)
         n += 5 if self.transform_mode == 0 else 8
         self._mark(4)
-        for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
-            capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]),
-                                        self.hodp, float(p['hod_bisection_search_min_log10mthresh']),
-                                        float(p['hod_bisection_search_max_log10mthresh']),
-                                        float(p['hod_bisection_search_rtol']), it0, it1, ptr(d["bis_ws"]),
-                                        C.c_void_p(self.mask.data_ptr()), st), "hmv_hod_bisect")
-            if self.zcomm is not None:
-                self.zcomm.all_reduce_and(self.mask)
-        capi.check(L.hmv_hod_pick(nz, ptr(d["bis_ws"]), C.c_void_p(self.mask.data_ptr()),
-                                  float(p['hod_A_log10mthresh']), ptr(d["l10"]), ptr(self.iters), st), "hmv_hod_pick")
-        capi.check(L.hmv_hod(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["l10"]), self.hodp, 0, ptr(d["nzm"]), ptr(d["bh"]),
-                             ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NsNsm1"]), ptr(d["NcNs"]), ptr(d["ngal"]), ptr(d["bg"]),
-                             st), "hmv_hod")
+        if not self.hod_overlap:
+            self._hod_stage(torch.cuda.current_stream())
         n += 6
         self._mark(5)
         # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
         torch.cuda.current_stream().wait_event(self.ev_pzk)            # Pzk of this step has arrived (see upload)
+        if self.hod_overlap:
+            torch.cuda.current_stream().wait_event(self.ev_hod)        # occupations, ngal, bg are in place
         nchunk = self.d2h_chunks if overlap_d2h else 1
         zb = np.linspace(0, nz, nchunk + 1).round().astype(int)
         S = nz * nk
@@ -298,6 +294,31 @@ class GridSix(object):
         self._mark(7)
         self.launches_per_run = n
         self._ev = None
+
+    def _hod_stage(self, main):
+        # The HOD solve needs only n(M,z) and b(M,z), is latency-bound (one CTA per redshift, 24 + 40 bisection
+        # iterations, two flag all-reduces when z is sharded) and writes only [nz,nm] arrays: it runs on a side stream
+        # next to the two cube kernels and rejoins in front of the mass integrals.
+        self.ev_mf.record(main)
+        hs = self.hod_stream if self.hod_overlap else main
+        L, d, ptr, p, nz, nm = capi.lib, self.d, capi.ptr, self.p, self.nz, self.nm
+        with torch.cuda.stream(hs):
+            hs.wait_event(self.ev_mf)
+            sth = capi.stream()
+            for it0, it1 in ((0, capi.HMV_BISECT_ROUND1), (capi.HMV_BISECT_ROUND1, capi.HMV_BISECT_MAXIT)):
+                capi.check(L.hmv_hod_bisect(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["nzm"]), ptr(d["ngal_target"]),
+                                            self.hodp, float(p['hod_bisection_search_min_log10mthresh']),
+                                            float(p['hod_bisection_search_max_log10mthresh']),
+                                            float(p['hod_bisection_search_rtol']), it0, it1, ptr(d["bis_ws"]),
+                                            C.c_void_p(self.mask.data_ptr()), sth), "hmv_hod_bisect")
+                if self.zcomm is not None:
+                    self.zcomm.all_reduce_and(self.mask)
+            capi.check(L.hmv_hod_pick(nz, ptr(d["bis_ws"]), C.c_void_p(self.mask.data_ptr()),
+                                      float(p['hod_A_log10mthresh']), ptr(d["l10"]), ptr(self.iters), sth), "hmv_hod_pick")
+            capi.check(L.hmv_hod(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["l10"]), self.hodp, 0, ptr(d["nzm"]), ptr(d["bh"]),
+                                 ptr(d["Nc"]), ptr(d["Ns"]), ptr(d["NsNsm1"]), ptr(d["NcNs"]), ptr(d["ngal"]), ptr(d["bg"]),
+                                 sth), "hmv_hod")
+            self.ev_hod.record(hs)
 
     def _limber(self, st):
         """P = P1h + P2h for mm and gm, all-gathered over z when sharded, then C_kk and C_kg (cosmology.py:536-568)."""
