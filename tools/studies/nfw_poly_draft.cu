@@ -19,7 +19,10 @@ namespace hmv {
 
 constexpr int NFWP_META = 6;                                     // c, a, a*c, ln(1+c), 1/m_c, pad
 constexpr int NFWP_REC = NFWP_NI * NFWP_STRIDE + NFWP_META;      // doubles per halo record
-constexpr int NFWP_T = 256, NFWP_E = 8, NFWP_CH = 32 * NFWP_E;
+#ifndef NFWP_EV
+#define NFWP_EV 8
+#endif
+constexpr int NFWP_T = 256, NFWP_E = NFWP_EV, NFWP_CH = 32 * NFWP_E;
 
 __global__ void __launch_bounds__(128) nfw_poly_record_kernel(int nz, int nm, const double* __restrict__ zs,
                                                               const double* __restrict__ cs,
@@ -141,3 +144,28 @@ __global__ void __launch_bounds__(NFWP_T, 3) uk_nfw_poly_kernel(int nk, int ldk,
 }
 
 }  // namespace hmv
+
+// ---- study hook (tools/studies/run_nfw_poly_draft.py): the draft as a stand-alone shared library ---------------------
+__global__ void nfwp_sorted_flag_kernel(int nk, const double* __restrict__ ks, int* __restrict__ flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  for (int k = threadIdx.x; k + 1 < nk; k += blockDim.x)
+    if (!(ks[k] <= ks[k + 1])) ok = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) *flag = ok;
+}
+
+extern "C" long long nfwp_ws_doubles(int nz, int nm) { return (long long)nz * nm * hmv::NFWP_REC + 2; }
+
+extern "C" int nfwp_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, const double* cs_d,
+                           const double* rvir_d, double* ws_d, double* uk_d, void* stream) {
+  using namespace hmv;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)nz * nm;
+  int* flag = reinterpret_cast<int*>(ws_d + rows * NFWP_REC);
+  nfwp_sorted_flag_kernel<<<1, 1024, 0, st>>>(nk < 0 ? -nk : nk, ks_d, flag);   // study hook: nk < 0 skips the pre-pass, ldk == 0 skips the cube
+  if (nk > 0) nfw_poly_record_kernel<<<(unsigned)((rows * NFWP_NI + 127) / 128), 128, 0, st>>>(nz, nm, zs_d, cs_d, rvir_d, ws_d);
+  if (ldk > 0) uk_nfw_poly_kernel<<<(unsigned)rows, NFWP_T, 0, st>>>(nk < 0 ? -nk : nk, ldk, ks_d, ws_d, flag, uk_d);
+  return (int)cudaGetLastError();
+}
