@@ -46,6 +46,7 @@ _SIGS = {
     "hmv_sigma2_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_sigma2": (_i, [_i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p]),
     "hmv_mass_function": (_i, [_i, _i, _p, _p, _d, _d, _d, _d, _d, _p, _p, _p]),
+    "hmv_mass_function_tinker": (_i, [_i, _i, _p, _p, _d, _d, _p, _p, _p, _p]),
     "hmv_halo_geometry": (_i, [_i, _i, _p, _p, _p, _d, _d, _d, _d, _p, _p, _p]),
     "hmv_mdelta": (_i, [_i, _i, _p, _p, _p, _p, _p, _p]),
     "hmv_uk_nfw_ws_doubles": (_ll, [_i, _i, _i]),

@@ -113,9 +113,15 @@ static int sigma2_splits(int nz, int nm, int nks) {
 }
 
 // ---- mass function and bias --------------------------------------------------------------------------
+// TINKER = false: Sheth-Tormen f(sigma), b(sigma) (hmvec.py:137-141, 152-156).
+// TINKER = true:  Tinker et al. 2010 (hmvec.py:142-145, 157-159 -> tinker.py:26-67): multiplicity nu f(nu) with the
+//                 per-redshift parameters tk[z] = (alpha, beta, phi, eta, gamma) prepared on the host (alpha from the
+//                 normalisation table), bias of eq. 6 for Delta = 200.
+template <bool TINKER>
 __global__ void mass_function_kernel(int nz, int nm, const double* __restrict__ sigma2,
                                      const double* __restrict__ ms, double rho_m0, double A, double a, double p,
-                                     double dc, double* __restrict__ nzm, double* __restrict__ bh) {
+                                     double dc, const double* __restrict__ tk, double* __restrict__ nzm,
+                                     double* __restrict__ bh) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nz * nm) return;
   const int z = (int)(idx / nm), m = (int)(idx - (long long)z * nm);
@@ -135,11 +141,25 @@ __global__ void mass_function_kernel(int nz, int nm, const double* __restrict__ 
     g = ca * fm + cb * f0 + cc * fp;
   }
   const double sig = sqrt(s2);
-  const double nu2a = a * dc * dc / s2;
-  // hmvec.py:141
-  const double f = A * sqrt(2.0 * a / M_PI) * (1.0 + pow(s2 / a / (dc * dc), p)) * (dc / sig) * exp(-0.5 * nu2a);
-  // hmvec.py:156
-  const double b = 1.0 + (nu2a - 1.0) / dc + (2.0 * p / dc) / (1.0 + pow(nu2a, p));
+  double f, b;
+  if constexpr (!TINKER) {
+    const double nu2a = a * dc * dc / s2;
+    // hmvec.py:141
+    f = A * sqrt(2.0 * a / M_PI) * (1.0 + pow(s2 / a / (dc * dc), p)) * (dc / sig) * exp(-0.5 * nu2a);
+    // hmvec.py:156
+    b = 1.0 + (nu2a - 1.0) / dc + (2.0 * p / dc) / (1.0 + pow(nu2a, p));
+  } else {
+    const double nu = dc / sig;
+    const double* t = tk + 5 * z;
+    const double al = t[0], be = t[1], ph = t[2], et = t[3], ga = t[4];
+    // tinker.py:62 times nu (hmvec.py:145: "f is actually nu*fnu")
+    f = nu * al * (1.0 + pow(be * nu, -2.0 * ph)) * pow(nu, 2.0 * et) * exp(-0.5 * ga * nu * nu);
+    // tinker.py:28-40 with delta = 200 and tinker's own deltac = 1.686 (its constants dict, not st_deltac)
+    const double y = log10(200.0), ey = exp(-pow(4.0 / y, 4.0));
+    const double tA = 1.0 + 0.24 * y * ey, ta = 0.44 * y - 0.88, tC = 0.019 + 0.107 * y + 0.19 * ey;
+    const double nua = pow(nu, ta);
+    b = 1.0 - tA * nua / (nua + pow(1.686, ta)) + 0.183 * pow(nu, 1.5) + tC * pow(nu, 2.4);
+  }
   const double M = ms[m];
   nzm[idx] = rho_m0 * f * g / (M * M);
   bh[idx] = b;
@@ -187,7 +207,18 @@ extern "C" int hmv_mass_function(int nz, int nm, const double* sigma2_d, const d
   HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_mass_function: need nz>0 and nm>=2 (numpy.gradient needs two samples)");
   HMV_REQUIRE(sigma2_d && ms_d && nzm_d && bh_d, "hmv_mass_function: null pointer");
   const long long n = (long long)nz * nm;
-  mass_function_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(nz, nm, sigma2_d, ms_d, rho_m0, st_A, st_a,
-                                                                        st_p, st_deltac, nzm_d, bh_d);
+  mass_function_kernel<false><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(nz, nm, sigma2_d, ms_d, rho_m0, st_A, st_a,
+                                                                               st_p, st_deltac, nullptr, nzm_d, bh_d);
   return check_launch("mass_function_kernel");
+}
+
+extern "C" int hmv_mass_function_tinker(int nz, int nm, const double* sigma2_d, const double* ms_d, double rho_m0,
+                                        double deltac, const double* tinker_z_d, double* nzm_d, double* bh_d,
+                                        void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2, "hmv_mass_function_tinker: need nz>0 and nm>=2 (numpy.gradient needs two samples)");
+  HMV_REQUIRE(sigma2_d && ms_d && tinker_z_d && nzm_d && bh_d, "hmv_mass_function_tinker: null pointer");
+  const long long n = (long long)nz * nm;
+  mass_function_kernel<true><<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(nz, nm, sigma2_d, ms_d, rho_m0, 0.0, 0.0,
+                                                                              0.0, deltac, tinker_z_d, nzm_d, bh_d);
+  return check_launch("mass_function_kernel<tinker>");
 }

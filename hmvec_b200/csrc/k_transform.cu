@@ -299,17 +299,19 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // The class kernels above run their three phases -- GNFW evaluation, tensor-core sine sums, interpolation + store --
 // one after the other inside a CTA, and the heavy classes fit one CTA per SM, so the FP64 pipe idles while the rows are
 // stored and the store path idles while the pipe works (ncu: 48 % tensor-pipe active, 8 % DRAM in the heaviest class).
-// Here ONE 512-thread CTA per SM splits into two roles that overlap:
-//   * 8 producer warps pull (z, 16-halo group) items from a global atomic queue, evaluate the samples into shared
-//     memory, run the DMMA sine sums and write the finished, normalised bin table u_j of the group into one slot of a
-//     per-CTA ring in global memory (WS_NSLOT x 16 x (N/2+2) doubles; only the bins a group needs are touched, so the
-//     ring lives in the 126 MB L2 and the consumer's re-reads hit L1);
-//   * 8 consumer warps wait for a slot and interpolate its 16 rows onto the target ks, one row per warp at a time: two
-//     binary searches split a sorted k axis into hold-u_1 / interpolate / zero spans (an unsorted axis is one
-//     general span), fills are plain 16-byte streaming stores, interpolated blocks load the table values of a lane's
-//     eight wavenumbers before the first use and prefetch the next block's table lines to L1; then release the slot.
-// full/empty mbarriers hand the slots over (producer: named barrier among its 256 threads, then one release-arrive;
-// consumer: acquire-wait), so the FP64-pipe-bound work of one group overlaps the HBM-bound stores of the previous ones.
+// Here ONE 512-thread CTA per SM holds TWO independent groups of 8 warps, each with its own 90 KB sample buffer and its
+// own bin table in global memory (only the bins an item needs are touched, so the tables live in the 126 MB L2).  A
+// group pulls (z, 16-halo group) items from a global atomic queue and runs, for each item,
+//   phase 1: evaluate the samples into its buffer, run the DMMA sine sums, write the normalised bin table u_j;
+//   phase 2: interpolate the 16 rows onto the target ks and store them.  A warp owns 256-wide k blocks and walks the 16
+//            rows of the item for each block: the wavenumbers stay in registers for all rows (no shared-memory copy of
+//            ks: that space holds the second sample buffer), and one pair of products per (row, block) classifies a
+//            block of a sorted k axis as hold-u_1 / zero / interior / general -- fills are plain 16-byte streaming
+//            stores, interior blocks interpolate without classification.
+// The two groups run free of each other ("ping-pong"): while one stores rows (HBM-bound) or sits in the latencies of
+// its phase changes, the other one's DMMAs keep the FP64 pipe busy.  There are no consumer warps, no ring and no
+// mbarriers: a group synchronises with itself through one named barrier.  Measured on a 64-z slab (tools/kbench.py):
+// phase 1 alone 2.66 ms, phase 2 alone 1.75 ms (pure fills: 1.56 ms = the HBM roof), both 3.87 ms.
 // Sixteen halos per item = two 8-row M tiles per B fragment: every sine value the recurrence produces feeds two DMMAs
 // (tools/micro/dmma_sweep.cu: one recurrence DFMA per DMMA caps the loop at 28 of 36 TFLOP/s), and a warp with 4 bin
 // tiles runs 8 independent accumulator chains (DMMA dependent-issue latency ~49 cycles, 16 cycles of pipe each).
@@ -317,17 +319,11 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // (DMMA-bound) groups alternate in every SM's queue instead of arriving as one heavy and one light phase; the last
 // redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
 // registers while the current one is being transformed.
-// Shared memory is the 90 KB sample chunk plus a copy of ks (when it fits), so there are no bin-count classes and no
-// limit on N from the bin table.
-#ifndef HMV_WS_PT
-#define HMV_WS_PT 256      // producer threads: 256 (default) or 384 (with the register re-split below; measured +0.6 %)
-#endif
-constexpr int WS_HB = 16, WS_NSLOT = 3, WS_MAXCTA = 192, WS_PT = HMV_WS_PT, WS_CT = 256;   // 8 producer + 8 consumer warps
-
-struct WsSlotMeta {
-  int z, m0, jn, nvalid;
-  double inv[WS_HB], u1[WS_HB];
-};
+#ifndef HMV_K1_ABL
+#define HMV_K1_ABL 0       // measurement builds only, bit mask: 1 skip the sample evaluation, 2 skip the sine sums,
+#endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill
+constexpr int WS_HB = 16, WS_NG = 2, WS_GT = 256, WS_MAXCTA = 192;
+constexpr int WS_GS_DOUBLES = (NCH_MMA / 4) * 64;      // one sample buffer: 16 halos x NCH_MMA samples
 
 // sum over the lanes of the caller's parity (even lanes hold halos 0-7, odd lanes halos 8-15)
 __device__ __forceinline__ double warp_sum_parity(double v) {
@@ -336,7 +332,8 @@ __device__ __forceinline__ double warp_sum_parity(double v) {
   return v;
 }
 
-__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(HMV_WS_PT) : "memory"); }
+// barrier among the 128 threads of producer group g (named barriers 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(WS_GT) : "memory"); }
 
 // sample n of halo h inside a chunk: [n/4][h%8][n%4][h/8] -- the A fragments (sample kq of halo nq, both M tiles) of a
 // 4-sample MMA step are 32 consecutive 16-byte words, one conflict-free LDS.128 per lane
@@ -461,17 +458,6 @@ __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned 
   af = __hiloint2double(fh & 0x7fffffff, __double2loint(frac));
 }
 
-// pairs [lo, hi) of a row <- (c, c): the spans of a sorted row that need no interpolation
-__device__ __forceinline__ void ws_fill(double2* orow, int lo, int hi, double c, int lane) {
-  const double2 v = make_double2(c, c);
-  int k2 = lo + lane;
-  for (; k2 + 96 < hi; k2 += 128) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) __stcs(orow + k2 + 32 * u, v);
-  }
-  for (; k2 < hi; k2 += 32) __stcs(orow + k2, v);
-}
-
 // queue position -> (z, mass-group index counted from the heavy end)
 __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
   z = item / nmg;
@@ -479,270 +465,264 @@ __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, i
   q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
 }
 
-__global__ void __launch_bounds__(WS_PT + WS_CT, 1)
-profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride, int ks_smem) {
-  extern __shared__ double smem[];
-  double* gs = smem;                          // [NCH_MMA/4][8][4][2]
-  double* kss = smem + (NCH_MMA / 4) * WS_GSB;       // [nk] copy of the target wavenumbers (when it fits: ks_smem)
-  __shared__ unsigned long long full[WS_NSLOT], empty[WS_NSLOT];
-  __shared__ WsSlotMeta meta[WS_NSLOT];
-  __shared__ double h_cmax[WS_HB], h_lxc[WS_HB], h_alpha[WS_HB], h_expo[WS_HB], h_amp[WS_HB], h_oscale[WS_HB],
-      h_inv[WS_HB];
-  __shared__ double redm[WS_PT / 32][WS_HB];
-  __shared__ int nxt_item;
+#ifndef HMV_K1_STORE
+#define HMV_K1_STORE 0
+#endif
+__device__ __forceinline__ void ws_store(double2* p, double2 v) {
+#if HMV_K1_STORE == 0
+  __stcs(p, v);
+#elif HMV_K1_STORE == 1
+  *p = v;
+#elif HMV_K1_STORE == 2
+  __stwt(p, v);
+#else
+  __stcg(p, v);
+#endif
+}
+#if HMV_K1_ABL & 16
+#define WS_NU 1
+#else
+#define WS_NU 4
+#endif
+
+struct WsGroupShared {                        // per group
+  double h_cmax[WS_HB], h_lxc[WS_HB], h_alpha[WS_HB], h_expo[WS_HB], h_amp[WS_HB], h_oscale[WS_HB], h_inv[WS_HB];
+  double u1[WS_HB];                           // bin 1 of the finished table (np.interp's left value)
+  double redm[WS_GT / 32][WS_HB];
+  int nxt_item;
+};
+
+__global__ void __launch_bounds__(WS_NG * WS_GT, 1)
+profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride) {
+  extern __shared__ double smem[];            // [WS_NG] sample buffers, each [NCH_MMA/4][8][4][2]
+  __shared__ WsGroupShared gsh[WS_NG];
   __shared__ GnfwTables tabs;
 
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < WS_NSLOT; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, WS_CT / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    nxt_item = atomicAdd(work_counter, 1);
-  }
-  gnfw_tables_init(tabs, tid, WS_PT + WS_CT);
+  if (tid < WS_NG) gsh[tid].nxt_item = atomicAdd(work_counter, 1);
+  gnfw_tables_init(tabs, tid, WS_NG * WS_GT);
   int ascending = 1;
-  for (int k = tid; k < p.nk; k += WS_PT + WS_CT) {
-    const double kv = __ldg(p.ks + k);
-    if (ks_smem) kss[k] = kv;
-    if (k + 1 < p.nk && !(kv <= __ldg(p.ks + k + 1))) ascending = 0;
-  }
-  const int sorted = __syncthreads_and(ascending);     // also publishes the mbarriers and kss
+  for (int k = tid; k + 1 < p.nk; k += WS_NG * WS_GT)
+    if (!(__ldg(p.ks + k) <= __ldg(p.ks + k + 1))) ascending = 0;
+  const int sorted = __syncthreads_and(ascending);     // also publishes the tables and nxt_item
   const int JS = p.JS;
-  double* slots = ring + (size_t)blockIdx.x * WS_NSLOT * WS_HB * JS;
 
-  if (tid < WS_PT) {
-#if HMV_WS_PT == 384
-    // 640 threads are launched with 96 registers each (61440); the producers take 112 and the consumers give back down
-    // to 72 (384*112 + 256*72 = 61440: the increase can only complete because the sum fits the CTA's allocation)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-#endif
-    // =============================== producers: samples -> sine sums -> bin table ================================
-    const double2* T = reinterpret_cast<const double2*>(p.sintab);
-    const int warp = tid >> 5, lane = tid & 31, hoff = (tid & 1) << 3;
-    // parameters of halo `tid` (tid < 16) of an item, fetched one item ahead
-    double f_cmax = -1.0, f_xc = 1.0, f_alpha = 0.0, f_expo = 0.0, f_amp = 0.0, f_oscale = 1.0, f_inv = 0.0;
-    int f_jn = 0;
-    auto fetch = [&](int item) {
-      if (item >= nitems) return;
-      int z, q;
-      ws_item(item, p.nz, p.nmg, stride, z, q);
-      f_jn = p.jn_cta[z * p.nmg + q];
-      if (tid < WS_HB) {
-        const int m = (p.nmg - 1 - q) * WS_HB + tid;
-        const bool ok = m < p.nm;
-        const long long rr = (long long)z * p.nm + (ok ? m : p.nm - 1);
-        f_cmax = ok ? p.cmax[rr] : -1.0;
-        f_xc = p.xc[rr];
-        f_alpha = p.alpha[rr];
-        f_expo = p.expo[rr];
-        f_amp = p.amp[rr];
-        f_oscale = p.outscale ? p.outscale[rr] : 1.0;
-        f_inv = p.rs[rr] * (1.0 + p.zs[z]) / p.kt1;            // k -> fractional bin index   (fft.py:92)
-      }
-    };
-    auto publish = [&]() {
-      if (tid < WS_HB) {
-        h_cmax[tid] = f_cmax; h_lxc[tid] = log(f_xc); h_alpha[tid] = f_alpha; h_expo[tid] = f_expo;
-        h_amp[tid] = f_amp; h_oscale[tid] = f_oscale; h_inv[tid] = f_inv;
-      }
-    };
-    int item = nxt_item;
-    fetch(item);
-    publish();
-    producer_bar();
-    for (unsigned it = 0;; ++it) {
-      const int s = (int)(it % WS_NSLOT);
-      const unsigned ph = (it / WS_NSLOT) & 1u;
-      if (tid == 0) nxt_item = atomicAdd(work_counter, 1);
-      mbar_wait(empty + s, ph ^ 1u);           // the consumers are done with this slot (first lap passes at once)
-      if (item >= nitems) {                    // queue drained: hand the consumers a stop marker
-        if (tid == 0) { meta[s].jn = -1; mbar_arrive(full + s); }
-        break;
-      }
-      int z, q;
-      ws_item(item, p.nz, p.nmg, stride, z, q);
-      const int jn = f_jn;
-      const int m0 = (p.nmg - 1 - q) * WS_HB;
-      HMV_DEV_ASSERT(jn >= 2 && jn <= p.J && m0 >= 0 && m0 < p.nm && z >= 0 && z < p.nz);
-      double* U = slots + (size_t)s * WS_HB * JS;
-      if (tid < WS_HB) meta[s].inv[tid] = h_inv[tid];
-      if (tid == 0) { meta[s].z = z; meta[s].m0 = m0; meta[s].jn = jn; meta[s].nvalid = min(WS_HB, p.nm - m0); }
-      producer_bar();                          // h_* of this item and nxt_item are visible
-      const int nxt = nxt_item;
-      fetch(nxt);                              // loads in flight behind the whole transform of this item
-
-      double cmx = -1.0;
-#pragma unroll
-      for (int h = 0; h < WS_HB; ++h) cmx = fmax(cmx, h_cmax[h]);
-      const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
-      const bool single = nb > 0 && nb <= NCH_MMA;
-      if (nb == 0)
-        for (int i = tid; i < WS_HB * (jn + 1); i += WS_PT) U[(size_t)(i / (jn + 1)) * JS + 1 + i % (jn + 1)] = 0.0;
-
-      double msum[8];                          // this lane's half of the halos (hoff ...)
-#pragma unroll
-      for (int h = 0; h < 8; ++h) msum[h] = 0.0;
-      double scale0 = 1.0, scale1 = 1.0;
-
-      for (int n0 = 0; n0 < nb; n0 += NCH_MMA) {
-        const int nfill = min(NCH_MMA, ((nb - n0) + 3) & ~3);
-        // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15, the eight
-        // chains of a thread in lock-step (gnfw_eval.cuh); samples outside a halo's theta-cut are masked afterwards
-        for (int sn = tid >> 1; sn < nfill; sn += WS_PT / 2) {
-          const int n = n0 + sn;
-          const double x = (double)(n + 1) * p.dx;
-          const double wx = ((n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx) * x;   // np.trapz weights on xs (fft.py:84)
-          double lt[8], y[8], f[8];
-          {
-            const double xv[1] = {x};
-            double lxv[1];
-            log_lockstep<1>(tabs, xv, 0.0, lxv);
-#pragma unroll
-            for (int hh = 0; hh < 8; ++hh) { lt[hh] = lxv[0] - h_lxc[hh + hoff]; y[hh] = h_alpha[hh + hoff] * lt[hh]; }
-          }
-          exp_lockstep<8>(tabs, y, f);                       // t^alpha
-          log_lockstep<8>(tabs, f, 1.0, y);                  // log(1 + t^alpha)
-#pragma unroll
-          for (int hh = 0; hh < 8; ++hh) y[hh] = fma(-h_expo[hh + hoff], y[hh], p.gamma * lt[hh]);
-          exp_lockstep<8>(tabs, y, f);                       // t^gamma (1 + t^alpha)^(-expo)
-#pragma unroll
-          for (int hh = 0; hh < 8; ++hh) {
-            const int h = hh + hoff;
-            const double v = (n < p.N && x <= h_cmax[h]) ? (x * h_amp[h]) * f[hh] : 0.0;   // x * rho(x) inside the cut
-            msum[hh] = fma(wx, v, msum[hh]);
-            HMV_DEV_ASSERT(ws_gs_index(sn, h) >= 0 && ws_gs_index(sn, h) < (NCH_MMA / 4) * WS_GSB);
-            gs[ws_gs_index(sn, h)] = v;
-          }
-        }
-        if (single && p.do_mass_norm) {
-#pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            const double v = warp_sum_parity(msum[h]);
-            if (lane < 2) redm[warp][h + hoff] = v;
-          }
-        }
-        producer_bar();
-        if (single) {
-          const int nq = lane >> 2;
-          double mn0 = 1.0, mn1 = 1.0;
-          if (p.do_mass_norm) {
-            mn0 = 0.0; mn1 = 0.0;
-#pragma unroll
-            for (int w8 = 0; w8 < WS_PT / 32; ++w8) { mn0 += redm[w8][nq]; mn1 += redm[w8][nq + 8]; }
-          }
-          scale0 = p.step / mn0 * h_oscale[nq];
-          scale1 = p.step / mn1 * h_oscale[nq + 8];
-        }
-        const int nlen = min(NCH_MMA, nb - n0);
-        constexpr int NW = WS_PT / 32;
-        const int ntile = (jn + 7) >> 3;
-#define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.rkt, meta[s].u1)
-        const bool first = n0 == 0;
-        // bin tiles split evenly over the warps (counts differ by at most one), each warp's share in passes of up to
-        // four tiles of equal size (5 tiles: 3 + 2, not 4 + 1, so that no pass runs on two accumulator chains)
-        int rem = ntile / NW + (warp < ntile % NW);
-        int tb = warp * (ntile / NW) + min(warp, ntile % NW);
-        for (int passes = (rem + 3) >> 2; passes > 0; --passes) {
-          const int ntc = (rem + passes - 1) / passes;
-          const int jw = 1 + 8 * tb;
-          switch (ntc) {
-            case 4: HMV_WS_ACC(4); break;
-            case 3: HMV_WS_ACC(3); break;
-            case 2: HMV_WS_ACC(2); break;
-            default: HMV_WS_ACC(1); break;
-          }
-          tb += ntc;
-          rem -= ntc;
-        }
-#undef HMV_WS_ACC
-        producer_bar();                        // the chunk's samples are consumed, its sums are in the table
-      }
-
-      if (!single) {
-        // profile longer than one chunk (or empty): normalise the finished table in a separate pass
-        if (p.do_mass_norm) {
-#pragma unroll
-          for (int h = 0; h < 8; ++h) {
-            const double v = warp_sum_parity(msum[h]);
-            if (lane < 2) redm[warp][h + hoff] = v;
-          }
-        }
-        producer_bar();
-        for (int i = tid; i < WS_HB * jn; i += WS_PT) {
-          const int h = i / jn, j = 1 + (i - h * jn);
-          double mn = 1.0;
-          if (p.do_mass_norm) {
-            mn = 0.0;
-            for (int w8 = 0; w8 < WS_PT / 32; ++w8) mn += redm[w8][h];
-          }
-          const double v = U[(size_t)h * JS + j] * (p.step / mn * h_oscale[h]) * __ldg(p.rkt + j);
-          U[(size_t)h * JS + j] = v;
-          if (j == 1) meta[s].u1[h] = v;
-        }
-      }
-      if (tid < WS_HB) U[(size_t)tid * JS + jn + 1] = 0.0;   // guard bin behind the last computed one
-      producer_bar();                          // table complete; nobody reads this item's h_* any more
-      if (tid == 0) mbar_arrive(full + s);     // release: the table and its meta record are visible to the consumers
-      publish();                               // next item's parameters (ordered by the next trip's first barrier)
-      item = nxt;
+  const int g = tid / WS_GT, gt = tid - g * WS_GT;
+  WsGroupShared& G = gsh[g];
+  double* gs = smem + (size_t)g * WS_GS_DOUBLES;
+  double* U = ring + ((size_t)blockIdx.x * WS_NG + g) * WS_HB * JS;        // this group's bin table (L2-resident)
+  const double2* T = reinterpret_cast<const double2*>(p.sintab);
+  const int warp = gt >> 5, lane = gt & 31, hoff = (gt & 1) << 3;
+  const int npair = p.nk >> 1;
+  const int nblk = (npair + 127) >> 7;
+  const double2* ks2 = reinterpret_cast<const double2*>(p.ks);
+  const double tJ = (double)p.J;
+  // parameters of halo `gt` (gt < 16) of an item, fetched one item ahead
+  double f_cmax = -1.0, f_xc = 1.0, f_alpha = 0.0, f_expo = 0.0, f_amp = 0.0, f_oscale = 1.0, f_inv = 0.0;
+  int f_jn = 0;
+  auto fetch = [&](int item) {
+    if (item >= nitems) return;
+    int z, q;
+    ws_item(item, p.nz, p.nmg, stride, z, q);
+    f_jn = p.jn_cta[z * p.nmg + q];
+    if (gt < WS_HB) {
+      const int m = (p.nmg - 1 - q) * WS_HB + gt;
+      const bool ok = m < p.nm;
+      const long long rr = (long long)z * p.nm + (ok ? m : p.nm - 1);
+      f_cmax = ok ? p.cmax[rr] : -1.0;
+      f_xc = p.xc[rr];
+      f_alpha = p.alpha[rr];
+      f_expo = p.expo[rr];
+      f_amp = p.amp[rr];
+      f_oscale = p.outscale ? p.outscale[rr] : 1.0;
+      f_inv = p.rs[rr] * (1.0 + p.zs[z]) / p.kt1;            // k -> fractional bin index   (fft.py:92)
     }
-  } else {
-#if HMV_WS_PT == 384
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-#endif
-    // =============================== consumers: interpolate onto ks, store the rows ==============================
-    const int ct = tid - WS_PT, lane = ct & 31, cw = ct >> 5;
-    const int npair = p.nk >> 1;
-    // wavenumbers come from shared memory when the grid fits there (generic pointer: LDS or LDG)
-    const double* ks1 = ks_smem ? kss : p.ks;
-    const double2* ks2 = reinterpret_cast<const double2*>(ks1);
-    const double tJ = (double)p.J;
-    for (unsigned it = 0;; ++it) {
-      const int s = (int)(it % WS_NSLOT);
-      const unsigned ph = (it / WS_NSLOT) & 1u;
-      mbar_wait(full + s, ph);
-      const int jn = meta[s].jn;
-      if (jn < 0) break;
-      const int nvalid = meta[s].nvalid;
-      const double* U = slots + (size_t)s * WS_HB * JS;
-      double* out0 = p.uk + ((long long)meta[s].z * p.nm + meta[s].m0) * (long long)p.ldk;
-      const int jcap = min(p.J - 1, jn);
-      for (int row = cw; row < nvalid; row += WS_CT / 32) {
-        const double inv = meta[s].inv[row], u1 = meta[s].u1[row];
-        const double* Uh = U + (size_t)row * JS;
-        double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk);
-        // sorted ks: [0, eA) is below the first bin (hold u_1), [eB, nk) is above the last one (zero); whole blocks
-        // inside those spans are plain fills.  Unsorted ks: every block takes the general path.
-        int pA = 0, pB = npair, pA1 = npair, pB0 = 0;   // (unsorted: no interior blocks)
-        if (sorted) {
-          int lo = 0, hi = p.nk;                       // first element with k*inv >= 1
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv >= 1.0) hi = mid; else lo = mid + 1; }
-          pA = lo >> 1;
-          pA1 = (lo + 1) >> 1;
-          lo = 0; hi = p.nk;                           // first element with k*inv > J
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (ks1[mid] * inv > tJ) hi = mid; else lo = mid + 1; }
-          pB = (lo + 1) >> 1;
-          pB0 = lo >> 1;                               // pairs [pA1, pB0) lie entirely inside [eA, eB)
+  };
+  auto publish = [&]() {
+    if (gt < WS_HB) {
+      G.h_cmax[gt] = f_cmax; G.h_lxc[gt] = log(f_xc); G.h_alpha[gt] = f_alpha; G.h_expo[gt] = f_expo;
+      G.h_amp[gt] = f_amp; G.h_oscale[gt] = f_oscale; G.h_inv[gt] = f_inv;
+    }
+  };
+  int item = G.nxt_item;
+  fetch(item);
+  publish();
+  group_bar(g);
+  while (item < nitems) {
+    if (gt == 0) G.nxt_item = atomicAdd(work_counter, 1);
+    int z, q;
+    ws_item(item, p.nz, p.nmg, stride, z, q);
+    const int jn = f_jn;
+    const int m0 = (p.nmg - 1 - q) * WS_HB;
+    HMV_DEV_ASSERT(jn >= 2 && jn <= p.J && m0 >= 0 && m0 < p.nm && z >= 0 && z < p.nz);
+    group_bar(g);                            // h_* of this item and nxt_item are visible
+    const int nxt = G.nxt_item;
+    fetch(nxt);                              // loads in flight behind the whole transform of this item
+
+    // ======================== phase 1: samples -> sine sums -> bin table of the item ========================
+    double cmx = -1.0;
+#pragma unroll
+    for (int h = 0; h < WS_HB; ++h) cmx = fmax(cmx, G.h_cmax[h]);
+    const int nb = (cmx > 0.0) ? (int)fmin((double)p.N, floor(cmx / p.dx) + 2.0) : 0;
+    const bool single = nb > 0 && nb <= NCH_MMA;
+    if (nb == 0)
+      for (int i = gt; i < WS_HB * (jn + 1); i += WS_GT) U[(size_t)(i / (jn + 1)) * JS + 1 + i % (jn + 1)] = 0.0;
+
+    double msum[8];                          // this lane's half of the halos (hoff ...)
+#pragma unroll
+    for (int h = 0; h < 8; ++h) msum[h] = 0.0;
+    double scale0 = 1.0, scale1 = 1.0;
+
+    for (int n0 = 0; n0 < nb; n0 += NCH_MMA) {
+      const int nfill = min(NCH_MMA, ((nb - n0) + 3) & ~3);
+      // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15, the eight
+      // chains of a thread in lock-step (gnfw_eval.cuh); samples outside a halo's theta-cut are masked afterwards
+#if !(HMV_K1_ABL & 1)
+      for (int sn = gt >> 1; sn < nfill; sn += WS_GT / 2) {
+        const int n = n0 + sn;
+        const double x = (double)(n + 1) * p.dx;
+        const double wx = ((n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx) * x;   // np.trapz weights on xs (fft.py:84)
+        double lt[8], y[8], f[8];
+        {
+          const double xv[1] = {x};
+          double lxv[1];
+          log_lockstep<1>(tabs, xv, 0.0, lxv);
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) { lt[hh] = lxv[0] - G.h_lxc[hh + hoff]; y[hh] = G.h_alpha[hh + hoff] * lt[hh]; }
         }
-        const int pA0 = pA & ~127;                                   // blocks stay aligned to 2 KB of the row
-        ws_fill(orow, 0, pA0, u1, lane);                             // below the first bin: hold u_1
-        for (int base = pA0; base < pB; base += 128) {
-          {  // table lines the NEXT block reads go to L1 while this one is interpolated: the bins between its first
-             // and last wavenumber, one 128-byte line per lane (sorted ks; merely a hint otherwise)
-            const double MAGIC = 6755399441055744.0;
-            const unsigned j0 = min((unsigned)__double2loint(fma(ks1[min(2 * (base + 128), p.nk - 1)], inv, MAGIC)), (unsigned)jcap);
-            const unsigned j1 = min((unsigned)__double2loint(fma(ks1[min(2 * (base + 256) - 1, p.nk - 1)], inv, MAGIC)), (unsigned)(jcap + 1));
-            for (unsigned j = (max(j0, 1u) - 1u & ~15u) + 16u * lane; j <= j1; j += 512u)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(Uh + j));
-          }
-          if (base >= pA1 && base + 128 <= pB0) {
-            // whole block strictly inside [eA, eB): 1 <= t <= J for all of its 256 wavenumbers
+        exp_lockstep<8>(tabs, y, f);                       // t^alpha
+        log_lockstep<8>(tabs, f, 1.0, y);                  // log(1 + t^alpha)
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh) y[hh] = fma(-G.h_expo[hh + hoff], y[hh], p.gamma * lt[hh]);
+        exp_lockstep<8>(tabs, y, f);                       // t^gamma (1 + t^alpha)^(-expo)
+#pragma unroll
+        for (int hh = 0; hh < 8; ++hh) {
+          const int h = hh + hoff;
+          const double v = (n < p.N && x <= G.h_cmax[h]) ? (x * G.h_amp[h]) * f[hh] : 0.0;   // x * rho(x) inside the cut
+          msum[hh] = fma(wx, v, msum[hh]);
+          HMV_DEV_ASSERT(ws_gs_index(sn, h) >= 0 && ws_gs_index(sn, h) < WS_GS_DOUBLES);
+          gs[ws_gs_index(sn, h)] = v;
+        }
+      }
+#else
+      msum[0] = 1.0;
+#endif
+      if (single && p.do_mass_norm) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const double v = warp_sum_parity(msum[h]);
+          if (lane < 2) G.redm[warp][h + hoff] = v;
+        }
+      }
+      group_bar(g);
+      if (single) {
+        const int nq = lane >> 2;
+        double mn0 = 1.0, mn1 = 1.0;
+        if (p.do_mass_norm) {
+          mn0 = 0.0; mn1 = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < WS_GT / 32; ++w8) { mn0 += G.redm[w8][nq]; mn1 += G.redm[w8][nq + 8]; }
+        }
+        scale0 = p.step / mn0 * G.h_oscale[nq];
+        scale1 = p.step / mn1 * G.h_oscale[nq + 8];
+      }
+#if !(HMV_K1_ABL & 2)
+      const int nlen = min(NCH_MMA, nb - n0);
+      constexpr int NW = WS_GT / 32;
+      const int ntile = (jn + 7) >> 3;
+#define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.rkt, G.u1)
+      const bool first = n0 == 0;
+      // bin tiles split evenly over the warps (counts differ by at most one), each warp's share in passes of up to
+      // four tiles of equal size (5 tiles: 3 + 2, not 4 + 1, so that no pass runs on two accumulator chains)
+      int rem = ntile / NW + (warp < ntile % NW);
+      int tb = warp * (ntile / NW) + min(warp, ntile % NW);
+      for (int passes = (rem + 3) >> 2; passes > 0; --passes) {
+        const int ntc = (rem + passes - 1) / passes;
+        const int jw = 1 + 8 * tb;
+        switch (ntc) {
+          case 4: HMV_WS_ACC(4); break;
+          case 3: HMV_WS_ACC(3); break;
+          case 2: HMV_WS_ACC(2); break;
+          default: HMV_WS_ACC(1); break;
+        }
+        tb += ntc;
+        rem -= ntc;
+      }
+#undef HMV_WS_ACC
+#else
+      if (gt < WS_HB) G.u1[gt] = scale0;
+#endif
+      group_bar(g);                          // the chunk's samples are consumed, its sums are in the table
+    }
+
+    if (!single) {
+      // profile longer than one chunk (or empty): normalise the finished table in a separate pass
+      if (p.do_mass_norm) {
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          const double v = warp_sum_parity(msum[h]);
+          if (lane < 2) G.redm[warp][h + hoff] = v;
+        }
+      }
+      group_bar(g);
+      for (int i = gt; i < WS_HB * jn; i += WS_GT) {
+        const int h = i / jn, j = 1 + (i - h * jn);
+        double mn = 1.0;
+        if (p.do_mass_norm) {
+          mn = 0.0;
+          for (int w8 = 0; w8 < WS_GT / 32; ++w8) mn += G.redm[w8][h];
+        }
+        const double v = U[(size_t)h * JS + j] * (p.step / mn * G.h_oscale[h]) * __ldg(p.rkt + j);
+        U[(size_t)h * JS + j] = v;
+        if (j == 1) G.u1[h] = v;
+      }
+    }
+    if (gt < WS_HB) U[(size_t)gt * JS + jn + 1] = 0.0;     // guard bin behind the last computed one
+    __threadfence_block();
+    group_bar(g);                            // table complete and visible to the whole group
+
+    // ======================== phase 2: interpolate the 16 rows onto ks, store them ========================
+#if !(HMV_K1_ABL & 4)
+    {
+      const int nvalid = min(WS_HB, p.nm - m0);
+      double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
+      const int jcap = min(p.J - 1, jn);
+      for (int blk = warp; blk < nblk; blk += WS_GT / 32) {
+        const int base = blk << 7;                       // first pair of the block
+        const bool whole = base + 128 <= npair;
+        double2 kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kk[u] = __ldg(ks2 + min(base + lane + 32 * u, npair - 1));
+        // lane r (and r + 16) classifies the block for row r: 0 all below the first bin (hold u_1), 1 all above the
+        // last bin (zero), 2 all inside [1, J] (interior), 3 mixed / unsorted ks / last partial block
+        int cls = 3;
+        if (sorted && whole) {
+          const double kf = __ldg(p.ks + 2 * base), kl = __ldg(p.ks + 2 * base + 255);
+          const double inv_r = G.h_inv[lane & 15];
+          const double tf = kf * inv_r, tl = kl * inv_r;
+          cls = (tl < 1.0) ? 0 : (tf > tJ) ? 1 : (tf >= 1.0 && tl <= tJ) ? 2 : 3;
+        }
+#if HMV_K1_ABL & 8
+        cls = 0;
+#endif
+        for (int row = 0; row < nvalid; ++row) {
+          const int c = __shfl_sync(0xffffffffu, cls, row);
+          double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk) + base + lane;
+          if (c < 2) {
+            const double fv = c ? 0.0 : G.u1[row];
+            const double2 v = make_double2(fv, fv);
+#pragma unroll
+            for (int u = 0; u < WS_NU; ++u)
+              if (whole || base + lane + 32 * u < npair) ws_store(orow + 32 * u, v);
+          } else if (c == 2) {
+            const double inv = G.h_inv[row];
+            const double* Uh = U + (size_t)row * JS;
             unsigned jc[8], jo[8];
             double af[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const double2 kk = ks2[base + lane + 32 * u];
-              ws_lerp_interior(kk.x, inv, (unsigned)(jcap + 1), jc[2 * u], jo[2 * u], af[2 * u]);
-              ws_lerp_interior(kk.y, inv, (unsigned)(jcap + 1), jc[2 * u + 1], jo[2 * u + 1], af[2 * u + 1]);
+              ws_lerp_interior(kk[u].x, inv, (unsigned)(jcap + 1), jc[2 * u], jo[2 * u], af[2 * u]);
+              ws_lerp_interior(kk[u].y, inv, (unsigned)(jcap + 1), jc[2 * u + 1], jo[2 * u + 1], af[2 * u + 1]);
             }
             double ua[8], uo[8];
 #pragma unroll
@@ -752,16 +732,16 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              __stcs(orow + base + lane + 32 * u, make_double2(fma(af[2 * u], uo[2 * u] - ua[2 * u], ua[2 * u]),
-                                                               fma(af[2 * u + 1], uo[2 * u + 1] - ua[2 * u + 1], ua[2 * u + 1])));
+              ws_store(orow + 32 * u, make_double2(fma(af[2 * u], uo[2 * u] - ua[2 * u], ua[2 * u]),
+                                                  fma(af[2 * u + 1], uo[2 * u + 1] - ua[2 * u + 1], ua[2 * u + 1])));
           } else {
+            const double inv = G.h_inv[row], u1 = G.u1[row];
+            const double* Uh = U + (size_t)row * JS;
             WsLerp e[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int k2 = min(base + lane + 32 * u, npair - 1);
-              const double2 kk = ks2[k2];
-              e[2 * u] = ws_lerp_setup(kk.x, inv, p.J, jcap);
-              e[2 * u + 1] = ws_lerp_setup(kk.y, inv, p.J, jcap);
+              e[2 * u] = ws_lerp_setup(kk[u].x, inv, p.J, jcap);
+              e[2 * u + 1] = ws_lerp_setup(kk[u].y, inv, p.J, jcap);
             }
             double ua[8], uo[8];
 #pragma unroll
@@ -771,27 +751,27 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int k2 = base + lane + 32 * u;
               const double2 v = make_double2(ws_lerp_finish(e[2 * u], ua[2 * u], uo[2 * u], u1),
                                              ws_lerp_finish(e[2 * u + 1], ua[2 * u + 1], uo[2 * u + 1], u1));
-              if (k2 < pB) __stcs(orow + k2, v);
+              if (whole || base + lane + 32 * u < npair) ws_store(orow + 32 * u, v);
             }
           }
         }
-        ws_fill(orow, pB, npair, 0.0, lane);                         // above the last bin: zero
-        if ((p.nk & 1) && lane == 0) {         // odd nk: the last wavenumber
-          const int k = p.nk - 1;
-          out0[(long long)row * p.ldk + k] = ws_interp(Uh, ks1[k] * inv, u1, tJ, jcap);
-        }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
+      if ((p.nk & 1) && warp == 0 && lane < nvalid) {      // odd nk: the last wavenumber, one row per lane
+        const int k = p.nk - 1;
+        out0[(long long)lane * p.ldk + k] = ws_interp(U + (size_t)lane * JS, __ldg(p.ks + k) * G.h_inv[lane], G.u1[lane], tJ, jcap);
+      }
     }
+#endif
+    group_bar(g);                            // every warp is done with the table, u1 and this item's h_*
+    publish();                               // next item's parameters (ordered by the next trip's first barrier)
+    item = nxt;
   }
 }
 
 static bool ws_ring_fits(int nxs) {
-  return (size_t)WS_MAXCTA * WS_NSLOT * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)4 << 30);   // only the bins a group needs are ever touched; covers every N the phase index allows (N < 65536)
+  return (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)8 << 30);   // only the bins a group needs are ever touched; covers every N the phase index allows (N < 65536)
 }
 
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
@@ -811,12 +791,10 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int stride = (int)(0.381966 * q.nmg);
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
-  size_t smem = (size_t)(NCH_MMA / 4) * WS_GSB * sizeof(double);
-  const int ks_smem = smem + (size_t)(p.nk + 1) * sizeof(double) <= (size_t)220 * 1024;
-  if (ks_smem) smem += (size_t)(p.nk + 1) * sizeof(double);
+  const size_t smem = (size_t)WS_NG * WS_GS_DOUBLES * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  profile_transform_ws_kernel<<<grid, WS_PT + WS_CT, smem, st>>>(q, ring, counter, nitems, stride, ks_smem);
+  profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride);
   return check_launch("profile_transform_ws_kernel");
 }
 
@@ -847,7 +825,7 @@ extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
   // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
   long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2 + (nxs / 2 + 2);   // ..., queue head, 1/kt_j
-  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NSLOT * WS_HB * (nxs / 2 + 2);   // bin-table ring of the persistent kernel
+  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NG * WS_HB * (nxs / 2 + 2);   // bin-table rings of the persistent kernel
   return n;
 }
 

@@ -44,6 +44,12 @@ int hmv_sigma2(int nz, int nm, int nks, const double* sPzk_d, const double* kw_d
  * nzm = rho_m0 * f * dln(sigma^-1)/dlnM / M^2 with numpy.gradient's non-uniform stencil along M. */
 int hmv_mass_function(int nz, int nm, const double* sigma2_d, const double* ms_d, double rho_m0, double st_A,
                       double st_a, double st_p, double st_deltac, double* nzm_d, double* bh_d, void* stream);
+/* f3: the same with the Tinker et al. 2010 multiplicity function nu f(nu) and bias (hmvec.py:142-145,157-159 ->
+ * tinker.py:26-67; mass_function="tinker").  tinker_z_d: [nz][5] = (alpha, beta, phi, eta, gamma) of f(nu) at each
+ * redshift -- O(nz) host work: redshifts clamped at 3, alpha from the reference's normalisation table
+ * hmvec/data/alpha_consistency.txt (tinker.py:56-66).  nu = deltac/sigma; the bias uses Delta = 200. */
+int hmv_mass_function_tinker(int nz, int nm, const double* sigma2_d, const double* ms_d, double rho_m0, double deltac,
+                             const double* tinker_z_d, double* nzm_d, double* bh_d, void* stream);
 
 /* ---- a3: Duffy concentration and r_vir  (hmvec.py:68-73,111-115,163-176,627) ------------------------
  * cs = A (h M/2e12)^alpha (1+z)^beta ; rvir = (3M/(4 pi drho1[z]))^(1/3), drho1 = Delta_vir rho_c or 200 rho_m. */
