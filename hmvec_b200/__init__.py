@@ -8,4 +8,5 @@ from .hmvec import *  # noqa: F401,F403
 from .hmvec import HaloModel, DeviceCubes, duffy_concentration, R_from_M  # noqa: F401
 from .cosmology import Cosmology, limber_integral, simpson_weights, Wkr, Wkr_taylor, a2z, get_eds_model  # noqa: F401
 from .params import default_params, battaglia_defaults  # noqa: F401
-from . import utils, zshard  # noqa: F401
+from . import utils, zshard, tinker, fft, hostfuncs  # noqa: F401
+from .fft import generic_profile_fft, fft_integral, analytic_fft_integral, uk_fft, uk_brute_force  # noqa: F401

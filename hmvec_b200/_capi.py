@@ -56,6 +56,7 @@ _SIGS = {
     "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_set_transform_mode": (_i, [_i]),
     "hmv_profile_transform": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
+    "hmv_profile_transform_samples": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _d, _i, _i, _p, _p, _p]),
     "hmv_hod": (_i, [_i, _i, _p, _p, _p, C.POINTER(_d), _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_hod_bisect": (_i, [_i, _i, _p, _p, _p, _p, C.POINTER(_d), _d, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_hod_pick": (_i, [_i, _p, _p, _d, _p, _p, _p]),
@@ -68,6 +69,8 @@ _SIGS = {
                                _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
+    "hmv_outer": (_i, [_i, _i, _p, _p, _p, _p]),
+    "hmv_sum2": (_i, [_ll, _p, _p, _p, _p]),
     "hmv_bench_dfma": (_d, [_i, _p]),
     "hmv_bench_dmma": (_d, [_i, _p]),
     "hmv_bench_copy": (_d, [_p, _p, _ll, _i, _p]),

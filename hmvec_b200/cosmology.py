@@ -245,17 +245,23 @@ class Cosmology(object):
         return eisenstein_hu(np.asarray(ks, dtype=np.float64), self.h, self.params['omch2'], self.params['ombh2'],
                              self.omm0, wiggles=(type == 'eisenhu_osc'))
 
-    def P_lin_approx(self, ks, zs, type='eisenhu_osc'):
-        """cosmology.py:391-402"""
-        zs = np.atleast_1d(zs)
-        ks = np.asarray(ks)
-        tk = self.Tk(ks, type=type)[None, :]
-        Dzs = self.D_growth(1 / (1 + zs), type='anorm')[:, None]
+    def P_lin_approx_factors(self, ks, zs, type='eisenhu_osc'):
+        """The two factors of the separable EH98 power of cosmology.py:391-402: (D(z)^2 [nz], pref k (k/kp)^(ns-1)
+        T(k)^2 [nk]); P(z,k) is their outer product (host: P_lin_approx, device: hmv_outer)."""
+        zs = np.atleast_1d(np.asarray(zs, dtype=np.float64))
+        ks = np.asarray(ks, dtype=np.float64).reshape(-1)
+        tk = self.Tk(ks, type=type)
+        Dzs = self.D_growth(1 / (1 + zs), type='anorm')
         kp, ns = self.params['pivot_scalar'], self.params['ns']
         omh2 = (self.params['omch2'] + self.params['ombh2']) * 100 ** 2. + self.get_Omega_nu() * self.params['H0'] ** 2.
         kfacts = (ks / kp) ** (ns - 1.) * ks
         pref = 8 * np.pi ** 2 * self.params['As'] / 25. / omh2 ** 2. * cspeed ** 4.
-        return pref * kfacts[None, :] * Dzs ** 2. * tk ** 2.
+        return Dzs ** 2., pref * kfacts * tk ** 2.
+
+    def P_lin_approx(self, ks, zs, type='eisenhu_osc'):
+        """cosmology.py:391-402"""
+        d2, v = self.P_lin_approx_factors(ks, zs, type=type)
+        return d2[:, None] * v[None, :]
 
     def P_lin(self, ks, zs, knorm=1e-4, kmax=None):
         """cosmology.py:353-374 (needs CAMB for the normalisation)."""

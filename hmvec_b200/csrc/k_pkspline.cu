@@ -73,6 +73,22 @@ __global__ void pk_spline_kernel(int nz, int nk, const double* __restrict__ zs, 
   out[(long long)z * nk + k] = scale * (islog ? exp(sp) : sp);
 }
 
+
+// P(z,k) = D2[z] * v[k]: the separable EH98 linear power of accuracy='low' (cosmology.py:391-402) formed on the
+// device from its two O(nz) and O(nk) host-side factors
+__global__ void outer_kernel(int nz, int nk, const double* __restrict__ a, const double* __restrict__ b,
+                             double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (k < nk) out[(long long)z * nk + k] = a[z] * b[k];
+}
+
+// out = a + b (P = P1h + P2h, hmvec.py:500-502)
+__global__ void sum2_kernel(long long n, const double* __restrict__ a, const double* __restrict__ b,
+                            double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b[i];
+}
+
 }  // namespace hmv
 using namespace hmv;
 
@@ -88,4 +104,18 @@ extern "C" int hmv_pk_spline(int nz, int nk, const double* zs_d, const double* k
   pk_spline_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(nz, nk, zs_d, ks_d, nx, ny, kx, ky, tx_d, ty_d, c_d, islog,
                                                             scale, out_d);
   return check_launch("pk_spline_kernel");
+}
+
+extern "C" int hmv_outer(int nz, int nk, const double* a_d, const double* b_d, double* out_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nk > 0 && nz <= 65535, "hmv_outer: bad sizes (nz=%d nk=%d)", nz, nk);
+  HMV_REQUIRE(a_d && b_d && out_d, "hmv_outer: null pointer");
+  dim3 grid(cdiv(nk, 256), nz);
+  outer_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nz, nk, a_d, b_d, out_d);
+  return check_launch("outer_kernel");
+}
+
+extern "C" int hmv_sum2(long long n, const double* a_d, const double* b_d, double* out_d, void* stream) {
+  HMV_REQUIRE(n > 0 && a_d && b_d && out_d, "hmv_sum2: bad arguments");
+  sum2_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, a_d, b_d, out_d);
+  return check_launch("sum2_kernel");
 }

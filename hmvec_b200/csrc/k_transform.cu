@@ -37,6 +37,7 @@ struct TParams {
   int nz, nm, nk, ldk, N, J, JS, nmg, do_mass_norm, jlo, jhi;
   double gamma, dx, step, kt1, kmax;
   const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab, *rkt;
+  const double* rho;      // user-supplied samples rho[z][m][n] = rho(x_n) (generic_profile_fft with any profile), or NULL
   const int* jn_cta;
   double* uk;
 };
@@ -530,10 +531,12 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       const bool ok = m < p.nm;
       const long long rr = (long long)z * p.nm + (ok ? m : p.nm - 1);
       f_cmax = ok ? p.cmax[rr] : -1.0;
-      f_xc = p.xc[rr];
-      f_alpha = p.alpha[rr];
-      f_expo = p.expo[rr];
-      f_amp = p.amp[rr];
+      if (!p.rho) {
+        f_xc = p.xc[rr];
+        f_alpha = p.alpha[rr];
+        f_expo = p.expo[rr];
+        f_amp = p.amp[rr];
+      }
       f_oscale = p.outscale ? p.outscale[rr] : 1.0;
       f_inv = p.rs[rr] * (1.0 + p.zs[z]) / p.kt1;            // k -> fractional bin index   (fft.py:92)
     }
@@ -578,6 +581,22 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       // thread pair (2i, 2i+1) shares a sample: even lanes evaluate halos 0-7, odd lanes halos 8-15, the eight
       // chains of a thread in lock-step (gnfw_eval.cuh); samples outside a halo's theta-cut are masked afterwards
 #if !(HMV_K1_ABL & 1)
+      if (p.rho) {
+        // samples supplied by the caller (rhofunc_x evaluated elsewhere, fft.py:76-81): x * rho(x) inside the cut
+        for (int sn = gt >> 1; sn < nfill; sn += WS_GT / 2) {
+          const int n = n0 + sn;
+          const double x = (double)(n + 1) * p.dx;
+          const double wx = ((n == 0 || n == p.N - 1) ? 0.5 * p.dx : p.dx) * x;
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) {
+            const int h = hh + hoff;
+            const long long row = (long long)z * p.nm + min(m0 + h, p.nm - 1);
+            const double v = (n < p.N && x <= G.h_cmax[h]) ? x * __ldg(p.rho + row * p.N + n) : 0.0;
+            msum[hh] = fma(wx, v, msum[hh]);
+            gs[ws_gs_index(sn, h)] = v;
+          }
+        }
+      } else
       for (int sn = gt >> 1; sn < nfill; sn += WS_GT / 2) {
         const int n = n0 + sn;
         const double x = (double)(n + 1) * p.dx;
@@ -835,15 +854,15 @@ extern "C" int hmv_set_transform_mode(int mode) {
   return HMV_OK;
 }
 
-extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
-                                     double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
-                                     const double* alpha_d, const double* expo_d, const double* amp_d,
-                                     const double* outscale_d, double gamma, double xmax, int nxs, int do_mass_norm,
-                                     double* ws_d, double* uk_d, void* stream) {
+static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
+                                  double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
+                                  const double* alpha_d, const double* expo_d, const double* amp_d,
+                                  const double* outscale_d, const double* rho_d, double gamma, double xmax, int nxs,
+                                  int do_mass_norm, double* ws_d, double* uk_d, void* stream) {
   HMV_REQUIRE(nz > 0 && nm > 0 && nk > 0 && ldk >= nk, "hmv_profile_transform: bad sizes");
   HMV_REQUIRE(nxs >= 4 && xmax > 0, "hmv_profile_transform: need nxs>=4 and xmax>0");
   HMV_REQUIRE((long long)nxs * (nxs / 2) < 2147483647LL, "hmv_profile_transform: nxs=%d too large (phase index overflow)", nxs);
-  HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && xc_d && alpha_d && expo_d && amp_d && ws_d && uk_d,
+  HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && ws_d && uk_d && (rho_d || (xc_d && alpha_d && expo_d && amp_d)),
               "hmv_profile_transform: null pointer");
   TParams p;
   p.nz = nz; p.nm = nm; p.nk = nk; p.ldk = ldk; p.N = nxs; p.J = nxs / 2; p.JS = p.J + 2;
@@ -855,6 +874,7 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
   p.kmax = kmax;
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
+  p.rho = rho_d;
   int* jn_cta = reinterpret_cast<int*>(ws_d + 2 * (size_t)nxs + 2);
   p.jn_cta = jn_cta;
   double* after_jn = ws_d + 2 * (size_t)nxs + 2 + ((size_t)nz * nm + 1) / 2 + 2;
@@ -879,6 +899,9 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
     if (rc) return rc;
     return launch_transform_ws(p, ring, counter, st);
   }
+  if (rho_d)
+    return fail(HMV_E_LIMIT, "hmv_profile_transform_samples: needs the persistent kernel (16-byte aligned ks/uk/ws, even ldk, "
+                "transform mode 0, nxs < 65536)");
   const size_t budget = 226 * 1024;   // 227 KB opt-in limit minus the static per-halo arrays
   const int J = p.J;
   if (transform_smem<8, NCH_MMA>(J + 2) <= budget) {
@@ -914,4 +937,22 @@ extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const doub
 #undef HMV_ROT
   return fail(HMV_E_LIMIT, "hmv_profile_transform: nxs=%d needs %zu B of shared memory per halo (limit %zu)", nxs,
               transform_smem<1, NCH_ROT>(J + 2), budget);
+}
+
+extern "C" int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
+                                     double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
+                                     const double* alpha_d, const double* expo_d, const double* amp_d,
+                                     const double* outscale_d, double gamma, double xmax, int nxs, int do_mass_norm,
+                                     double* ws_d, double* uk_d, void* stream) {
+  return profile_transform_impl(nz, nm, nk, ldk, zs_d, ks_d, kmax, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, outscale_d,
+                                nullptr, gamma, xmax, nxs, do_mass_norm, ws_d, uk_d, stream);
+}
+
+extern "C" int hmv_profile_transform_samples(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
+                                             double kmax, const double* rs_d, const double* cmax_d,
+                                             const double* rho_d, const double* outscale_d, double xmax, int nxs,
+                                             int do_mass_norm, double* ws_d, double* uk_d, void* stream) {
+  HMV_REQUIRE(rho_d, "hmv_profile_transform_samples: null samples");
+  return profile_transform_impl(nz, nm, nk, ldk, zs_d, ks_d, kmax, rs_d, cmax_d, nullptr, nullptr, nullptr, nullptr,
+                                outscale_d, rho_d, 0.0, xmax, nxs, do_mass_norm, ws_d, uk_d, stream);
 }

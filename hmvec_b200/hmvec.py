@@ -30,18 +30,10 @@ from .params import default_params, battaglia_defaults
 _KIND_MATTER, _KIND_HOD, _KIND_PRESSURE = 0, 1, 2
 
 
-def duffy_concentration(m, z, A=None, alpha=None, beta=None, h=None):
-    """Host helper with the reference's defaults (hmvec.py:68-73); the device path is hmv_halo_geometry."""
-    A = default_params['duffy_A_mean'] if A is None else A
-    alpha = default_params['duffy_alpha_mean'] if alpha is None else alpha
-    beta = default_params['duffy_beta_mean'] if beta is None else beta
-    h = default_params['H0'] / 100. if h is None else h
-    return A * ((h * m / 2.e12) ** alpha) * (1 + z) ** beta
-
-
-def R_from_M(M, rho, delta):
-    """hmvec.py:627-628"""
-    return (3. * M / 4. / np.pi / delta / rho) ** (1. / 3.)
+from .hostfuncs import *  # noqa: F401,F403,E402  (module-level helpers of hmvec.py:627-957)
+from .hostfuncs import R_from_M, duffy_concentration, Fcon  # noqa: F401,E402
+from . import tinker  # noqa: F401,E402  (reference: `from . import tinker,utils`)
+from .fft import generic_profile_fft  # noqa: F401,E402  (hmvec.py:13)
 
 
 class DeviceCubes(MutableMapping):
@@ -57,12 +49,26 @@ class DeviceCubes(MutableMapping):
 
     def __getitem__(self, name):
         t = self._t[name]
-        return t[..., :self._owner._nk].cpu().numpy()
+        o = self._owner
+        if o._ldk == o._nk:
+            return o._host(t)
+        return o._host(t[..., :o._nk].contiguous())
 
     def __setitem__(self, name, value):
         o = self._owner
-        if isinstance(value, torch.Tensor) and value.is_cuda and value.dim() == 3 and value.shape[-1] == o._ldk:
-            self._t[name] = value
+        o._invalidate_spectra()
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+            # zero-copy only for exactly the layout the kernels read: float64, contiguous [nz][nm][ldk], this device,
+            # 16-byte aligned (cp.async.bulk sources); anything else is converted and copied into a fresh cube
+            if (value.dtype == torch.float64 and value.is_contiguous() and tuple(value.shape) == (o._nz, o._nm, o._ldk)
+                    and value.device == o.device and value.data_ptr() % 16 == 0):
+                self._t[name] = value
+                return
+            if tuple(value.shape) not in ((o._nz, o._nm, o._nk), (o._nz, o._nm, o._ldk)):
+                raise ValueError("profile cube must have shape (nz,nm,nk)=%s" % ((o._nz, o._nm, o._nk),))
+            t = o._cube()
+            t[..., :o._nk] = value[..., :o._nk].to(device=o.device, dtype=torch.float64)
+            self._t[name] = t
             return
         arr = torch.as_tensor(np.asarray(value, dtype=np.float64))
         if tuple(arr.shape) != (o._nz, o._nm, o._nk):
@@ -76,6 +82,7 @@ class DeviceCubes(MutableMapping):
         return name in self._t
 
     def __delitem__(self, name):
+        self._owner._invalidate_spectra()
         del self._t[name]
 
     def __iter__(self):
@@ -85,7 +92,79 @@ class DeviceCubes(MutableMapping):
         return len(self._t)
 
 
+def _lazy_host(name, dev_attr):
+    """Public numpy attribute mirrored from a device tensor: downloaded (through pinned memory) on first read,
+    uploaded when assigned.  The reference holds these as plain numpy attributes (hmvec.py:99-131)."""
+
+    def fget(self):
+        c = self._hostc
+        if name not in c:
+            t = getattr(self, dev_attr, None)
+            if t is None:
+                raise AttributeError(name)
+            c[name] = self._host(t)
+        return c[name]
+
+    def fset(self, value):
+        arr = np.array(value, dtype=np.float64)
+        self._hostc[name] = arr
+        setattr(self, dev_attr, self._dev(arr))
+        self._invalidate_spectra()
+
+    return property(fget, fset)
+
+
+class HodRecord(dict):
+    """hods[name] (hmvec.py:452-460): 'Nc','Ns','NsNsm1','NcNs' [nz,nm], 'ngal','bg' [nz], 'log10mthresh' [nz,1] plus
+    the profile names.  The arrays live on the device; each one is downloaded the first time it is read."""
+
+    def __init__(self, owner, dev, **plain):
+        dict.__init__(self, **plain)
+        self._owner, self._dev = owner, dev
+
+    def __missing__(self, key):
+        if key in self._dev:
+            v = self._owner._host(self._dev[key])
+            if key == 'log10mthresh':
+                v = v[:, None]
+            dict.__setitem__(self, key, v)
+            return v
+        raise KeyError(key)
+
+    def _all(self):
+        for k in self._dev:
+            self[k]
+        return self
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._dev
+
+    def keys(self):
+        return dict.keys(self._all())
+
+    def items(self):
+        return dict.items(self._all())
+
+    def values(self):
+        return dict.values(self._all())
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+
 class HaloModel(Cosmology):
+    Pzk = _lazy_host('Pzk', '_Pzk_d')
+    sPzk = _lazy_host('sPzk', '_sPzk_d')
+    sigma2 = _lazy_host('sigma2', '_sigma2_d')
+    nzm = _lazy_host('nzm', '_nzm_d')
+    bh = _lazy_host('bh', '_bh_d')
+
     def __init__(self, zs, ks, ms=None, params={}, mass_function="sheth-torman", halofit=None, mdef='vir',
                  nfw_numeric=False, skip_nfw=False, accuracy='medium', engine='camb', device=None, Pzk=None,
                  sPzk=None, zcomm=None):
@@ -93,11 +172,17 @@ class HaloModel(Cosmology):
         device -- CUDA device (default: current); Pzk [nz,nk], sPzk [nz,sigma2_numks] -- host-supplied linear power
         on `ks` and on the sigma^2 grid (the CAMB products; skips the internal producer); zcomm -- a
         `zshard.ZComm` when `zs` is this rank's slab of a redshift axis sharded over several GPUs."""
+        self._hostc = {}
+        self._six = {}
+        self._ws = {}
         self.zs = np.asarray(zs, dtype=np.float64).reshape(-1)
         self.ks = ks
         self._ks64 = np.asarray(ks, dtype=np.float64).reshape(-1)
+        self._kmax = float(np.max(self._ks64))
         self._Pzk_in, self._sPzk_in = Pzk, sPzk
         self._zcomm = zcomm
+        self._nz, self._nk = self.zs.size, self._ks64.size
+        self._ldk = ((self._nk + 15) // 16) * 16
         Cosmology.__init__(self, params, halofit, accuracy=accuracy, engine=engine, device=device)
         if mdef not in ('vir', 'mean'):
             raise ValueError("mdef must be 'vir' or 'mean'")
@@ -105,12 +190,11 @@ class HaloModel(Cosmology):
         self.mode = mass_function
         self.hods = {}
         self._hod_d = {}
-        self._nz, self._nk = self.zs.size, self._ks64.size
-        self._ldk = ((self._nk + 15) // 16) * 16
         self._zs_d = self._dev(self.zs)
         self._ks_d = self._dev(self._ks64)
-        self._Pzk_d = self._dev(self.Pzk)
         self._rho_m0 = float(np.atleast_1d(self.rho_matter_z(0.))[0])
+        self._hod_stream = None
+        self._ev_mf = self._ev_hod = None
         self.uk_profiles = DeviceCubes(self)
         self.pk_profiles = DeviceCubes(self)
         if ms is not None:
@@ -120,29 +204,46 @@ class HaloModel(Cosmology):
             self.add_nfw_profile("nfw", numeric=nfw_numeric)
 
     # ------------------------------------------------------------------ host-side inputs
+    def _plin_device(self, ks, zs):
+        """accuracy='low': EH98 P(z,k) = D(z)^2 v(k) (cosmology.py:391-402) formed on the device from its two factor
+        vectors -- O(nz)+O(nk) host work, no [nz,nk] array on the host or on PCIe."""
+        d2, v = self.P_lin_approx_factors(ks, zs)
+        out = self._empty(d2.size, v.size)
+        d2_d, v_d = self._dev(d2), self._dev(v)          # named: a temporary's block would be recycled at once
+        capi.check(capi.lib.hmv_outer(d2.size, v.size, capi.ptr(d2_d), capi.ptr(v_d), capi.ptr(out), capi.stream()),
+                   "hmv_outer")
+        return out
+
     def _init_cosmology(self, params, halofit):
         Cosmology._init_cosmology(self, params, halofit)
         if self._Pzk_in is not None:
-            self.Pzk = np.array(self._Pzk_in, dtype=np.float64)
-            if self.Pzk.shape != (self.zs.size, self._ks64.size):
+            P = np.array(self._Pzk_in, dtype=np.float64)
+            if P.shape != (self.zs.size, self._ks64.size):
                 raise ValueError("Pzk must have shape (nz,nk)")
+            self.Pzk = P
         elif self.accuracy == 'low':
-            self.Pzk = self.P_lin_approx(self._ks64, self.zs)               # hmvec.py:98-99
+            self._Pzk_d = self._plin_device(self._ks64, self.zs)             # hmvec.py:98-99
         else:
             self.Pzk = self._get_matter_power(self.zs, self._ks64, nonlinear=False)
         if halofit is not None and self._Pzk_in is None:
             self.nPzk = self._get_matter_power(self.zs, self._ks64, nonlinear=True)
 
     def _sigma2_inputs(self, zs, kmin=None, kmax=None, numks=None):
-        if self._sPzk_in is None:
-            return Cosmology._sigma2_inputs(self, zs, kmin, kmax, numks)
         from .cosmology import simpson_weights
         ks_sigma2 = np.geomspace(self.p['sigma2_kmin'] if kmin is None else kmin,
                                  self.p['sigma2_kmax'] if kmax is None else kmax,
                                  int(self.p['sigma2_numks'] if numks is None else numks))
-        self.sPzk = np.array(self._sPzk_in, dtype=np.float64)
-        if self.sPzk.shape != (np.size(zs), ks_sigma2.size):
-            raise ValueError("sPzk must have shape (nz, sigma2_numks)")
+        same_z = np.size(zs) == self.zs.size and np.array_equal(np.asarray(zs, dtype=np.float64).reshape(-1), self.zs)
+        if self._sPzk_in is not None and same_z:
+            sP = np.array(self._sPzk_in, dtype=np.float64)
+            if sP.shape != (np.size(zs), ks_sigma2.size):
+                raise ValueError("sPzk must have shape (nz, sigma2_numks)")
+            self.sPzk = sP
+        elif self.accuracy == 'low' and same_z:
+            self._hostc.pop('sPzk', None)
+            self._sPzk_d = self._plin_device(ks_sigma2, self.zs)              # cosmology.py:259-260
+        else:
+            return Cosmology._sigma2_inputs(self, zs, kmin, kmax, numks)
         return ks_sigma2, simpson_weights(ks_sigma2) * ks_sigma2 ** 2. / 2. / np.pi ** 2.
 
     def deltav(self, z):
@@ -171,14 +272,25 @@ class HaloModel(Cosmology):
             t[..., self._nk:] = 0.0          # pad columns are read (and ignored) by the 16-byte loads of hmv_power
         return t
 
+    def _workspace(self, kind, ndoubles):
+        """Per-object scratch buffers, allocated once per kind and reused by every later call (all calls of one object
+        are ordered on one stream)."""
+        t = self._ws.get(kind)
+        if t is None or t.numel() < ndoubles:
+            t = self._ws[kind] = self._empty(int(ndoubles))
+        return t
+
     @staticmethod
     def _host(t):
-        """Device tensor -> numpy through a pinned staging buffer (a pageable `.cpu()` runs at ~2 GB/s, pinned at
-        PCIe speed); the returned array owns the pinned buffer."""
+        """Device tensor -> numpy through pinned memory (a pageable `.cpu()` runs at ~2 GB/s, pinned at PCIe speed).
+        The pinned block comes from torch's caching host allocator and is owned by the returned array."""
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return h.numpy()
+
+    def _invalidate_spectra(self):
+        self._six = {}
 
     def _duffy(self):
         tag = 'mean' if self.mdef == 'mean' else 'vir'
@@ -186,44 +298,55 @@ class HaloModel(Cosmology):
 
     # ------------------------------------------------------------------ mass function (K3, K3b, geometry)
     def get_sigma2(self):
-        return self._sigma2_d.cpu().numpy()
+        return self._host(self._sigma2_d)
 
     def init_mass_function(self, ms):
-        """sigma^2 -> n(M,z), b(M,z) and the per-halo geometry, all on the device (hmvec.py:127-185)."""
-        if self.mode != "sheth-torman":
-            raise NotImplementedError("mass_function=%r: only 'sheth-torman' is on the device path" % (self.mode,))
+        """sigma^2 -> n(M,z), b(M,z) and the per-halo geometry, all on the device (hmvec.py:127-185).  The numpy
+        attributes `sigma2`, `nzm`, `bh` are downloaded when first read."""
+        if self.mode not in ("sheth-torman", "tinker"):
+            raise NotImplementedError("mass_function=%r" % (self.mode,))
         self.ms = np.asarray(ms, dtype=np.float64).reshape(-1)
         self._nm = self.ms.size
         self._ms_d = self._dev(self.ms)
+        self._invalidate_spectra()
+        for k in ('sigma2', 'nzm', 'bh'):
+            self._hostc.pop(k, None)
         ks_sig, kw = self._sigma2_inputs(self.zs)
         R = np.asarray(self.R_of_m(self.ms), dtype=np.float64).reshape(-1)
-        self._sigma2_d = self._sigma2_device(self._dev(R), self._dev(self.sPzk), self._dev(ks_sig), self._dev(kw))
+        self._sigma2_d = self._sigma2_device(self._dev(R), self._sPzk_d, self._dev(ks_sig), self._dev(kw))
         self._nzm_d, self._bh_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
         p = self.p
-        capi.check(capi.lib.hmv_mass_function(self._nz, self._nm, capi.ptr(self._sigma2_d), capi.ptr(self._ms_d),
-                                              self._rho_m0, p['st_A'], p['st_a'], p['st_p'], p['st_deltac'],
-                                              capi.ptr(self._nzm_d), capi.ptr(self._bh_d), capi.stream()),
-                   "hmv_mass_function")
+        if self.mode == "tinker":
+            from . import tinker
+            tk = self._dev(tinker.redshift_parameters(self.zs))                # [nz,5], hmvec.py:142-145 -> tinker.py
+            capi.check(capi.lib.hmv_mass_function_tinker(self._nz, self._nm, capi.ptr(self._sigma2_d),
+                                                         capi.ptr(self._ms_d), self._rho_m0, p['st_deltac'],
+                                                         capi.ptr(tk), capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
+                                                         capi.stream()), "hmv_mass_function_tinker")
+        else:
+            capi.check(capi.lib.hmv_mass_function(self._nz, self._nm, capi.ptr(self._sigma2_d), capi.ptr(self._ms_d),
+                                                  self._rho_m0, p['st_A'], p['st_a'], p['st_p'], p['st_deltac'],
+                                                  capi.ptr(self._nzm_d), capi.ptr(self._bh_d), capi.stream()),
+                       "hmv_mass_function")
+        self._ev_mf = torch.cuda.Event()
+        self._ev_mf.record()                                                  # the HOD side stream starts from here
         A, alpha, beta = self._duffy()
         self._drho1_d = self._dev(self._delta_rhos1())
         self._cs_d, self._rvir_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
         capi.check(capi.lib.hmv_halo_geometry(self._nz, self._nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d),
                                               capi.ptr(self._drho1_d), A, alpha, beta, self.h, capi.ptr(self._cs_d),
                                               capi.ptr(self._rvir_d), capi.stream()), "hmv_halo_geometry")
-        self.sigma2 = self._sigma2_d.cpu().numpy()
-        self.nzm = self._nzm_d.cpu().numpy()
-        self.bh = self._bh_d.cpu().numpy()
 
     def get_nzm(self):
-        return self._nzm_d.cpu().numpy()
+        return self._host(self._nzm_d)
 
     def get_bh(self):
-        return self._bh_d.cpu().numpy()
+        return self._host(self._bh_d)
 
     def concentration(self, mode='duffy'):
         if mode != 'duffy':
             raise NotImplementedError
-        return self._cs_d.cpu().numpy()
+        return self._host(self._cs_d)
 
     # ------------------------------------------------------------------ profiles (K0, K1, K2)
     def _m200c_device(self):
@@ -237,10 +360,10 @@ class HaloModel(Cosmology):
 
     def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm):
         out = self._cube()
-        ws = self._empty(int(capi.lib.hmv_profile_transform_ws_doubles(self._nz, self._nm, int(nxs))))
+        ws = self._workspace('transform', capi.lib.hmv_profile_transform_ws_doubles(self._nz, self._nm, int(nxs)))
         capi.check(capi.lib.hmv_profile_transform(
             self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d), capi.ptr(self._ks_d),
-            float(np.max(self._ks64)), capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
+            self._kmax, capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
             capi.ptr(expo_d), capi.ptr(amp_d), capi.ptr(oscale_d), float(gamma), float(xmax), int(nxs),
             int(bool(mass_norm)), capi.ptr(ws), capi.ptr(out), capi.stream()), "hmv_profile_transform")
         return out
@@ -325,9 +448,9 @@ class HaloModel(Cosmology):
             out = self._transform(rs_d, self._cs_d, one, one, 2.0 * one, one, one, -1.0, xmax, nxs, mass_norm=True)
         else:
             out = self._cube()
-            ws = self._empty(int(capi.lib.hmv_uk_nfw_ws_doubles(self._nz, self._nm, self._nk)))
+            ws = self._workspace('nfw', capi.lib.hmv_uk_nfw_ws_doubles(self._nz, self._nm, self._nk))
             capi.check(capi.lib.hmv_uk_nfw(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d),
-                                           capi.ptr(self._ks_d), float(np.max(self._ks64)), capi.ptr(self._cs_d),
+                                           capi.ptr(self._ks_d), self._kmax, capi.ptr(self._cs_d),
                                            capi.ptr(self._rvir_d), capi.ptr(ws), capi.ptr(out), capi.stream()),
                        "hmv_uk_nfw")
         self.uk_profiles[name] = out
@@ -360,32 +483,43 @@ class HaloModel(Cosmology):
         hodp = capi.darr([pp['hod_sig_log_mstellar'], pp['hod_alphasat'], pp['hod_Bsat'], pp['hod_betasat'],
                           pp['hod_Bcut'], pp['hod_betacut'], 0.0, 0.0])
         nz, nm = self._nz, self._nm
+        self._invalidate_spectra()
+        # The HOD solve needs only n(M,z) and b(M,z) and is latency-bound: it runs on a side stream that forks after
+        # the mass function, next to the profile-cube kernels of the main stream, and rejoins in front of the spectra.
+        if self._hod_stream is None:
+            self._hod_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        hs = self._hod_stream
         iters = 0
-        if ngal is not None:
-            ngal = np.asarray(ngal, dtype=np.float64)
-            if ngal.size != nz:
-                raise ValueError("ngal has to be a vector of size self.zs")
-            assert mthresh is None
-            l10_d, iters = self._solve_mthresh(self._dev(ngal.reshape(-1)), hodp, pp)
-            print("Bisection search converged in ", iters, " iterations.")   # utils.py:41
-        else:
-            mthresh = np.asarray(mthresh, dtype=np.float64)
-            if mthresh.size != nz:
-                raise ValueError("mthresh has to be a vector of size self.zs")
-            l10_d = self._dev(np.log10(mthresh.reshape(-1)))
-        d = {k: self._empty(nz, nm) for k in ('Nc', 'Ns', 'NsNsm1', 'NcNs')}
-        d['ngal'], d['bg'] = self._empty(nz), self._empty(nz)
-        capi.check(capi.lib.hmv_hod(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d), capi.ptr(l10_d), hodp,
-                                    0 if corr == "max" else 1, capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
-                                    capi.ptr(d['Nc']), capi.ptr(d['Ns']), capi.ptr(d['NsNsm1']), capi.ptr(d['NcNs']),
-                                    capi.ptr(d['ngal']), capi.ptr(d['bg']), capi.stream()), "hmv_hod")
+        with torch.cuda.stream(hs):
+            hs.wait_event(self._ev_mf)
+            if ngal is not None:
+                ngal = np.asarray(ngal, dtype=np.float64)
+                if ngal.size != nz:
+                    raise ValueError("ngal has to be a vector of size self.zs")
+                assert mthresh is None
+                l10_d, iters = self._solve_mthresh(self._dev(ngal.reshape(-1)), hodp, pp)
+                print("Bisection search converged in ", iters, " iterations.")   # utils.py:41
+            else:
+                mthresh = np.asarray(mthresh, dtype=np.float64)
+                if mthresh.size != nz:
+                    raise ValueError("mthresh has to be a vector of size self.zs")
+                l10_d = self._dev(np.log10(mthresh.reshape(-1)))
+            d = {k: self._empty(nz, nm) for k in ('Nc', 'Ns', 'NsNsm1', 'NcNs')}
+            d['ngal'], d['bg'] = self._empty(nz), self._empty(nz)
+            capi.check(capi.lib.hmv_hod(nz, nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d), capi.ptr(l10_d), hodp,
+                                        0 if corr == "max" else 1, capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
+                                        capi.ptr(d['Nc']), capi.ptr(d['Ns']), capi.ptr(d['NsNsm1']), capi.ptr(d['NcNs']),
+                                        capi.ptr(d['ngal']), capi.ptr(d['bg']), capi.stream()), "hmv_hod")
+            d['log10mthresh'] = l10_d
+            for t in d.values():
+                t.record_stream(main)
+            ev = torch.cuda.Event()
+            ev.record(hs)
+        main.wait_event(ev)                    # later work on the main stream (spectra, downloads) sees the HOD arrays
         self._hod_d[name] = d
-        h = {k: v.cpu().numpy() for k, v in d.items()}
-        h['satellite_profile'] = satellite_profile_name
-        h['central_profile'] = central_profile_name
-        h['log10mthresh'] = l10_d.cpu().numpy()[:, None]
-        h['iterations'] = iters
-        self.hods[name] = h
+        self.hods[name] = HodRecord(self, d, satellite_profile=satellite_profile_name,
+                                    central_profile=central_profile_name, iterations=iters)
 
     def _solve_mthresh(self, target_d, hodp, pp):
         """All-z bisection (utils.py:9-42): every redshift bisects on the device and records, per iteration,
@@ -410,7 +544,7 @@ class HaloModel(Cosmology):
         capi.check(capi.lib.hmv_hod_pick(nz, capi.ptr(ws), C.c_void_p(mask_d.data_ptr()),
                                          float(pp['hod_A_log10mthresh']), capi.ptr(l10_d), capi.ptr(iters_d),
                                          capi.stream()), "hmv_hod_pick")
-        iters = int(iters_d.item())
+        iters = int(iters_d.item())            # waits for the side stream only (mass function + bisection)
         if iters == 0:
             raise capi.HmvError("mthresh<->ngal bisection did not converge within %d iterations"
                                 % capi.HMV_BISECT_MAXIT)
@@ -439,22 +573,22 @@ class HaloModel(Cosmology):
         keep = []
         if kind == _KIND_HOD:
             hod, d = self.hods[name], self._hod_d[name]
-            t.us_d = self.uk_profiles.device(hod['satellite_profile']).data_ptr()
+            t.us_d = capi.ptr(self.uk_profiles.device(hod['satellite_profile'])).value
             cen = hod['central_profile']
-            t.uc_d = self.uk_profiles.device(cen).data_ptr() if cen is not None else None
+            t.uc_d = capi.ptr(self.uk_profiles.device(cen)).value if cen is not None else None
             t.Nc_d, t.Ns_d = d['Nc'].data_ptr(), d['Ns'].data_ptr()
             t.NcNs_d, t.NsNsm1_d = d['NcNs'].data_ptr(), d['NsNsm1'].data_ptr()
             t.ngal_d = d['ngal'].data_ptr()
         elif kind == _KIND_MATTER:
-            t.us_d = self.uk_profiles.device(name).data_ptr()
+            t.us_d = capi.ptr(self.uk_profiles.device(name)).value
         else:
-            t.us_d = self.pk_profiles.device(name).data_ptr()
+            t.us_d = capi.ptr(self.pk_profiles.device(name)).value
         if bias_d is not None:
             t.bias_d = bias_d.data_ptr()
             keep.append(bias_d)
         return t, keep
 
-    def _power(self, name, name2, want1, want2, b1_in=None, b2_in=None, kinds=None, to_host=True):
+    def _power(self, name, name2, want1, want2, b1_in=None, b2_in=None, kinds=None, to_host=True, add=False):
         name2 = name if name2 is None else name2
         kA, kB = kinds
         bA = self._dev(np.asarray(b1_in, dtype=np.float64).reshape(-1)) if b1_in is not None else None
@@ -462,9 +596,14 @@ class HaloModel(Cosmology):
         for b in (bA, bB):
             if b is not None and b.numel() != self._nz:
                 raise ValueError("b1_in/b2_in must have one value per redshift")
+        if bA is None and bB is None:
+            six = self._six_lookup(name, name2, kA, kB)
+            if six is not None:
+                p1, p2 = six
+                return self._power_out(p1 if want1 else None, p2 if want2 else None, to_host, add)
         A, keepA = self._tracer(name, kA, bA)
         B, keepB = self._tracer(name2, kB, bB)
-        ws = self._empty(int(capi.lib.hmv_power_ws_doubles(self._nz, self._nm)))
+        ws = self._workspace('power', capi.lib.hmv_power_ws_doubles(self._nz, self._nm))
         p1 = self._empty(self._nz, self._nk) if want1 else None
         p2 = self._empty(self._nz, self._nk) if want2 else None
         capi.check(capi.lib.hmv_power(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._ms_d),
@@ -472,9 +611,50 @@ class HaloModel(Cosmology):
                                       capi.ptr(self._Pzk_d), self._rho_m0, float(self.p['kstar_damping']),
                                       C.byref(A), C.byref(B), capi.ptr(ws), capi.ptr(p1), capi.ptr(p2),
                                       capi.stream()), "hmv_power")
+        return self._power_out(p1, p2, to_host, add)
+
+    def _power_out(self, p1, p2, to_host, add):
+        if add:                                  # get_power: P1h + P2h formed on the device, one download
+            out = self._empty(self._nz, self._nk)
+            capi.check(capi.lib.hmv_sum2(out.numel(), capi.ptr(p1), capi.ptr(p2), capi.ptr(out), capi.stream()),
+                       "hmv_sum2")
+            return self._host(out) if to_host else out
         if not to_host:
             return p1, p2
-        return (self._host(p1) if want1 else None), (self._host(p2) if want2 else None)
+        return (self._host(p1) if p1 is not None else None), (self._host(p2) if p2 is not None else None)
+
+    # The usual workflow asks for the six auto/cross spectra of (matter, electron, galaxies) one after the other
+    # (README.rst:75-100); each of them alone streams one or two 32 GB cubes.  The first such request runs ONE pass
+    # over the two cubes (hmv_power_six) and keeps the twelve [nz,nk] results on the device; the others are lookups.
+    _SIX = ("mm", "ee", "me", "gg", "gm", "ge")
+
+    def _six_lookup(self, name, name2, kA, kB):
+        if _KIND_PRESSURE in (kA, kB):
+            return None
+        hod = [n for n, k in ((name, kA), (name2, kB)) if k == _KIND_HOD]
+        mat = [n for n, k in ((name, kA), (name2, kB)) if k == _KIND_MATTER]
+        if len(set(hod)) > 1:
+            return None
+        g = hod[0] if hod else next((n for n in reversed(list(self.hods)) if self.hods[n]['central_profile'] is None), None)
+        if g is None or self.hods[g]['central_profile'] is not None:
+            return None
+        m = self.hods[g]['satellite_profile']
+        others = [n for n in mat if n != m]
+        if len(set(others)) > 1:
+            return None
+        e = others[0] if others else next((n for n in reversed(list(self.uk_profiles)) if n != m), None)
+        if e is None:
+            return None
+        tag = "".join("g" if n == g and k == _KIND_HOD else ("m" if n == m else "e") for n, k in ((name, kA), (name2, kB)))
+        tag = {"em": "me", "mg": "gm", "eg": "ge"}.get(tag, tag)
+        if tag not in self._SIX:
+            return None
+        key = (m, e, g)
+        if key not in self._six:
+            self._six = {key: self.get_power_six(m, e, g, to_host=False, stacked=True)}
+        p1, p2 = self._six[key]
+        i = self._SIX.index(tag)
+        return p1[i], p2[i]
 
     # 1-halo looks names up as HOD first (hmvec.py:510-523); 2-halo as matter profile first (hmvec.py:536-550)
     def _kinds_1h(self, name, name2):
@@ -495,24 +675,26 @@ class HaloModel(Cosmology):
         return self._power(name, name2, False, True, b1_in, b2_in, kinds=kinds)[1]
 
     def get_power(self, name, name2=None, verbose=False, b1=None, b2=None):
-        """P1h + P2h (hmvec.py:500-502); one pass over the cubes produces both terms."""
+        """P1h + P2h (hmvec.py:500-502); one pass over the cubes produces both terms, summed on the device."""
         name2 = name if name2 is None else name2
         k1, k2 = self._kinds_1h(name, name2), self._kinds_2h(name, name2)
         if k1 == k2:
-            p1, p2 = self._power(name, name2, True, True, b1, b2, kinds=k1)
-            return p1 + p2
+            if _KIND_PRESSURE in k1:
+                print('Check the consistency relation for tSZ')             # hmvec.py:544
+            return self._power(name, name2, True, True, b1, b2, kinds=k1, add=True)
         return self.get_power_1halo(name, name2) + self.get_power_2halo(name, name2, verbose, b1, b2)
 
-    def get_power_six(self, matter="nfw", electron="electron", hod="g", to_host=True):
+    def get_power_six(self, matter="nfw", electron="electron", hod="g", to_host=True, stacked=False):
         """{mm, ee, me, gg, gm, ge} 1h and 2h spectra in ONE pass over the two cubes (hmv_power_six).
 
         Requires the HOD's satellite profile to be `matter` and its central profile to be None.  Returns
-        (P1h, P2h), each a dict tag -> [nz,nk] (numpy, or CUDA tensors when to_host=False)."""
+        (P1h, P2h), each a dict tag -> [nz,nk] (numpy, or CUDA tensors when to_host=False; stacked=True returns the
+        two [6,nz,nk] device tensors themselves)."""
         h = self.hods[hod]
         if h['satellite_profile'] != matter or h['central_profile'] is not None:
             raise ValueError("get_power_six needs satellite_profile == matter profile and no central profile")
         d = self._hod_d[hod]
-        ws = self._empty(int(capi.lib.hmv_power_ws_doubles(self._nz, self._nm)))
+        ws = self._workspace('power', capi.lib.hmv_power_ws_doubles(self._nz, self._nm))
         p1, p2 = self._empty(6, self._nz, self._nk), self._empty(6, self._nz, self._nk)
         capi.check(capi.lib.hmv_power_six(self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._ms_d),
                                           capi.ptr(self._ks_d), capi.ptr(self._nzm_d), capi.ptr(self._bh_d),
@@ -522,11 +704,49 @@ class HaloModel(Cosmology):
                                           capi.ptr(d['Ns']), capi.ptr(d['NcNs']), capi.ptr(d['NsNsm1']),
                                           capi.ptr(d['ngal']), capi.ptr(ws), 0, capi.ptr(p1), capi.ptr(p2),
                                           capi.stream()), "hmv_power_six")
-        tags = ("mm", "ee", "me", "gg", "gm", "ge")
+        if stacked:
+            return p1, p2
+        tags = self._SIX
         if not to_host:
             return {t: p1[i] for i, t in enumerate(tags)}, {t: p2[i] for i, t in enumerate(tags)}
         h1, h2 = self._host(p1), self._host(p2)
         return {t: h1[i] for i, t in enumerate(tags)}, {t: h2[i] for i, t in enumerate(tags)}
+
+
+    # ------------------------------------------------------------------ cluster-lensing helper
+    def kappa_2h_profiles(self, thetas, Ms, zsource, delta=200, rho='mean', rho_at_z=True, lmin=100, lmax=10000,
+                          verbose=True):
+        """Two-halo convergence profile kappa_2h(theta) of a halo of mass Ms at the lens redshift (hmvec.py:598-622):
+        rho_m b_h / (1+z)^3 / Sigma_cr / D_A^2 * int dl l/(2 pi) J0(l theta) P_lin(k = l/chi), trapezoid over the
+        l = k chi inside (lmin, lmax).  Returns [n_theta, nz].  The reference forms `self.ks*chis`, which only
+        broadcasts for ONE lens redshift (zs of length 1); that case is reproduced exactly, and several lens redshifts
+        are handled one by one with the same expression.  Host-side O(n_theta nk) Hankel sum on [nz,nk] inputs; the
+        bias b_h it interpolates is the device mass function's."""
+        from scipy.special import j0
+        zlens = self.zs
+        Ms = np.broadcast_to(np.asarray(Ms, dtype=np.float64).reshape(-1), (zlens.size,)) if np.size(Ms) in (1, zlens.size) \
+            else np.asarray(Ms, dtype=np.float64).reshape(-1)
+        if Ms.size != zlens.size:
+            raise ValueError("Ms must be a scalar or one mass per lens redshift")
+        sigmac = np.atleast_1d(self.sigma_crit(zlens, zsource))
+        rhomz = np.atleast_1d(self.rho_matter_z(zlens))
+        chis = np.atleast_1d(np.asarray(self.comoving_radial_distance(zlens), dtype=np.float64))
+        DAz = np.atleast_1d(self.angular_diameter_distance(zlens))
+        Pzk, bh = self.Pzk, self.bh
+        bhs = np.array([np.interp(Ms[i], self.ms, bh[i]) for i in range(zlens.size)])
+        if verbose:
+            print("bias ", bhs)
+            print("sigmacr ", sigmac)
+        thetas = np.atleast_1d(np.asarray(thetas, dtype=np.float64))
+        out = np.zeros((thetas.size, zlens.size))
+        for i in range(zlens.size):
+            ells = self._ks64 * chis[i]
+            sel = np.logical_and(ells > lmin, ells < lmax)
+            l = ells[sel]
+            pref = rhomz[i] * bhs[i] / (1 + zlens[i]) ** 3. / sigmac[i] / DAz[i] ** 2
+            for it, theta in enumerate(thetas):
+                out[it, i] = _trapz(pref * Pzk[i, sel] * j0(l * theta) * l / 2. / np.pi, l)
+        return out
 
 
 class LazyCube(object):

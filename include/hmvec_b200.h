@@ -98,6 +98,14 @@ int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, c
                           const double* cmax_d, const double* xc_d, const double* alpha_d, const double* expo_d,
                           const double* amp_d, const double* outscale_d, double gamma, double xmax, int nxs,
                           int do_mass_norm, double* ws_d, double* uk_d, void* stream);
+/* a7 in its general form, generic_profile_fft(rhofunc_x, ...) for ANY radial profile (fft.py:56-94): the samples
+ * rho_d[z][m][n] = rho(x_n), x_n = (n+1) xmax/nxs, are supplied by the caller (the reference evaluates a Python
+ * callable); theta-cut at cmax, mass norm, sine transform, interpolation onto ks exactly as above.  Needs the
+ * persistent kernel (16-byte aligned ks_d / uk_d / ws_d, even ldk); same workspace size. */
+int hmv_profile_transform_samples(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, double kmax,
+                                  const double* rs_d, const double* cmax_d, const double* rho_d,
+                                  const double* outscale_d, double xmax, int nxs, int do_mass_norm, double* ws_d,
+                                  double* uk_d, void* stream);
 
 /* ---- a9: HOD occupations and their mass integrals  (hmvec.py:634-731, 462-466, 936-957) -------------
  * hodp[8] = (sig_log_mstellar, alphasat, Bsat, betasat, Bcut, betacut, Msat_override or <=0, Mcut_override or <=0)
@@ -194,6 +202,13 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
 int hmv_pk_spline(int nz, int nk, const double* zs_d, const double* ks_d, int nx, int ny, int kx, int ky,
                   const double* tx_d, const double* ty_d, const double* c_d, int islog, double scale, double* out_d,
                   void* stream);
+
+/* accuracy='low' linear power (cosmology.py:391-402) is separable, P(z,k) = D(z)^2 * [pref k (k/kp)^(ns-1) T(k)^2]:
+ * out[z][k] = a[z] * b[k] from the two host-side factor vectors, so that neither Pzk [nz,nk] nor the sigma^2 spectrum
+ * [nz,sigma2_numks] crosses PCIe. */
+int hmv_outer(int nz, int nk, const double* a_d, const double* b_d, double* out_d, void* stream);
+/* out = a + b elementwise: P = P1h + P2h of get_power (hmvec.py:500-502) formed on the device before the download. */
+int hmv_sum2(long long n, const double* a_d, const double* b_d, double* out_d, void* stream);
 
 /* ---- test hook: elementwise Si(x), Ci(x) of the device routine used by hmv_uk_nfw (x > 0) -----------*/
 int hmv_sici_test(int n, const double* x_d, double* si_d, double* ci_d, void* stream);

@@ -238,10 +238,39 @@ def st_bias(s2, a=0.707, p=0.3, dc=1.686):
     return 1.0 + (nu2a - 1.0) / dc + (2.0 * p / dc) / (1.0 + nu2a ** p)
 
 
-def mass_function(s2, ms, rho_m0, **st):
+def mass_function(s2, ms, rho_m0, fsigma=None, **st):
     """hmvec.py:178-185: n(M,z) = rho_m0 f(sigma) dln(sigma^-1)/dlnM / M^2 with np.gradient on ln M."""
     g = np.gradient(-0.5 * np.log(s2), np.log(ms), axis=-1)
-    return rho_m0 * st_fsigma(s2, **st) * g / ms[None, :] ** 2
+    f = st_fsigma(s2, **st) if fsigma is None else fsigma
+    return rho_m0 * f * g / ms[None, :] ** 2
+
+
+def tinker_fsigma(s2, zs, alpha_table, dc=1.686):
+    """Tinker et al. 2010 multiplicity nu f(nu) as hmvec.py:142-145 calls tinker.py:43-67: redshifts above 3 are
+    evaluated at 3 (two half-open Heaviside steps: z == 3 exactly maps to 0), f's parameters scale with (1+z), and
+    alpha(z) is linearly interpolated in the reference's table hmvec/data/alpha_consistency.txt
+    (`alpha_table` = its two columns; out-of-range redshifts are an error there and here)."""
+    tz, ta = alpha_table
+    zs = np.asarray(zs, dtype=np.float64)
+    zc = zs * np.heaviside(3 - zs, 0) + 3 * np.heaviside(zs - 3, 0)
+    if np.any(zc < tz[0]) or np.any(zc > tz[-1]):
+        raise ValueError("redshift outside the alpha(z) table")
+    alpha = np.interp(zc, tz, ta)[:, None]
+    beta = (0.589 * (1 + zc) ** 0.20)[:, None]
+    phi = (-0.729 * (1 + zc) ** (-0.08))[:, None]
+    eta = (-0.243 * (1 + zc) ** 0.27)[:, None]
+    gamma = (0.864 * (1 + zc) ** (-0.01))[:, None]
+    nu = dc / np.sqrt(s2)
+    return nu * alpha * (1.0 + (beta * nu) ** (-2.0 * phi)) * nu ** (2 * eta) * np.exp(-gamma * nu ** 2 / 2.0)
+
+
+def tinker_bias(s2, dc=1.686, delta=200.0):
+    """tinker.py:26-40 (eq. 6 of Tinker et al. 2010) at nu = dc/sigma; the exponents use tinker.py's own 1.686."""
+    nu = dc / np.sqrt(s2)
+    y = np.log10(delta)
+    ey = np.exp(-(4.0 / y) ** 4)
+    A, a, C = 1.0 + 0.24 * y * ey, 0.44 * y - 0.88, 0.019 + 0.107 * y + 0.19 * ey
+    return 1.0 - A * nu ** a / (nu ** a + 1.686 ** a) + 0.183 * nu ** 1.5 + C * nu ** 2.4
 
 
 # ----------------------------------------------------------------------------------------------
@@ -602,7 +631,8 @@ class PKOracle(object):
 class OracleHaloModel(object):
     """Mirrors HaloModel(zs,ks,ms,accuracy='low') of hmvec.py:75-572 on top of the functions above."""
 
-    def __init__(self, zs, ks, ms, params=None, mdef="vir", skip_nfw=False, Pzk=None, sPzk=None):
+    def __init__(self, zs, ks, ms, params=None, mdef="vir", skip_nfw=False, Pzk=None, sPzk=None,
+                 mass_function_mode="sheth-torman", alpha_table=None):
         self.zs = np.asarray(zs, dtype=np.float64)
         self.ks = np.asarray(ks, dtype=np.float64)
         self.ms = np.asarray(ms, dtype=np.float64)
@@ -618,8 +648,13 @@ class OracleHaloModel(object):
         R = R_from_M(self.ms, self.rho_m0, 1.0)                                          # hmvec.py:117-118
         self.sigma2 = sigma2(R, self.ks_sig, self.sPzk, self.p["Wkr_taylor_switch"])
         st = dict(A=self.p["st_A"], a=self.p["st_a"], p=self.p["st_p"], dc=self.p["st_deltac"])
-        self.nzm = mass_function(self.sigma2, self.ms, self.rho_m0, **st)
-        self.bh = st_bias(self.sigma2, a=st["a"], p=st["p"], dc=st["dc"])
+        if mass_function_mode == "tinker":                                               # hmvec.py:142-145,157-159
+            f = tinker_fsigma(self.sigma2, self.zs, alpha_table, dc=st["dc"])
+            self.nzm = mass_function(self.sigma2, self.ms, self.rho_m0, fsigma=f)
+            self.bh = tinker_bias(self.sigma2, dc=st["dc"])
+        else:
+            self.nzm = mass_function(self.sigma2, self.ms, self.rho_m0, **st)
+            self.bh = st_bias(self.sigma2, a=st["a"], p=st["p"], dc=st["dc"])
         self.uk_profiles, self.pk_profiles, self.hods = {}, {}, {}
         if not skip_nfw:
             self.add_nfw_profile("nfw")

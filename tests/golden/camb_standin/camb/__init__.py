@@ -64,6 +64,10 @@ class _Background(object):
     def angular_diameter_distance(self, z):
         return self.comoving_radial_distance(z) / (1.0 + np.asarray(z, dtype=np.float64))
 
+    def angular_diameter_distance2(self, z1, z2):
+        # flat background: D_A(z1 -> z2) = (chi(z2) - chi(z1)) / (1 + z2)
+        return (self.comoving_radial_distance(z2) - self.comoving_radial_distance(z1)) / (1.0 + np.asarray(z2, dtype=np.float64))
+
     def get_Omega(self, what):
         return 0.0
 

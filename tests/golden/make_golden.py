@@ -58,6 +58,11 @@ def _import_reference():
     hcosm.interp2d = _Interp2d
     # reference: si.dfitpack.bispeu(tx,ty,c,kx,ky,x,y)[0]  ->  same FITPACK routine, new home
     hcosm.si = types.SimpleNamespace(dfitpack=types.SimpleNamespace(bispeu=_fp.bispeu))
+    # --- tinker.py:64 looks for its table in <package>/../data/; the file ships in <package>/data/.  Redirect the
+    #     one dirname() call it makes so that the reference's own f_nu body runs with the reference's own table.
+    import hmvec.tinker as htinker
+    htinker.os = types.SimpleNamespace(path=types.SimpleNamespace(
+        dirname=lambda f: os.path.join(REF, "hmvec", "data")))
     return hmvec
 
 
@@ -287,7 +292,76 @@ def case_pkspline(hm):
     return out
 
 
-CASES = dict(cky=case_cky, pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
+def case_tinker(hm):
+    """mass_function='tinker' with mdef='mean' (the tSZ notebook's configuration, examples/tSZ example.ipynb cell 4;
+    hmvec.py:142-145,157-159 -> tinker.py:26-67), plus the free functions of tinker.py on fixed arguments."""
+    from hmvec import tinker as rt
+    zs, ms, ks = MINI_ZS, MINI_MS, MINI_KS
+    h = hm.HaloModel(zs, ks, ms=ms, accuracy='low', mass_function='tinker', mdef='mean')
+    out = {}
+    _common(h, out)
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    _hod(h, "g", out)
+    for tag, a, b in (("mm", "nfw", "nfw"), ("gg", "g", "g"), ("gm", "g", "nfw"), ("yy", "y", "y"), ("ym", "y", "nfw")):
+        out["P1h_" + tag] = h.get_power_1halo(a, b)
+        out["P2h_" + tag] = h.get_power_2halo(a, b)
+    nu = np.geomspace(0.2, 6., 23)[None, :] * np.ones((zs.size, 1))
+    out["kat_nu"] = nu
+    out["kat_bias"] = rt.bias(nu)
+    out["kat_f_nu"] = rt.f_nu(nu, zs[:, None])
+    out["kat_f_nu_nonorm"] = rt.f_nu(nu, zs[:, None], norm_consistency=False)
+    out["kat_simple_f_nu"] = rt.simple_f_nu(nu)
+    out["kat_NlnMsub"] = rt.NlnMsub(np.geomspace(1e9, 1e13, 7), np.geomspace(1e12, 1e15, 5))
+    return out
+
+
+def case_hostfuncs(hm):
+    """The free functions of hmvec.py:627-957 on fixed arguments (what `from hmvec import *` hands to user scripts),
+    and kappa_2h_profiles (hmvec.py:598-622) for a single lens redshift, the case its broadcasting supports."""
+    out = {}
+    z = np.array([0.1, 0.8, 0.81, 2.5])
+    lmh = np.log10(np.geomspace(1e10, 1e16, 31))[None, :]
+    thr = np.array([10.2, 10.5, 10.5, 11.0])[:, None]
+    out["z"], out["log10mhalo"], out["thresh"] = z, lmh, thr
+    out["Mhalo_stellar"] = hm.Mhalo_stellar(z[:, None], np.linspace(8., 12., 9)[None, :])
+    out["Mstellar_halo"] = hm.Mstellar_halo(z[:, None], lmh)
+    Nc = hm.avg_Nc(lmh, z[:, None], thr, 0.2)
+    Ns = hm.avg_Ns(lmh, z[:, None], thr, Nc, 0.2, 1.0, 9.04, 0.74, 1.65, 0.59)
+    out["avg_Nc"], out["avg_Ns"] = Nc, Ns
+    out["avg_NsNsm1_max"], out["avg_NsNsm1_min"] = hm.avg_NsNsm1(Nc, Ns, "max"), hm.avg_NsNsm1(Nc, Ns, "min")
+    out["avg_NcNs_max"], out["avg_NcNs_min"] = hm.avg_NcNs(Nc, Ns, "max"), hm.avg_NcNs(Nc, Ns, "min")
+    out["hod_default_mfunc"] = hm.hod_default_mfunc(np.array([11.5, 12.0, 13.0]), 9.04, 0.74)
+    ms = np.geomspace(1e11, 1e15, 9)
+    C1 = hm.duffy_concentration(ms[None, :], z[:, None], 7.85, -0.081, -0.71, 0.673)
+    d1 = np.array([1.2e13, 3e13, 3.1e13, 2e14]); d2 = np.array([2.6e13, 6e13, 6.1e13, 4e14])
+    out["ms"], out["C1"], out["d1"], out["d2"] = ms, C1, d1, d2
+    out["duffy_default"] = hm.duffy_concentration(ms, 0.5)
+    out["mdelta"] = hm.mdelta_from_mdelta(ms, C1, d1, d2)
+    out["mdelta_unvec"] = hm.mdelta_from_mdelta_unvectorized(ms[3], C1[1, 3], d1[1], d2[1])
+    out["R_from_M"] = hm.R_from_M(ms, 3e10, 200.)
+    out["Fcon"] = hm.Fcon(np.array([0.5, 4., 11.]))
+    out["rho_nfw"] = hm.rho_nfw(np.array([0.1, 1., 3.]), 2e15, 0.4)
+    x = np.geomspace(1e-2, 20., 17)
+    m200 = np.array([3e12, 1e14, 2e15])[:, None]
+    out["x"], out["m200"] = x, m200
+    out["battaglia_gas_fit"] = hm.battaglia_gas_fit(m200, 0.7, 4000., 0.29, -0.66)
+    out["rho_gas_generic_x"] = hm.rho_gas_generic_x(x[None, :], m200, 0.7, 0.049, 0.31, 1.5e11)
+    out["rho_gas_SH"] = hm.rho_gas(x[None, :], m200, 0.7, 0.049, 0.31, 1.5e11, profile="SH")
+    out["P_e_generic_x"] = hm.P_e_generic_x(x[None, :], m200, 1.3, 0.7, 0.049, 0.31, 1.5e11)
+    out["P_e"] = hm.P_e(x[None, :], m200, 0.7, 0.049, 0.31, 1.5e11)
+    out["a2z"] = hm.a2z(np.array([0.2, 0.5, 1.0]))
+    # kappa_2h_profiles: one lens redshift
+    zl = np.array([0.45])
+    ks = np.geomspace(1e-3, 50, 400)
+    h = hm.HaloModel(zl, ks, ms=MINI_MS, accuracy='low', skip_nfw=True)
+    thetas = np.geomspace(1e-4, 1e-2, 9)
+    out["k2h_zl"], out["k2h_ks"], out["k2h_thetas"] = zl, ks, thetas
+    out["k2h"] = h.kappa_2h_profiles(thetas, 3e14, 1.1, verbose=False)
+    return out
+
+
+CASES = dict(tinker=case_tinker, hostfuncs=case_hostfuncs, cky=case_cky, pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
 
 if __name__ == "__main__":
     hm = _import_reference()

@@ -236,7 +236,7 @@ def test_errors(hm, mini):
     with pytest.raises(ValueError):
         mini.get_power_1halo("nfw", "doesnotexist")
     with pytest.raises(NotImplementedError):
-        hm.HaloModel(mini.zs, mini.ks, ms=mini.ms, accuracy='low', mass_function="tinker")
+        hm.HaloModel(mini.zs, mini.ks, ms=mini.ms, accuracy='low', mass_function="press-schechter")
     from hmvec_b200 import _capi as capi
     assert capi.lib.hmv_uk_nfw(0, 1, 1, 16, None, None, 1.0, None, None, None, None, None) == -1
     assert "bad sizes" in capi.last_error()

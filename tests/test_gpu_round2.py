@@ -1,0 +1,123 @@
+"""Round-2 additions, GPU side (all through the drop-in API / C ABI):
+Tinker-2010 mass function, generic_profile_fft on caller-supplied samples, device mdelta_from_mdelta,
+kappa_2h_profiles (8f-4), the lazily mirrored attributes and the cached six-spectra pass behind get_power."""
+import numpy as np
+import pytest
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+OSC, HOD_FLOOR = 1e-9, 1e-14
+
+
+@pytest.fixture(scope="module")
+def hm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
+    import hmvec_b200
+    return hmvec_b200
+
+
+def test_tinker_mass_function_and_tsz_config(hm):
+    """mass_function='tinker', mdef='mean' -- the tSZ notebook's configuration -- against the reference's arrays."""
+    g = load_golden("tinker")
+    zs = g["zs"]
+    h = hm.HaloModel(zs, g["ks"], ms=g["ms"], accuracy='low', mass_function='tinker', mdef='mean')
+    assert_close(h.sigma2, g["sigma2"], 1e-9, name="sigma2")
+    assert_close(h.nzm, g["nzm"], 1e-6, name="nzm")
+    assert_close(h.bh, g["bh"], 1e-9, name="bh")
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    h.add_hod("g", mthresh=10 ** 10.5 + zs * 0.)
+    for k in ("Nc", "Ns", "ngal", "bg"):
+        assert_close(h.hods["g"][k], g["hod_g_" + k], 1e-6, HOD_FLOOR, name=k)
+    for tag, a, b in (("mm", "nfw", "nfw"), ("gg", "g", "g"), ("gm", "g", "nfw"), ("yy", "y", "y"), ("ym", "y", "nfw")):
+        assert_close(h.get_power_1halo(a, b), g["P1h_" + tag], 1e-6, name="P1h_" + tag)
+        assert_close(h.get_power_2halo(a, b), g["P2h_" + tag], 1e-6, name="P2h_" + tag)
+    with pytest.raises(ValueError):          # alpha(z) table ends at z = 3... negative z is outside, as in the reference
+        hm.HaloModel(np.array([-0.05, 0.5]), g["ks"], ms=g["ms"], accuracy='low', mass_function='tinker')
+    with pytest.raises(NotImplementedError):
+        hm.HaloModel(zs, g["ks"], ms=g["ms"], accuracy='low', mass_function='press-schechter')
+
+
+def test_generic_profile_fft_any_profile(hm):
+    """generic_profile_fft with a caller-supplied callable (here an Einasto-like profile with per-halo shape) against
+    the oracle's restatement of fft.py:56-115; also the 1-D helpers against the reference's known answer."""
+    from oracle import hmvec_oracle as orc
+    zs = np.array([0.1, 1.0, 2.2])
+    nm = 21                                    # not a multiple of 16: ragged last item
+    rss = np.geomspace(0.02, 1.5, nm)[None, :] * (1 + 0.1 * zs[:, None])
+    cmaxs = np.linspace(3.0, 9.0, nm)[None, :] + zs[:, None]
+    ks = np.geomspace(1e-3, 80., 333)
+    al = np.linspace(0.15, 0.3, nm)[None, :, None]
+    prof = lambda x: np.exp(-2. / al * (x[None, None, :] ** al - 1.)) * (1 + zs[:, None, None])
+    for norm in (True, False):
+        kk, u = hm.generic_profile_fft(prof, cmaxs, rss, zs, ks, 30., 3000, do_mass_norm=norm)
+        want = orc.profile_transform(prof, cmaxs, rss, zs, ks, 30., 3000, mass_norm=norm)
+        assert kk is ks
+        assert_close(u, want, 1e-6, OSC, name="generic_profile_fft norm=%s" % norm)
+    xs = np.linspace(0., 30., 6001)[1:]
+    kt, U = hm.fft_integral(xs, np.exp(-xs ** 2 / 2.))
+    g = load_golden("kat")
+    assert_close(kt, g["gauss_kt"], 1e-13)
+    assert_close(U, g["gauss_U"], 1e-9, 1e-12)
+    assert_close(hm.analytic_fft_integral(kt), g["gauss_analytic"], 1e-13)
+
+
+def test_device_mdelta_and_kappa2h(hm):
+    g = load_golden("hostfuncs")
+    got = hm.mdelta_from_mdelta(g["ms"], g["C1"], g["d1"], g["d2"])
+    assert_close(got, g["mdelta"], 1e-9, name="mdelta_from_mdelta")
+    h = hm.HaloModel(g["k2h_zl"], g["k2h_ks"], ms=np.geomspace(1e11, 1e16, 64), accuracy='low', skip_nfw=True)
+    k2 = h.kappa_2h_profiles(g["k2h_thetas"], 3e14, 1.1, verbose=False)
+    assert_close(k2, g["k2h"], 1e-6, name="kappa_2h_profiles")
+
+
+def test_lazy_mirrors_and_six_cache(hm, golden_mini):
+    g = golden_mini
+    zs = g["zs"]
+    h = hm.HaloModel(zs, g["ks"], ms=g["ms"], accuracy='low')
+    assert not h._hostc                          # nothing has crossed PCIe yet
+    h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+    h.add_hod("g2", ngal=g["g2_ngal_target"])
+    rec = h.hods["g2"]
+    assert set(rec.keys()) >= {"Nc", "Ns", "NsNsm1", "NcNs", "ngal", "bg", "log10mthresh", "satellite_profile",
+                               "central_profile"}
+    assert rec["log10mthresh"].shape == (zs.size, 1) and rec["satellite_profile"] == "nfw"
+    assert_close(rec["ngal"], g["g2_ngal_target"], 2e-4)
+    # six standard pairs: first request runs hmv_power_six once, the rest are lookups; compare with the generic pair kernel
+    pairs = [("nfw", "nfw"), ("electron", "electron"), ("nfw", "electron"), ("g2", "g2"), ("g2", "nfw"), ("electron", "g2")]
+    cached = {p: h.get_power(*p) for p in pairs}
+    assert len(h._six) == 1
+    c1 = h.get_power_1halo("g2", "electron")
+    h._six_lookup = lambda *a: None              # force the generic hmv_power path
+    for p in pairs:
+        assert_close(cached[p], h.get_power(*p), 1e-12, name="six-cache %s x %s" % p)
+    assert_close(c1, h.get_power_1halo("g2", "electron"), 1e-12)
+    assert_close(cached[("g2", "g2")], g["P1h_g2g2"] + g["P2h_g2g2"], 1e-6)
+    assert_close(cached[("electron", "g2")], g["P1h_g2e"] + g["P2h_g2e"], 1e-6)
+    del h._six_lookup
+    # assigning a mirrored attribute uploads it and drops cached spectra
+    P0 = h.get_power("nfw", "nfw")
+    h.Pzk = 2.0 * h.Pzk
+    P1 = h.get_power("nfw", "nfw")
+    p1h = h.get_power_1halo("nfw", "nfw")
+    assert_close(P1 - p1h, 2.0 * (P0 - p1h), 1e-9, 1e-12)
+
+
+def test_device_cubes_validate_user_tensors(hm, golden_mini):
+    """only float64 contiguous [nz,nm,ldk] tensors on the owner's device are aliased; others are copied."""
+    import torch
+    g = golden_mini
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    u = h.uk_profiles.device("nfw")
+    h.uk_profiles["alias"] = u
+    assert h.uk_profiles.device("alias").data_ptr() == u.data_ptr()
+    h.uk_profiles["f32"] = u[..., :h._nk].to(torch.float32)
+    t = h.uk_profiles.device("f32")
+    assert t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == (h._nz, h._nm, h._ldk)
+    assert_close(h.get_power("f32", "f32"), h.get_power("nfw", "nfw"), 1e-5)
+    h.uk_profiles["view"] = u.permute(0, 1, 2)[..., :h._nk]            # non-contiguous slice of the right shape
+    assert_close(h.get_power_1halo("view"), h.get_power_1halo("nfw"), 1e-12)
+    with pytest.raises(ValueError):
+        h.uk_profiles["bad"] = torch.zeros((h._nz, h._nm + 1, h._ldk), dtype=torch.float64, device=u.device)
