@@ -68,6 +68,7 @@ _SIGS = {
     "hmv_power_six_nfw": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll,
                                _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "hmv_pack_sum": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p]),
     "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "hmv_outer": (_i, [_i, _i, _p, _p, _p, _p]),
     "hmv_sum2": (_i, [_ll, _p, _p, _p, _p]),
@@ -117,3 +118,23 @@ def stream():
 
 def darr(vals):
     return (C.c_double * len(vals))(*[float(v) for v in vals])
+
+
+# ---- host<->device copy accounting (bench.py reports the bytes the API moved per step) ----------------------------
+_copied = [0, 0]
+
+
+def count_h2d(nbytes):
+    _copied[0] += int(nbytes)
+
+
+def count_d2h(nbytes):
+    _copied[1] += int(nbytes)
+
+
+def reset_copy_counters():
+    _copied[0] = _copied[1] = 0
+
+
+def copy_counters():
+    return tuple(_copied)

@@ -109,7 +109,9 @@ class Cosmology(object):
         return self._device
 
     def _dev(self, a):
-        return torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=self.device)
+        a = np.array(a, dtype=np.float64, order='C')
+        capi.count_h2d(a.nbytes)
+        return torch.as_tensor(a, device=self.device)
 
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=self.device)
@@ -415,11 +417,20 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
     with np.errstate(all="ignore"):
         pref = hzs * np.array(Wz1s, dtype=np.float64).reshape(-1) * np.array(Wz2s, dtype=np.float64).reshape(-1) / chis ** 2.
     pref = np.broadcast_to(pref, gzs.shape)
-    dev = lambda a: torch.as_tensor(np.array(a, dtype=np.float64, order='C'), device=device)
+    def dev(a):
+        a = np.array(a, dtype=np.float64, order='C')
+        capi.count_h2d(a.nbytes)
+        return torch.as_tensor(a, device=device)
+
     if isinstance(Pzks, torch.Tensor):
         P_d = Pzks.to(device=device, dtype=torch.float64).contiguous()
     else:
-        P_d = dev(Pzks)
+        # the [nz,nk] table: arrays handed out by get_power live in pinned memory and go up at PCIe speed; anything
+        # else is a pageable copy
+        h = torch.from_numpy(np.ascontiguousarray(Pzks, dtype=np.float64))
+        capi.count_h2d(h.numel() * 8)
+        P_d = torch.empty(h.shape, dtype=torch.float64, device=device)
+        P_d.copy_(h, non_blocking=h.is_pinned())
     if P_d.dim() != 2 or P_d.shape[0] != zs.size or P_d.shape[1] != ks.size:
         raise ValueError("Pzks must have shape (zs.size, ks.size)")
     out = torch.empty(ells.size, dtype=torch.float64, device=device)
@@ -428,4 +439,5 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
     capi.check(capi.lib.hmv_limber(ells.size, capi.ptr(ells_d), zs.size, ks.size, ks.size, capi.ptr(zs_d),
                                    capi.ptr(ks_d), capi.ptr(P_d), None, gzs.size, capi.ptr(gzs_d), capi.ptr(pref_d),
                                    capi.ptr(chis_d), capi.ptr(out), capi.stream()), "hmv_limber")
+    capi.count_d2h(out.numel() * 8)
     return out.cpu().numpy()

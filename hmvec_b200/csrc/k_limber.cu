@@ -89,6 +89,17 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ s
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) dst[i] = src[i];
 }
 
+
+// out[z][s][k] = a_s[z][k] + b_s[z][k]: the P = P1h + P2h tables Limber needs, summed and packed z-major so that ONE
+// all-gather over the redshift slabs yields [nz_total][nsp][nk] (each spectrum is then a table of row stride nsp*nk)
+struct PackPtrs { const double* a[4]; const double* b[4]; };
+__global__ void pack_sum_kernel(int nz, int nk, int nsp, PackPtrs q, double* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.y;
+  if (k >= nk) return;
+  const long long i = (long long)z * nk + k;
+  for (int s = 0; s < nsp; ++s) out[((long long)z * nsp + s) * nk + k] = q.a[s][i] + (q.b[s] ? q.b[s][i] : 0.0);
+}
+
 }  // namespace hmv
 using namespace hmv;
 
@@ -101,6 +112,20 @@ extern "C" int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp
   limber_kernel<<<cdiv(nl, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, P_d, P2_d,
                                                                       ngz, gzs_d, pref_d, chis_d, cl_d);
   return check_launch("limber_kernel");
+}
+
+extern "C" int hmv_pack_sum(int nz, int nk, int nsp, const double* const* a_h, const double* const* b_h, double* out_d,
+                            void* stream) {
+  HMV_REQUIRE(nz > 0 && nz <= 65535 && nk > 0 && nsp >= 1 && nsp <= 4 && a_h && out_d, "hmv_pack_sum: bad arguments");
+  PackPtrs q;
+  for (int s = 0; s < 4; ++s) {
+    q.a[s] = s < nsp ? a_h[s] : nullptr;
+    q.b[s] = (s < nsp && b_h) ? b_h[s] : nullptr;
+    HMV_REQUIRE(s >= nsp || q.a[s], "hmv_pack_sum: null table");
+  }
+  dim3 grid(cdiv(nk, 256), nz);
+  pack_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(nz, nk, nsp, q, out_d);
+  return check_launch("pack_sum_kernel");
 }
 
 extern "C" double hmv_bench_dfma(int iters, void* stream) {

@@ -17,6 +17,7 @@ one cube is 32 GB, which is why they are not mirrored eagerly).  There is no CPU
 """
 from collections.abc import MutableMapping
 import ctypes as C
+import weakref
 
 import numpy as np
 import torch
@@ -36,12 +37,24 @@ from . import tinker  # noqa: F401,E402  (reference: `from . import tinker,utils
 from .fft import generic_profile_fft  # noqa: F401,E402  (hmvec.py:13)
 
 
+def pressure_constants(omb, omm):
+    """Constant factors of the Battaglia pressure profile and of its Compton-y normalisation (hmvec.py:313-316,
+    918-927): amp_const = eFrac (omb/omm) 200 G [x m200c rho_c/(2 r200c) P0 on the device],
+    pref = 4 pi sigma_T/(m_e c^2) [x r200c^3 (1+z)^2/H on the device], m_e in solar masses."""
+    XH = .76
+    eFrac = 2.0 * (XH + 1.0) / (5.0 * XH + 3.0)
+    G_newt = constants.G / (default_params['parsec'] * 1e6) ** 3 * default_params['mSun']
+    sigmaT = constants.physical_constants['Thomson cross section'][0]
+    mElect = constants.physical_constants['electron mass'][0] / default_params['mSun']
+    return eFrac * (omb / omm) * 200 * G_newt, 4 * np.pi * (sigmaT / (mElect * constants.c ** 2))
+
+
 class DeviceCubes(MutableMapping):
     """name -> u(z,M,k) cube resident in HBM ([nz][nm][ldk] float64).  Reading an item returns a numpy
     [nz,nm,nk] copy (what reference callers index); assigning a numpy/torch [nz,nm,nk] array uploads it."""
 
     def __init__(self, owner):
-        self._owner = owner
+        self._owner = weakref.proxy(owner) if owner is not None else None    # no reference cycle: dropping the model frees its cubes at once
         self._t = {}
 
     def device(self, name):
@@ -74,6 +87,7 @@ class DeviceCubes(MutableMapping):
         if tuple(arr.shape) != (o._nz, o._nm, o._nk):
             raise ValueError("profile cube must have shape (nz,nm,nk)=%s" % ((o._nz, o._nm, o._nk),))
         t = o._cube()
+        capi.count_h2d(arr.numel() * 8)
         t[..., :o._nk] = arr.to(o.device)
         self._t[name] = t
 
@@ -120,7 +134,7 @@ class HodRecord(dict):
 
     def __init__(self, owner, dev, **plain):
         dict.__init__(self, **plain)
-        self._owner, self._dev = owner, dev
+        self._owner, self._dev = weakref.proxy(owner), dev
 
     def __missing__(self, key):
         if key in self._dev:
@@ -286,6 +300,7 @@ class HaloModel(Cosmology):
         The pinned block comes from torch's caching host allocator and is owned by the returned array."""
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t, non_blocking=True)
+        capi.count_d2h(h.numel() * h.element_size())
         torch.cuda.current_stream().synchronize()
         return h.numpy()
 
@@ -422,14 +437,7 @@ class HaloModel(Cosmology):
                 if key in ('battaglia_pres_gamma', 'battaglia_pres_alpha') or key in battaglia_defaults[family]:
                     pparams[key] = param_override[key]
         fit9 = [pparams[q + s] for q in ('P0', 'xc', 'beta') for s in ('_A0', '_alpham', '_alphaz')]
-        XH = .76
-        eFrac = 2.0 * (XH + 1.0) / (5.0 * XH + 3.0)                         # hmvec.py:918-920
-        omb = self.p['ombh2'] / self.h ** 2.
-        G_newt = constants.G / (default_params['parsec'] * 1e6) ** 3 * default_params['mSun']
-        amp_const = eFrac * (omb / self.omm0) * 200 * G_newt                # x m200c rho_c /(2 r200c) P0 on device
-        sigmaT = constants.physical_constants['Thomson cross section'][0]
-        mElect = constants.physical_constants['electron mass'][0] / default_params['mSun']
-        pref = 4 * np.pi * (sigmaT / (mElect * constants.c ** 2))           # x r200c^3 (1+z)^2/H on device (:316)
+        amp_const, pref = pressure_constants(self.p['ombh2'] / self.h ** 2., self.omm0)
         self.pk_profiles[name] = self._gnfw(1, fit9, pparams['battaglia_pres_gamma'],
                                             pparams['battaglia_pres_alpha'], amp_const, pref, xmax, nxs)
 

@@ -1,11 +1,11 @@
 """GridSix: the whole hot path for one z-slab as a stream-ordered, allocation-free launch sequence.
 
     sigma^2 -> n(M,z), b(M,z) -> halo geometry -> u_NFW cube -> M200c, GNFW parameters -> u_electron cube ->
-    HOD (mthresh<->ngal bisection + occupations) -> {mm,ee,me,gg,gm,ge} 1h+2h spectra -> [all-gather over z] ->
-    Limber C_kk, C_kg
+    Compton-y pressure cube -> HOD (mthresh<->ngal bisection + occupations) -> {mm,ee,me,gg,gm,ge} 1h+2h spectra ->
+    yy 1h+2h spectrum -> [all-gather over z] -> Limber C_kk, C_kg, C_yy
 
-This is what `HaloModel(...)`, `add_battaglia_profile`, `add_hod(ngal=...)`, six `get_power` calls and
-`C_kk`/`C_kg` do in the reference (hmvec.py:76-572, cosmology.py:536-568,867-904), arranged B200-first: every buffer
+This is what `HaloModel(...)`, `add_battaglia_profile`, `add_battaglia_pres_profile`, `add_hod(ngal=...)`, seven
+`get_power` calls and `C_kk`/`C_kg`/`C_yy` do in the reference (hmvec.py:76-572, cosmology.py:536-568,867-904), arranged B200-first: every buffer
 (two [nz][nm][ldk] cubes, ~20 [nz,nm] arrays, workspaces, outputs) is allocated once in __init__, `run()` only issues
 kernel launches through the C ABI on the current stream with no host synchronisation, host inputs arrive through
 pinned staging buffers (`upload`) and results leave through pinned buffers (`download`).  Host-side inputs (the CAMB
@@ -21,6 +21,7 @@ from .cosmology import Cosmology, simpson_weights
 from .params import default_params, battaglia_defaults
 
 TAGS = ("mm", "ee", "me", "gg", "gm", "ge")
+_KIND_PRESSURE = 2
 
 # host inputs that change with the cosmology / redshift slab (uploaded every e2e step), name -> shape key
 _PER_STEP = ("Pzk", "sPzk", "drho1", "drho2", "rhocrit", "hofz", "ngal_target")
@@ -33,10 +34,7 @@ def make_inputs(zs, ms, ks, params=None, mdef='vir', ngal=None, ells=None, lzs=2
     zs = np.asarray(zs, dtype=np.float64).reshape(-1)
     ms = np.asarray(ms, dtype=np.float64).reshape(-1)
     ks = np.asarray(ks, dtype=np.float64).reshape(-1)
-    import warnings
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        c = Cosmology(dict(params or {}), accuracy=accuracy)
+    c = Cosmology(dict(params or {}), accuracy=accuracy)
     p = c.p
     ks_sig = np.geomspace(p['sigma2_kmin'], p['sigma2_kmax'], int(p['sigma2_numks']))
     rho_m0 = float(np.atleast_1d(c.rho_matter_z(0.))[0])
@@ -67,6 +65,8 @@ def make_inputs(zs, ms, ks, params=None, mdef='vir', ngal=None, ells=None, lzs=2
             inp["gz"] = np.array([gz])
             inp["chig"] = chig
             inp["pref_kg"] = c.h_of_z(np.array([gz])) * c.lensing_window(np.array([gz]), lzs) / chig ** 2.
+            inp["pref_yy"] = inp["hofz"] / chis ** 2.                         # cosmology.py:591-597: both windows 1
+    inp["omm0"] = c.omm0
     return inp
 
 
@@ -79,10 +79,10 @@ def slab_inputs(inp, sl):
 
 
 class GridSix(object):
-    STAGES = ("sigma2", "massfn", "uk_nfw", "uk_electron", "hod", "power_six", "limber")
+    STAGES = ("sigma2", "massfn", "uk_nfw", "uk_electron", "uk_pressure", "hod", "power_six", "power_yy", "limber")
 
     def __init__(self, inp, device=None, zcomm=None, family="AGN", xmax=None, nxs=None, nz_total_zs=None,
-                 fused_nfw=False):
+                 fused_nfw=False, tsz=True):
         """inp: this rank's slab of `make_inputs` (see slab_inputs).  zcomm: zshard.ZComm for a sharded z axis;
         nz_total_zs: the full redshift vector (needed for Limber after the all-gather).  fused_nfw: spectra-only
         variant -- the NFW profile is evaluated inside the mass reduction (hmv_power_six_nfw), its cube is never
@@ -106,6 +106,14 @@ class GridSix(object):
         fam = battaglia_defaults[family]
         self.gamma = float(p['battaglia_gas_gamma'])
         self.fit9 = capi.darr([fam[q + s] for q in ('rho0', 'alpha', 'beta') for s in ('_A0', '_alpham', '_alphaz')])
+        # tSZ leg (BASELINE.json configs[4]): Battaglia-2012 pressure profile -> P_yy -> C_yy
+        self.tsz = bool(tsz)
+        pf = battaglia_defaults[p['battaglia_pres_family']]
+        self.pfit9 = capi.darr([pf[q + s] for q in ('P0', 'xc', 'beta') for s in ('_A0', '_alpham', '_alphaz')])
+        from .hmvec import pressure_constants
+        self.p_amp, self.p_pref = pressure_constants(p['ombh2'] / inp["h"] ** 2., inp["omm0"])
+        self.p_xmax = float(p['electron_pressure_profile_integral_xmax'])
+        self.p_nxs = int(p['electron_pressure_profile_integral_numxs'])
         self.hodp = capi.darr([p['hod_sig_log_mstellar'], p['hod_alphasat'], p['hod_Bsat'], p['hod_betasat'],
                                p['hod_Bcut'], p['hod_betacut'], 0.0, 0.0])
         f64 = dict(dtype=torch.float64, device=self.device)
@@ -125,7 +133,7 @@ class GridSix(object):
         self.d["ngal"], self.d["bg"], self.d["l10"] = E(nz), E(nz), E(nz)
         self.d["sig_ws"] = E(int(capi.lib.hmv_sigma2_ws_doubles(nz, nm, self.nks)))
         self.d["nfw_ws"] = E(int(capi.lib.hmv_uk_nfw_ws_doubles(nz, nm, nk)))
-        self.d["tr_ws"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(nz, nm, self.nxs)))
+        self.d["tr_ws"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(nz, nm, max(self.nxs, self.p_nxs if self.tsz else 0))))
         self.d["pow_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
         self.d["bis_ws"] = E(nz * (capi.HMV_BISECT_MAXIT + 4))
         self.mask = torch.empty(1, dtype=torch.int64, device=self.device)
@@ -140,34 +148,50 @@ class GridSix(object):
                 self.um[..., nk:] = 0.0
         if self.fused_nfw:
             self.d["pow_ws"] = E(int(capi.lib.hmv_power_six_nfw_ws_doubles(nz, nm)))
-        self.p1 = E(6, nz, nk)
-        self.p2 = E(6, nz, nk)
-        self.h_p1 = torch.empty((6, nz, nk), dtype=torch.float64).pin_memory()
-        self.h_p2 = torch.empty((6, nz, nk), dtype=torch.float64).pin_memory()
+        # spectra: rows 0-5 = TAGS, row 6 = yy (Compton-y auto spectrum) when the tSZ leg is on
+        self.nsp = 7 if self.tsz else 6
+        self.p1 = E(self.nsp, nz, nk)
+        self.p2 = E(self.nsp, nz, nk)
+        self.h_p1 = torch.empty((self.nsp, nz, nk), dtype=torch.float64).pin_memory()
+        self.h_p2 = torch.empty((self.nsp, nz, nk), dtype=torch.float64).pin_memory()
+        if self.tsz:
+            self.uy = torch.empty((nz, nm, self.ldk), **f64)
+            if self.ldk > nk:
+                self.uy[..., nk:] = 0.0
+            for k in ("y_rs", "y_cmax", "y_xc", "y_alpha", "y_expo", "y_amp", "y_oscale"):
+                self.d[k] = E(nz, nm)
+            self.d["pair_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
+            self.ty = capi.Tracer()
+            self.ty.kind = _KIND_PRESSURE
+            self.ty.us_d = self.uy.data_ptr()
         # Limber (replicated on every rank after the all-gather)
         self.has_limber = "ells" in inp
         if self.has_limber:
             self.zs_all = torch.as_tensor(np.array(inp["zs"] if nz_total_zs is None else nz_total_zs, dtype=np.float64),
                                           device=self.device)
             self.nl = inp["ells"].size
-            for k in ("ells", "chis", "pref_kk", "gz", "chig", "pref_kg"):
+            for k in ("ells", "chis", "pref_kk", "gz", "chig", "pref_kg", "pref_yy"):
                 self.d[k] = torch.as_tensor(np.array(inp[k], dtype=np.float64), device=self.device)
-            self.cl = E(2, self.nl)
-            self.h_cl = torch.empty((2, self.nl), dtype=torch.float64).pin_memory()
+            self.ncl = 3 if self.tsz else 2
+            self.cl = E(self.ncl, self.nl)
+            self.h_cl = torch.empty((self.ncl, self.nl), dtype=torch.float64).pin_memory()
         self.launches_per_run = 0
         self.transform_mode = 0
         self._ev = None
         self._Pfull = None
         self._Ppack = None
-        # the download (192 MB on the full grid) takes about as long as the reduction: start it early, end it small --
-        # but keep >= 20 redshifts (400 CTAs, 2.7 waves) per reduction launch
-        self.d2h_chunks = int(min(10, max(1, self.nz // 20)))
+        # the download (224 MB on the full grid) takes about as long as the reduction: start it early, end it small.
+        # >= 12 redshifts per reduction launch: a 25-z slab (8 GPUs) still runs as two launches of ~1.7 waves each --
+        # the same four wave-times as one launch of 3.4 -- and the first half's copy hides behind the second half
+        self.d2h_chunks = int(min(10, max(1, self.nz // 12)))
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ev_chunk = [torch.cuda.Event() for _ in range(self.d2h_chunks)]
         self.ev_pzk = torch.cuda.Event()
+        self.ev_yy = torch.cuda.Event()
         self.hod_stream = torch.cuda.Stream(device=self.device)
         self.ev_mf, self.ev_hod = torch.cuda.Event(), torch.cuda.Event()
         self.hod_overlap = True
+        self.h_iters = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     # ------------------------------------------------------------------ host <-> device
     def h2d_bytes(self):
@@ -191,15 +215,24 @@ class GridSix(object):
     def download(self):
         self.h_p1.copy_(self.p1, non_blocking=True)
         self.h_p2.copy_(self.p2, non_blocking=True)
+        self.h_iters.copy_(self.iters, non_blocking=True)
         if self.has_limber:
             self.h_cl.copy_(self.cl, non_blocking=True)
 
+    def _check_converged(self):
+        """hmv_hod_pick reports 0 iterations when the all-z bisection never met rtol (target outside the mthresh
+        bracket, NaN n(M)); spectra built on that midpoint are meaningless, so this is an error as in HaloModel."""
+        if int(self.h_iters[0]) == 0:
+            raise capi.HmvError("mthresh<->ngal bisection did not converge within %d iterations" % capi.HMV_BISECT_MAXIT)
+
     def finish_e2e(self):
         """After run(overlap_d2h=True): copy the C_ell and wait until every result is in the pinned host buffers."""
+        self.h_iters.copy_(self.iters, non_blocking=True)
         if self.has_limber:
             self.h_cl.copy_(self.cl, non_blocking=True)
         self.copy_stream.synchronize()
         torch.cuda.current_stream().synchronize()
+        self._check_converged()
 
     # ------------------------------------------------------------------ the launch sequence
     def _mark(self, i):
@@ -247,10 +280,25 @@ class GridSix(object):
         # mdelta, gnfw_params, sine_table, bin_count + one persistent kernel (or the four bin-count classes)
         n += 5 if self.transform_mode == 0 else 8
         self._mark(4)
+        if self.tsz:
+            # Compton-y profile (hmvec.py:252-316): pressure GNFW, no mass norm, scaled by 4 pi sigma_T/(m_e c^2)
+            # r200c^3 (1+z)^2/H -- the second invocation of the transform kernel
+            capi.check(L.hmv_gnfw_params(1, nz, nm, ptr(d["zs"]), ptr(d["m200c"]), ptr(d["rvir"]), ptr(d["rhocrit"]),
+                                         ptr(d["hofz"]), self.pfit9, float(p['battaglia_pres_gamma']),
+                                         float(p['battaglia_pres_alpha']), self.p_amp, self.p_pref, ptr(d["y_rs"]),
+                                         ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                         ptr(d["y_amp"]), ptr(d["y_oscale"]), st), "hmv_gnfw_params(pressure)")
+            capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
+                                               ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                               ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
+                                               self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.uy), st),
+                       "hmv_profile_transform(pressure)")
+            n += 4 if self.transform_mode == 0 else 7
+        self._mark(5)
         if not self.hod_overlap:
             self._hod_stage(torch.cuda.current_stream())
         n += 6
-        self._mark(5)
+        self._mark(6)
         # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
         torch.cuda.current_stream().wait_event(self.ev_pzk)            # Pzk of this step has arrived (see upload)
         if self.hod_overlap:
@@ -288,10 +336,24 @@ class GridSix(object):
                     for q in range(6):       # one contiguous [z1-z0, nk] block per spectrum: plain async memcpys
                         self.h_p1[q, z0:z1].copy_(self.p1[q, z0:z1], non_blocking=True)
                         self.h_p2[q, z0:z1].copy_(self.p2[q, z0:z1], non_blocking=True)
-        self._mark(6)
+        self._mark(7)
+        if self.tsz:
+            # P_yy 1h+2h (hmvec.py:512-514, 541-545: pressure tracers, b = 0, no consistency terms)
+            capi.check(L.hmv_power(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                   ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), C.byref(self.ty),
+                                   C.byref(self.ty), ptr(d["pair_ws"]), ptr(self.p1[6]), ptr(self.p2[6]), st),
+                       "hmv_power(yy)")
+            n += 2
+            if overlap_d2h:
+                self.ev_yy.record()
+                self.copy_stream.wait_event(self.ev_yy)
+                with torch.cuda.stream(self.copy_stream):
+                    self.h_p1[6].copy_(self.p1[6], non_blocking=True)
+                    self.h_p2[6].copy_(self.p2[6], non_blocking=True)
+        self._mark(8)
         if self.has_limber:
             n += self._limber(st)
-        self._mark(7)
+        self._mark(9)
         self.launches_per_run = n
         self._ev = None
 
@@ -321,48 +383,50 @@ class GridSix(object):
             self.ev_hod.record(hs)
 
     def _limber(self, st):
-        """P = P1h + P2h for mm and gm, all-gathered over z when sharded, then C_kk and C_kg (cosmology.py:536-568)."""
+        """P = P1h + P2h of mm, gm (and yy) summed and packed z-major by one kernel, all-gathered over z when sharded
+        (ONE collective), then C_kk, C_kg (and C_yy) (cosmology.py:536-597)."""
         L, d, ptr = capi.lib, self.d, capi.ptr
-        nk = self.nk
-        if self.zcomm is not None and getattr(self.zcomm, "nz_total", -1) == getattr(self.zcomm, "world", 0) * self.nz:
-            # ONE all-gather: the four [nz_local,nk] slabs Limber needs (P1h, P2h of mm and gm) are packed z-major as
-            # [nz_local][4][nk]; rank order is z order, so the gathered buffer is [nz_total][4][nk] and each spectrum is
-            # a table with row stride 4 nk (hmv_limber's ldp)
+        nk, nq = self.nk, self.ncl
+        rows = (0, 4, 6)[:nq]                                # mm, gm, yy in self.p1 / self.p2
+        if self._Ppack is None:
+            self._Ppack = torch.empty((self.nz, nq, nk), dtype=torch.float64, device=self.device)
+            self._pa = (C.c_void_p * nq)(*[self.p1[r].data_ptr() for r in rows])
+            self._pb = (C.c_void_p * nq)(*[self.p2[r].data_ptr() for r in rows])
+        capi.check(L.hmv_pack_sum(self.nz, nk, nq, self._pa, self._pb, ptr(self._Ppack), st), "hmv_pack_sum")
+        full = self._Ppack
+        if self.zcomm is not None:
+            # rank order is z order, so the gathered buffer is [nz_total][nq][nk]: each spectrum is a table with row
+            # stride nq*nk (hmv_limber's ldp)
             if self._Pfull is None:
-                self._Ppack = torch.empty((self.nz, 4, nk), dtype=torch.float64, device=self.device)
-                self._Pfull = torch.empty((self.zs_all.numel(), 4, nk), dtype=torch.float64, device=self.device)
-            torch.stack((self.p1[0], self.p2[0], self.p1[4], self.p2[4]), dim=1, out=self._Ppack)
-            self.zcomm.all_gather_rows(self._Ppack.view(self.nz, 4 * nk), self._Pfull.view(-1, 4 * nk))
-            base, ldp = self._Pfull.data_ptr(), 4 * nk
-            mm1, mm2, gm1, gm2 = (C.c_void_p(base + 8 * q * nk) for q in range(4))
-            nzt = self._Pfull.shape[0]
-        else:
-            if self.zcomm is not None:          # unequal slabs: one all-gather per spectrum into [4, nz_total, nk]
-                if self._Pfull is None:
-                    self._Pfull = torch.empty((4, self.zs_all.numel(), nk), dtype=torch.float64, device=self.device)
-                for i, src in enumerate((self.p1[0], self.p2[0], self.p1[4], self.p2[4])):
-                    self.zcomm.all_gather_rows(src, self._Pfull[i])
-                t = [self._Pfull[i] for i in range(4)]
-            else:
-                t = [self.p1[0], self.p2[0], self.p1[4], self.p2[4]]
-            mm1, mm2, gm1, gm2 = (ptr(x) for x in t)
-            nzt, ldp = t[0].shape[0], nk
+                self._Pfull = torch.empty((self.zs_all.numel(), nq, nk), dtype=torch.float64, device=self.device)
+            self.zcomm.all_gather_rows(self._Ppack.view(self.nz, nq * nk), self._Pfull.view(-1, nq * nk))
+            full = self._Pfull
+        base, ldp, nzt = full.data_ptr(), nq * nk, full.shape[0]
+        tab = [C.c_void_p(base + 8 * q * nk) for q in range(nq)]
         capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
-                                mm1, mm2, nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
+                                tab[0], None, nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
                                 ptr(self.cl[0]), st), "hmv_limber(kk)")
         capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
-                                gm1, gm2, 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
+                                tab[1], None, 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
                                 st), "hmv_limber(kg)")
-        return 2
+        if nq > 2:
+            capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
+                                    tab[2], None, nzt, ptr(self.zs_all), ptr(d["pref_yy"]), ptr(d["chis"]),
+                                    ptr(self.cl[2]), st), "hmv_limber(yy)")
+        return 1 + nq
 
     def spectra(self):
-        """Download and return ({tag: P1h}, {tag: P2h}, C_kk, C_kg) as numpy (synchronises)."""
+        """Download and return ({tag: P1h}, {tag: P2h}, C_kk, C_kg) as numpy (synchronises); with the tSZ leg the
+        dicts also hold 'yy' and `self.last_cyy` is C_yy."""
         self.download()
         torch.cuda.current_stream().synchronize()
+        self._check_converged()
         p1, p2 = self.h_p1.numpy().copy(), self.h_p2.numpy().copy()
-        out1 = {t: p1[i] for i, t in enumerate(TAGS)}
-        out2 = {t: p2[i] for i, t in enumerate(TAGS)}
+        tags = TAGS + (("yy",) if self.tsz else ())
+        out1 = {t: p1[i] for i, t in enumerate(tags)}
+        out2 = {t: p2[i] for i, t in enumerate(tags)}
         if self.has_limber:
             cl = self.h_cl.numpy().copy()
+            self.last_cyy = cl[2] if self.tsz else None
             return out1, out2, cl[0], cl[1]
         return out1, out2, None, None

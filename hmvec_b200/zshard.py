@@ -60,6 +60,24 @@ class ZComm(object):
             out.copy_(self.all_gather_z(local))
         return out
 
+    def all_gather_host(self, local):
+        """numpy [nz_local, n] slab -> numpy [nz_total, n] on every rank (what a user of the drop-in API does with the
+        per-rank get_power results before the Limber integral): upload, one all-gather over NVLink, download."""
+        from . import _capi as capi
+        h = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+        t = h.to(dev, non_blocking=h.is_pinned()) if dev.type == "cuda" else h
+        out = torch.empty((self.nz_total, t.shape[1]), dtype=torch.float64, device=dev)
+        self.all_gather_rows(t, out)
+        if dev.type != "cuda":
+            return out.numpy()
+        capi.count_h2d(h.numel() * 8)
+        capi.count_d2h(out.numel() * 8)
+        res = torch.empty(out.shape, dtype=torch.float64, pin_memory=True)
+        res.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res.numpy()
+
     def all_gather_z(self, local):
         """local: [..., nz_local, n] slab (z is dim -2) -> [..., nz_total, n] on every rank."""
         if local.shape[-2] != self.nz_local:

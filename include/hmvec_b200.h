@@ -193,6 +193,13 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
                const double* P_d, const double* P2_d, int ngz, const double* gzs_d, const double* pref_d,
                const double* chis_d, double* cl_d, void* stream);
 
+/* Sum-and-pack in front of the one all-gather of a z-sharded run: out_d[z][s][k] = a_s[z][k] + b_s[z][k] for up to
+ * four spectra (P1h + P2h of C_kk's P_mm, C_kg's P_gm, C_yy's P_yy, cosmology.py:536-597).  a_h / b_h: HOST arrays of
+ * nsp device pointers to [nz][nk] tables (b_h or any b_h[s] may be NULL).  After all_gather the table of spectrum s is
+ * out + s*nk with row stride ldp = nsp*nk for hmv_limber. */
+int hmv_pack_sum(int nz, int nk, int nsp, const double* const* a_h, const double* const* b_h, double* out_d,
+                 void* stream);
+
 /* ---- next row: P(z,k) from a matter-power interpolator  (cosmology.py:227-229, 353-382;
  *      utils.py:95-103 `PKInterpolator.P`; CAMB get_matter_power_interpolator) -------------------------------
  * out[z][k] = scale * (islog ? exp(s) : s),  s = the tensor-product B-spline (knots tx[nx], ty[ny], degrees kx, ky,

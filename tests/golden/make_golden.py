@@ -35,35 +35,11 @@ warnings.filterwarnings("ignore")
 
 
 def _import_reference():
-    try:
-        import camb  # noqa: F401
-        raise SystemExit("a real camb is installed; the stand-in must not shadow it")
-    except ImportError:
-        pass
-    sys.path.insert(0, os.path.join(HERE, "camb_standin"))
-    sys.path.insert(0, REF)
-    # --- shims for SciPy>=1.14 (see module docstring) -------------------------------------
-    import hmvec  # noqa
-    import hmvec.cosmology as hcosm
-    import scipy.interpolate._fitpack as _fp
-    from scipy.interpolate import RectBivariateSpline
-
-    class _Interp2d(object):
-        """interp2d(ks, zs, Pzks[nz,nk]) for a regular grid == FITPACK regrid with kx=ky=1, s=0."""
-
-        def __init__(self, x, y, z, bounds_error=False, **kw):
-            tx, ty, c = RectBivariateSpline(np.asarray(x), np.asarray(y), np.asarray(z).T, kx=1, ky=1, s=0).tck
-            self.tck = (tx, ty, c, 1, 1)
-
-    hcosm.interp2d = _Interp2d
-    # reference: si.dfitpack.bispeu(tx,ty,c,kx,ky,x,y)[0]  ->  same FITPACK routine, new home
-    hcosm.si = types.SimpleNamespace(dfitpack=types.SimpleNamespace(bispeu=_fp.bispeu))
-    # --- tinker.py:64 looks for its table in <package>/../data/; the file ships in <package>/data/.  Redirect the
-    #     one dirname() call it makes so that the reference's own f_nu body runs with the reference's own table.
-    import hmvec.tinker as htinker
-    htinker.os = types.SimpleNamespace(path=types.SimpleNamespace(
-        dirname=lambda f: os.path.join(REF, "hmvec", "data")))
-    return hmvec
+    """The unmodified reference at /root/reference with the camb stand-in and the SciPy / data-path shims
+    (oracle/ref_loader.py documents each one)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ref_loader
+    return ref_loader.load(REF)
 
 
 def _meta():

@@ -41,6 +41,9 @@ def test_gridsix_matches_golden_and_halomodel(setup, fused):
         assert_close(p1[tag], g["P1h_" + gold], 1e-6, name="P1h_" + tag)
         assert_close(p2[tag], g["P2h_" + gold], 1e-6, name="P2h_" + tag)
     assert_close(ckk, g["C_kk"], 1e-6, name="C_kk")
+    assert_close(p1["yy"], g["P1h_yy"], 1e-6, name="P1h_yy")
+    assert_close(p2["yy"], g["P2h_yy"], 1e-6, name="P2h_yy")
+    assert_close(gs.last_cyy, g["C_yy"], 1e-6, name="C_yy")
     assert int(gs.iters.item()) > 1
     import hmvec_b200 as hm
     h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
@@ -56,6 +59,15 @@ def test_gridsix_matches_golden_and_halomodel(setup, fused):
         assert_close(gs.h_p1[i].numpy(), p1[tag], 0, name="e2e P1h_" + tag)
         assert_close(gs.h_p2[i].numpy(), p2[tag], 0, name="e2e P2h_" + tag)
     assert_close(gs.h_cl[0].numpy(), ckk, 0, name="e2e C_kk")
+    assert_close(gs.h_p1[6].numpy(), p1["yy"], 0, name="e2e P1h_yy")
+    assert_close(gs.h_cl[2].numpy(), gs.last_cyy, 0, name="e2e C_yy")
+    # an unreachable number density must be reported, not silently turned into spectra
+    bad = dict(inp); bad["ngal_target"] = inp["ngal_target"] * 1e12
+    gb = pipeline.GridSix(bad, fused_nfw=fused)
+    gb.upload(); gb.run()
+    from hmvec_b200 import _capi as capi
+    with pytest.raises(capi.HmvError):
+        gb.spectra()
 
 
 class _StandInComm(object):
@@ -76,10 +88,7 @@ class _StandInComm(object):
 
     def all_gather_rows(self, local, out):
         import torch
-        if not hasattr(self, "_i"):
-            self._i = 0
-        other = self.other_P[self._i % 4]
-        self._i += 1
+        other = self.other_P.reshape(-1, local.shape[1])          # the other slab's packed [nz_b][nq*nk] tables
         out.copy_(torch.cat((local, other) if self.first else (other, local), dim=0))
         return out
 
@@ -100,7 +109,7 @@ def test_z_sharding_emulated_on_one_gpu(setup):
     ma, mb = ga.mask.clone(), gb.mask.clone()
     gb2 = pipeline.GridSix(ib, zcomm=_StandInComm(ma, None, False), nz_total_zs=g["zs"]); gb2.has_limber = False
     gb2.upload(); gb2.run(); torch.cuda.synchronize()
-    Pb = torch.stack((gb2.p1[0], gb2.p2[0], gb2.p1[4], gb2.p2[4])).clone()
+    Pb = torch.stack([gb2.p1[r] + gb2.p2[r] for r in (0, 4, 6)], dim=1).clone()      # [nz_b][3][nk], as hmv_pack_sum
     ga2 = pipeline.GridSix(ia, zcomm=_StandInComm(mb, Pb, True), nz_total_zs=g["zs"])
     ga2.upload(); ga2.run()
     a1, a2, akk, akg = ga2.spectra()
@@ -110,6 +119,7 @@ def test_z_sharding_emulated_on_one_gpu(setup):
         assert_close(np.concatenate([a2[t], b2[t]]), f2[t], 1e-12, name="sharded P2h_" + t)
     assert_close(akk, fkk, 1e-12, name="sharded C_kk")
     assert_close(akg, fkg, 1e-12, name="sharded C_kg")
+    assert_close(ga2.last_cyy, g["C_yy"], 1e-6, name="sharded C_yy")
 
 
 def _nccl_worker(rank, world, port, q):
@@ -127,7 +137,7 @@ def _nccl_worker(rank, world, port, q):
         gs = pipeline.GridSix(pipeline.slab_inputs(inp, zc.slab), zcomm=zc, nz_total_zs=g["zs"])
         gs.upload(); gs.run()
         p1, p2, ckk, ckg = gs.spectra()
-        q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg))
+        q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg, gs.last_cyy))
     finally:
         dist.destroy_process_group()
 
@@ -154,6 +164,7 @@ def test_z_sharding_nccl_two_gpus(setup):
     for o in out:
         assert_close(o[5], fkk, 1e-12)
         assert_close(o[6], fkg, 1e-12)
+        assert_close(o[7], g["C_yy"], 1e-6)
 
 
 def test_large_grid_properties():
@@ -166,8 +177,8 @@ def test_large_grid_properties():
     if not torch.cuda.is_available():
         pytest.fail("GPU tests need a CUDA device; there is no CPU fallback")
     free, _ = torch.cuda.mem_get_info()
-    if free < 90e9:
-        pytest.skip("needs ~75 GB of free HBM")
+    if free < 115e9:
+        pytest.skip("needs ~105 GB of free HBM (three 32 GB cubes)")
     from hmvec_b200 import pipeline, _capi as capi
     zs = np.linspace(0.01, 3., 200)
     ms = np.geomspace(2e10, 1e17, 2000)

@@ -24,13 +24,16 @@ def _worker(rank, world, port, nz, q):
         zc.all_gather_rows(full[1, zc.slab].contiguous(), out)
         ok_gather2 = ok_gather2 and bool(torch.equal(out, full[1]))
         if nz % world == 0:
-            # the Limber hand-over of the pipeline: four slabs packed z-major [nz_local][4][n] -> ONE all-gather ->
-            # [nz_total][4][n], every spectrum a table with row stride 4 n
+            # the Limber hand-over of the pipeline: the spectra packed z-major [nz_local][nq][n] -> ONE all-gather ->
+            # [nz_total][nq][n], every spectrum a table with row stride nq n
             nzl, n = zc.nz_local, full.shape[-1]
             pack = torch.stack([full[i, zc.slab] for i in range(4)], dim=1).contiguous()
             allp = torch.empty((nz, 4, n), dtype=torch.float64)
             zc.all_gather_rows(pack.view(nzl, 4 * n), allp.view(nz, 4 * n))
             ok_gather2 = ok_gather2 and all(bool(torch.equal(allp[:, i], full[i])) for i in range(4))
+        # the drop-in API's hand-over: per-rank numpy slabs -> the full numpy table on every rank (even and ragged slabs)
+        host = zc.all_gather_host(full[2, zc.slab].numpy())
+        ok_gather2 = ok_gather2 and isinstance(host, np.ndarray) and bool(np.array_equal(host, full[2].numpy()))
         # rank 0 passes from iteration 3 on, rank 1 from iteration 5 on -> global first pass = iteration 5
         mask = torch.tensor([(~0) << (3 if rank == 0 else 5)], dtype=torch.int64)
         zc.all_reduce_and(mask)
