@@ -68,6 +68,7 @@ _SIGS = {
     "hmv_power_six_nfw": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll,
                                _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "hmv_ksz_nvv_integral": (_i, [_i, _i, _p, _p, _ll, _p, _ll, _p, _ll, _p, _p, _p]),
     "hmv_pack_sum": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p]),
     "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "hmv_outer": (_i, [_i, _i, _p, _p, _p, _p]),

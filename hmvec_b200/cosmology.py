@@ -97,6 +97,7 @@ class Cosmology(object):
         for key, val in default_params.items():
             self.p.setdefault(key, val)
         self._device = torch.device(device) if device is not None else None
+        self._bg_cache = {}
         self._init_cosmology(self.p, halofit)
 
     # ------------------------------------------------------------------ device plumbing
@@ -162,19 +163,41 @@ class Cosmology(object):
         self.ombh2 = self.params['ombh2']
         self.YHe = getattr(getattr(self, '_camb_pars', None), 'YHe', params.get('YHe', 0.24))
 
+    def _bg(self, what, z):
+        """Background quantity `what` at z, memoised per argument: the same redshift vector is asked for again and
+        again (every window, every Limber call), and each evaluation is a quadrature (or a CAMB call)."""
+        if np.ndim(z) == 0:
+            return getattr(self._camb_results, what)(z)
+        za = np.ascontiguousarray(z, dtype=np.float64)
+        key = (what, za.shape, za.tobytes())
+        hit = self._bg_cache.get(key)
+        if hit is None:
+            if len(self._bg_cache) > 64:
+                self._bg_cache.clear()
+            hit = self._bg_cache[key] = np.asarray(getattr(self._camb_results, what)(z))
+        return hit.copy()
+
     def angular_diameter_distance(self, z1, z2=None):
         if z2 is not None:
             return self._camb_results.angular_diameter_distance2(z1, z2)
-        return self._camb_results.angular_diameter_distance(z1)
+        return self._bg('angular_diameter_distance', z1)
 
     def comoving_radial_distance(self, z):
-        return self._camb_results.comoving_radial_distance(z)
+        return self._bg('comoving_radial_distance', z)
 
     def hubble_parameter(self, z):  # km/s/Mpc
-        return self._camb_results.hubble_parameter(z)
+        return self._bg('hubble_parameter', z)
 
     def h_of_z(self, z):  # 1/Mpc
-        return self._camb_results.h_of_z(z)
+        return self._bg('h_of_z', z)
+
+    def get_growth_rate_f(self, zs):
+        """Logarithmic growth rate f = dlnD/dlna.  The reference takes it from CLASS and raises for engine='camb'
+        (cosmology.py:345-350); here it is the derivative of the closed-form growing mode D_growth_approx
+        (cosmology.py:297-313, flat LCDM), by central differences in ln a."""
+        a = 1. / (1. + np.atleast_1d(np.asarray(zs, dtype=np.float64)))
+        e = 1e-4
+        return (np.log(self.D_growth_approx(a * np.exp(e))) - np.log(self.D_growth_approx(a * np.exp(-e)))) / (2. * e)
 
     def get_Omega_nu(self):
         return self._camb_results.get_Omega('nu')

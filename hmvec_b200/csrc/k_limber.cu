@@ -90,6 +90,34 @@ __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ s
 }
 
 
+// ---- kSZ velocity-reconstruction noise: the short-wavelength integral of Nvv_core_integral (ksz.py:299-336) ----------
+//   I[b] = trapz_kS( sanitize( kS * Pge[b,kS]^2 / (Pgg_tot[b,kS] * Cl_tot(chi* kS)) [* Pgg_photo_tot/Pgg_tot] ) )
+// b runs over the (mu, kL) plane when the spectra carry the photo-z window and is a single row otherwise; non-finite
+// integrand values (C_l = inf beyond the table, C_l = 0 below l = 2) count as zero (ksz.py:98-100).  One warp per b.
+__global__ void ksz_nvv_integral_kernel(int nb, int nk, const double* __restrict__ ks, const double* __restrict__ pge,
+                                        long long pge_stride, const double* __restrict__ pgg, long long pgg_stride,
+                                        const double* __restrict__ pgg_photo, long long photo_stride,
+                                        const double* __restrict__ clk, double* __restrict__ out) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= nb) return;
+  const double* e = pge ? pge + b * pge_stride : nullptr;
+  const double* g = pgg + b * pgg_stride;
+  const double* ph = pgg_photo ? pgg_photo + b * photo_stride : nullptr;
+  double acc = 0.0;
+  for (int k = lane; k < nk; k += 32) {
+    const double pe = e ? e[k] : 1.0;
+    double v = ks[k] * (pe * pe / (g[k] * clk[k]));
+    if (!isfinite(v)) v = 0.0;
+    if (ph) {
+      v *= ph[k] / g[k];
+      if (!isfinite(v)) v = 0.0;
+    }
+    acc = fma(v, trapz_weight(ks, k, nk), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc;
+}
+
 // out[z][s][k] = a_s[z][k] + b_s[z][k]: the P = P1h + P2h tables Limber needs, summed and packed z-major so that ONE
 // all-gather over the redshift slabs yields [nz_total][nsp][nk] (each spectrum is then a table of row stride nsp*nk)
 struct PackPtrs { const double* a[4]; const double* b[4]; };
@@ -112,6 +140,15 @@ extern "C" int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp
   limber_kernel<<<cdiv(nl, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, P_d, P2_d,
                                                                       ngz, gzs_d, pref_d, chis_d, cl_d);
   return check_launch("limber_kernel");
+}
+
+extern "C" int hmv_ksz_nvv_integral(int nb, int nk, const double* ks_d, const double* pge_d, long long pge_stride,
+                                    const double* pgg_d, long long pgg_stride, const double* pgg_photo_d,
+                                    long long photo_stride, const double* clk_d, double* out_d, void* stream) {
+  HMV_REQUIRE(nb > 0 && nk >= 2 && ks_d && pgg_d && clk_d && out_d, "hmv_ksz_nvv_integral: bad arguments");
+  ksz_nvv_integral_kernel<<<cdiv((long long)nb * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      nb, nk, ks_d, pge_d, pge_stride, pgg_d, pgg_stride, pgg_photo_d, photo_stride, clk_d, out_d);
+  return check_launch("ksz_nvv_integral_kernel");
 }
 
 extern "C" int hmv_pack_sum(int nz, int nk, int nsp, const double* const* a_h, const double* const* b_h, double* out_d,

@@ -200,6 +200,15 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
 int hmv_pack_sum(int nz, int nk, int nsp, const double* const* a_h, const double* const* b_h, double* out_d,
                  void* stream);
 
+/* ---- f2: kSZ consumer -- the short-wavelength integral of the velocity-reconstruction noise
+ * (ksz.py:299-336, Nvv_core_integral):  out[b] = trapz_kS( kS Pge[b,kS]^2 / (Pgg_tot[b,kS] C_tot(chi* kS)) ) with
+ * non-finite integrand values set to zero (ksz.py:98-100).  b = 0..nb-1 runs over the (mu,kL) plane when the spectra
+ * carry the photo-z window (stride nk) or is one row (nb = 1).  pge_d NULL = 1 (errs mode); pgg_photo_d optional
+ * (robust term: integrand * Pgg_photo_tot/Pgg_tot).  clk_d[k] = C_tot at l = chi* kS[k] (host lookup, O(nk)). */
+int hmv_ksz_nvv_integral(int nb, int nk, const double* ks_d, const double* pge_d, long long pge_stride,
+                         const double* pgg_d, long long pgg_stride, const double* pgg_photo_d, long long photo_stride,
+                         const double* clk_d, double* out_d, void* stream);
+
 /* ---- next row: P(z,k) from a matter-power interpolator  (cosmology.py:227-229, 353-382;
  *      utils.py:95-103 `PKInterpolator.P`; CAMB get_matter_power_interpolator) -------------------------------
  * out[z][k] = scale * (islog ? exp(s) : s),  s = the tensor-product B-spline (knots tx[nx], ty[ny], degrees kx, ky,

@@ -32,6 +32,13 @@ class _Pars(object):
         self.H0 = kw["H0"]
         self.ombh2 = kw["ombh2"]
         self.omch2 = kw["omch2"]
+        self.ns = kw.get("ns", 0.965)
+        self.As = kw.get("As", 2.2e-9)
+        self.NonLinear = None
+
+    def set_matter_power(self, redshifts=None, kmax=None, silent=True, **kw):
+        self.pk_redshifts, self.pk_kmax = list(redshifts or []), kmax
+        return self
 
 
 class _Background(object):
@@ -70,6 +77,40 @@ class _Background(object):
 
     def get_Omega(self, what):
         return 0.0
+
+
+class _MatterPower(object):
+    """Stand-in for the object camb.get_matter_power_interpolator returns: P(z,k) in Mpc^3 with the call convention
+    the reference uses, `PK.P(z, k, grid=True)` -> [nz,nk].  A smooth closed form (BBKS transfer function, Carroll-
+    Press-Turner growth), NOT a Boltzmann solution: it only has to be one deterministic function that the reference
+    and hmvec_b200 both receive when accuracy='medium'/'high' is exercised without CAMB."""
+
+    def __init__(self, pars):
+        h = float(pars.H0) / 100.0
+        self.h, self.ns, self.As = h, float(pars.ns), float(pars.As)
+        self.om = (pars.ombh2 + pars.omch2) / h ** 2
+        self.gam = self.om * h * np.exp(-pars.ombh2 / h ** 2 * (1.0 + np.sqrt(2.0 * h) / self.om))
+
+    def _growth(self, z):
+        a3 = (1.0 + np.asarray(z, dtype=np.float64)) ** 3
+        omz = self.om * a3 / (self.om * a3 + 1.0 - self.om)
+        olz = 1.0 - omz
+        g = 2.5 * omz / (omz ** (4.0 / 7.0) - olz + (1.0 + omz / 2.0) * (1.0 + olz / 70.0))
+        g0 = 2.5 * self.om / (self.om ** (4.0 / 7.0) - (1.0 - self.om) + (1.0 + self.om / 2.0) * (1.0 + (1.0 - self.om) / 70.0))
+        return g / g0 / (1.0 + np.asarray(z, dtype=np.float64))
+
+    def P(self, z, k, grid=True):
+        z = np.atleast_1d(np.asarray(z, dtype=np.float64))
+        k = np.atleast_1d(np.asarray(k, dtype=np.float64))
+        q = k / (self.gam * self.h)
+        T = np.log(1.0 + 2.34 * q) / (2.34 * q) * (1.0 + 3.89 * q + (16.1 * q) ** 2 + (5.46 * q) ** 3 + (6.71 * q) ** 4) ** -0.25
+        pk0 = 2.0e13 * self.As / 2.2e-9 * k * (k / 0.05) ** (self.ns - 1.0) * T ** 2
+        return self._growth(z)[:, None] ** 2 * pk0[None, :]
+
+
+def get_matter_power_interpolator(pars, nonlinear=False, hubble_units=False, k_hunit=False, kmax=None, zmax=None,
+                                  var1=None, var2=None, **kw):
+    return _MatterPower(pars)
 
 
 def set_params(**kw):

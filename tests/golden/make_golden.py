@@ -337,7 +337,73 @@ def case_hostfuncs(hm):
     return out
 
 
-CASES = dict(tinker=case_tinker, hostfuncs=case_hostfuncs, cky=case_cky, pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
+def case_ksz(hm):
+    """kSZ consumer: the free functions of ksz.py on fixed arguments, and the attributes + Nvv of the
+    reference's own `kSZ` class.  The class needs three things this image lacks, all shimmed test-side:
+    accuracy='medium' power (HaloModel's default; the camb stand-in's closed-form PK, see camb_standin), engine='camb'
+    (no classy), and a growth rate for that engine -- `Cosmology.get_growth_rate_f` raises for 'camb'
+    (cosmology.py:345-350) and is replaced by dlnD/dlna of the reference's own D_growth_approx (cosmology.py:297-313)."""
+    from hmvec import ksz as rk
+    import hmvec.cosmology as hcosm
+
+    def growth_rate_f(self, zs):
+        a = 1. / (1. + np.atleast_1d(np.asarray(zs, dtype=np.float64)))
+        e = 1e-4
+        return (np.log(self.D_growth_approx(a * np.exp(e))) - np.log(self.D_growth_approx(a * np.exp(-e)))) / (2. * e)
+
+    hcosm.Cosmology.get_growth_rate_f = growth_rate_f
+    out = {}
+    # free functions
+    out["ne0_shaw"] = rk.ne0_shaw(0.02225, 0.24)
+    zz = np.array([0.3, 1.0, 2.0])
+    out["kat_z"], out["ksz_radial_function"] = zz, rk.ksz_radial_function(zz, 0.02225, 0.24)
+    out["get_kmin"] = rk.get_kmin(np.array([1.0, 50.0]))
+    out["chi"] = rk.chi(0.24, 1)
+    Cls = 1e-6 / (1.0 + np.arange(6000.) / 300.) ** 2 + 3e-8
+    out["Cls"] = Cls.copy()
+    kS = np.geomspace(0.1, 10., 101)
+    out["kS"] = kS
+    out["interp_cls"] = rk.get_interpolated_cls(Cls.copy(), 1800., kS)
+    mu, kL = np.linspace(-1., 1., 12), np.geomspace(2e-3, 0.1, 9)
+    Pge1, Pgg1 = 3e2 * kS ** -1.5, 4e3 * kS ** -1.2 + 1e4
+    out["mu"], out["kL"], out["Pge1"], out["Pgg1"] = mu, kL, Pge1, Pgg1
+    out["Nvv_1d"] = rk.Nvv_core_integral(1800., 2.2e-7, mu, kL, kS, Cls.copy(), Pge1, Pgg1)
+    W = np.exp(-(mu[:, None] * kL[None, :] * 40.) ** 2)[..., None]
+    Pge3, Pgg3 = Pge1[None, None] * W, Pgg1[None, None] * W ** 2 + 50.
+    out["Nvv_3d"] = rk.Nvv_core_integral(1800., 2.2e-7, mu, kL, kS, Cls.copy(), Pge3, Pgg3)
+    nv, pe = rk.Nvv_core_integral(1800., 2.2e-7, mu, kL, kS, Cls.copy(), Pge3, Pgg3, errs=True)
+    out["Nvv_errs"] = nv
+    out["Nvv_robust"] = rk.Nvv_core_integral(1800., 2.2e-7, mu, kL, kS, Cls.copy(), Pge3, Pgg3,
+                                             Pgg_photo_tot=Pgg3 * 1.3, robust_term=True, photo=False)
+    edges = np.geomspace(0.1, 10., 6)
+    out["ks_bin_edges"] = edges
+    out["pge_err_core"] = rk.pge_err_core(3.5, 2.2e-7, 1800., 4.0, kS, edges, Pgg1, Cls.copy())
+    # the class, two redshift boxes, with and without photo-z scatter
+    zs = [0.4, 1.1]
+    vols, ngals = [5., 12.], [3e-4, 1e-4]
+    ms = np.geomspace(1e10, 1e16, 96)
+    out["c_zs"], out["c_vols"], out["c_ngals"], out["c_ms"] = np.array(zs), np.array(vols), np.array(ngals), ms
+    for tag, sigz in (("", None), ("_pz", 0.03)):
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            k = rk.kSZ(np.array(zs), vols, ngals, num_kL_bins=24, num_kS_bins=41, num_mu_bins=14, ms=ms, sigz=sigz,
+                       engine='camb', electron_profile_nxs=5000, electron_profile_xmax=20)
+        for a in ("kLs", "krs", "mu", "kS", "Hphotozs", "sPggs", "sPges", "Pmms", "fs", "adotf", "d2vs", "kstars",
+                  "chistars", "vrec", "sPggtot", "sPge", "bgs"):
+            out["c%s_%s" % (tag, a)] = np.asarray(getattr(k, a))
+        out["c%s_Nvv0" % tag] = k.Nvv(0, Cls.copy())
+        out["c%s_Nvv1" % tag] = k.Nvv(1, Cls.copy())
+        out["c%s_lPgg" % tag] = k.lPgg(0, 1.5, 1.7)
+        out["c%s_lPgv" % tag] = k.lPgv(1, 1.4)
+        out["c%s_lPvv" % tag] = k.lPvv(1)
+        if sigz is None:       # with the photo-z window the reference's Pge_err indexes a (kL, kS) slice and fails
+            out["c%s_Pge_err" % tag] = k.Pge_err(0, edges, Cls.copy())
+        out["c%s_sigma2" % tag], out["c%s_Pzk" % tag] = k.sigma2, k.Pzk
+    return out
+
+
+CASES = dict(ksz=case_ksz, tinker=case_tinker, hostfuncs=case_hostfuncs, cky=case_cky, pkspline=case_pkspline, readme=case_readme, mini=case_mini, mini_mean=case_mini_mean, largeslab=case_largeslab, kat=case_kat)
 
 if __name__ == "__main__":
     hm = _import_reference()
