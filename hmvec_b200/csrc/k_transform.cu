@@ -38,6 +38,9 @@ struct TParams {
   double gamma, dx, step, kt1, kmax;
   const double *zs, *ks, *rs, *cmax, *xc, *alpha, *expo, *amp, *outscale, *sintab, *rkt;
   const double* rho;      // user-supplied samples rho[z][m][n] = rho(x_n) (generic_profile_fft with any profile), or NULL
+  // two-stage (Cooley-Tukey) form of the sine sums for items with many bins: N = TS_P * ts_Q
+  int ts_Q, ts_QT;        // Q = N / TS_P (0: not available for this N), number of 8-wide q tiles
+  const double *ts_a1, *ts_tw, *ts_a2;   // fragment-ordered twiddle tables (global)
   const int* jn_cta;
   double* uk;
 };
@@ -325,6 +328,17 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 #endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill
 constexpr int WS_HB = 16, WS_NG = 2, WS_GT = 256, WS_MAXCTA = 192;
 constexpr int WS_GS_DOUBLES = (NCH_MMA / 4) * 64;      // one sample buffer: 16 halos x NCH_MMA samples
+constexpr int WS_PAGE = 256;                           // doubles per fill page = one 256-wide k block of a row (2 KB)
+#ifndef HMV_K1_TMAFILL
+#define HMV_K1_TMAFILL 0   // 1: fills of sorted rows leave as bulk async stores from a constant page.  Measured SLOWER (3.70 vs
+#endif                     // 3.26 ms on a 64-z slab): one warp pacing 800 KB per item through the copy engine is the straggler
+
+// 2 KB of a row <- the constant page in shared memory: one bulk async store (SASS UBLKCP.G.S), issued by one lane and
+// carried out by the copy engine, so the hold-u_1 / zero spans (63 % of the bytes) cost the SM one instruction per 2 KB
+__device__ __forceinline__ void bulk_fill(double* dst, const double* page) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(page)), "n"(WS_PAGE * 8) : "memory");
+}
 
 // sum over the lanes of the caller's parity (even lanes hold halos 0-7, odd lanes halos 8-15)
 __device__ __forceinline__ double warp_sum_parity(double v) {
@@ -466,6 +480,168 @@ __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, i
   q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two-stage form of the sine sums (the Cooley-Tukey factorisation of the zero-padded, output-pruned transform), used
+// for items that need many bins.  With N = P Q, samples n = P n1 + n0 and bins j = q + Q j1:
+//     stage 1   H(q, n0)  = sum_n1 g[P n1 + n0] exp(i 2 pi q n1 / Q)               [q < Q, n0 < P; n1 < nb/P <= 18]
+//     twiddle   H'(q, n0) = H(q, n0) exp(i 2 pi q n0 / N)
+//     stage 2   U[q + Q j1] = Im sum_n0 H'(q, n0) exp(i 2 pi j1 n0 / P)            [j1 <= jn/Q]
+// Both stages are small dense contractions with HALO-INDEPENDENT matrices, so they run on the same FP64 tensor-core
+// instruction: stage 1 as D[q][n0] += A1[q][n1] B[n1][n0] (B = the halo's samples), stage 2 as
+// D[j1][q] += A2[j1][(n0, re/im)] B[(n0, re/im)][q], where the B fragment of stage 2 is exactly what a lane holds of the
+// stage-1 result after the twiddle (the k index of stage 2 is ordered to match), so nothing is shuffled or stored in
+// between.  Work per halo: 16 q-tiles x (50 + 20 R) DMMAs (R = ceil((jn/Q + 1)/8) <= 3) instead of
+// ceil(nb/4) ceil(jn/8)/8 x 2: 3.4 x fewer for the heaviest halos (jn = 2207), break-even near jn = 410; the heavy
+// third of the items carries three quarters of the direct form's DMMAs.  No recurrences: every twiddle is exact.
+// All 8 warps of a group work on the same q tile (two halos each); the tile's A1 / twiddle slice (7.5 KB) is staged in
+// shared memory once per tile for the whole group, the A2 table (15 KB) once per kernel.
+constexpr int TS_P = 40, TS_U = TS_P / 8, TS_S = 5, TS_RMAX = 3;      // n0 tiles, stage-1 k-steps (n1 < 20), j1 tiles
+constexpr int TS_A1_SLICE = TS_S * 2 * 32, TS_TW_SLICE = TS_U * 2 * 32 * 2, TS_SLICE = TS_A1_SLICE + TS_TW_SLICE;
+constexpr int TS_A2_DOUBLES = TS_RMAX * TS_U * 4 * 32;
+
+// fragment-ordered tables: a1[qt][s][cos|sin][lane], tw[qt][u][e][lane]{cos,sin}, a2[r][u][a][lane]
+__global__ void twostage_tables_kernel(int N, int Q, int QT, double* __restrict__ a1, double* __restrict__ tw,
+                                       double* __restrict__ a2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = i & 31, g = lane >> 2, t = lane & 3;
+  if (i < QT * TS_S * 32) {
+    const int s = (i >> 5) % TS_S, qt = (i >> 5) / TS_S;
+    const long long q = 8 * qt + g, n1 = 4 * s + t;
+    double sn, cs;
+    sincospi(2.0 * (double)((q * n1) % Q) / (double)Q, &sn, &cs);
+    a1[((qt * TS_S + s) * 2 + 0) * 32 + lane] = cs;
+    a1[((qt * TS_S + s) * 2 + 1) * 32 + lane] = sn;
+  }
+  if (i < QT * TS_U * 2 * 32) {
+    const int e = (i >> 5) & 1, u = ((i >> 5) >> 1) % TS_U, qt = ((i >> 5) >> 1) / TS_U;
+    const long long q = 8 * qt + g, n0 = 8 * u + 2 * t + e;
+    double sn, cs;
+    sincospi(2.0 * (double)((q * n0) % N) / (double)N, &sn, &cs);
+    reinterpret_cast<double2*>(tw)[((qt * TS_U + u) * 2 + e) * 32 + lane] = make_double2(cs, sn);
+  }
+  if (i < TS_A2_DOUBLES) {
+    const int a = (i >> 5) & 3, u = ((i >> 5) >> 2) % TS_U, r = ((i >> 5) >> 2) / TS_U;
+    const long long j1 = 8 * r + g, n0 = 8 * u + 2 * t + (a & 1);
+    double sn, cs;
+    sincospi(2.0 * (double)((j1 * n0) % TS_P) / (double)TS_P, &sn, &cs);
+    a2[i] = (a < 2) ? sn : cs;
+  }
+}
+
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// One item (16 halos, one sample chunk) by a group of 8 warps; warp w owns halos 2w and 2w+1.  gs is halo-major
+// [16][NCH_MMA]; slice = this group's staging buffer; a2s = the A2 table in shared memory.
+template <int R>
+__device__ __forceinline__ void accum_two_stage(const TParams& p, const double* __restrict__ gs, int nfill, int ksteps,
+                                                const double* __restrict__ a2s, double* slice, double* U, int JS,
+                                                int jn, int g_id, int gt, double sc0, double sc1, double* u1_out) {
+  const int warp = gt >> 5, lane = gt & 31, gq = lane >> 2, t = lane & 3;
+  const int Q = p.ts_Q, QT = p.ts_QT;
+  const double* a1g = p.ts_a1;
+  const double* twg = p.ts_tw;
+  const double* g0 = gs + (size_t)(2 * warp) * NCH_MMA;
+  const double* g1 = g0 + NCH_MMA;
+  double* U0 = U + (size_t)(2 * warp) * JS;
+  double* U1 = U0 + JS;
+  // stage the slice of q tile 0
+  for (int i = gt; i < TS_SLICE; i += WS_GT)
+    slice[i] = (i < TS_A1_SLICE) ? __ldg(a1g + i) : __ldg(twg + (i - TS_A1_SLICE));
+  group_bar(g_id);
+  for (int qt = 0; qt < QT; ++qt) {
+    // next tile's slice travels through registers while this one is being used
+    double nx[(TS_SLICE + WS_GT - 1) / WS_GT];
+    if (qt + 1 < QT) {
+#pragma unroll
+      for (int i = 0; i < (TS_SLICE + WS_GT - 1) / WS_GT; ++i) {
+        const int idx = gt + i * WS_GT;
+        if (idx < TS_SLICE)
+          nx[i] = (idx < TS_A1_SLICE) ? __ldg(a1g + (size_t)(qt + 1) * TS_A1_SLICE + idx)
+                                      : __ldg(twg + (size_t)(qt + 1) * TS_TW_SLICE + (idx - TS_A1_SLICE));
+      }
+    }
+    double a1c[TS_S], a1s[TS_S];
+#pragma unroll
+    for (int s = 0; s < TS_S; ++s) { a1c[s] = slice[(s * 2 + 0) * 32 + lane]; a1s[s] = slice[(s * 2 + 1) * 32 + lane]; }
+    const double2* tws = reinterpret_cast<const double2*>(slice + TS_A1_SLICE);
+    // stage-2 accumulators [halo][j1 tile][k split]: with one j1 tile the k index is split over two accumulators per
+    // halo, so that an accumulator is never reused by the next DMMA but one (dependent-issue latency ~49 cycles)
+    constexpr int KS = (R == 1) ? 2 : 1;
+    double acc[2][R][KS][2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x)
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int k = 0; k < KS; ++k) acc[x][r][k][0] = acc[x][r][k][1] = 0.0;
+#pragma unroll
+    for (int u = 0; u < TS_U; ++u) {
+      double hr[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, hi[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+      for (int s = 0; s < TS_S; ++s) {
+        if (s < ksteps) {
+          const int n = TS_P * (4 * s + t) + 8 * u + gq;
+          const bool in = n < nfill;
+          const double b0 = in ? g0[n] : 0.0, b1 = in ? g1[n] : 0.0;
+          dmma(hr[0], a1c[s], b0);
+          dmma(hr[1], a1c[s], b1);
+          dmma(hi[0], a1s[s], b0);
+          dmma(hi[1], a1s[s], b1);
+        }
+      }
+      const double2 w0 = tws[(u * 2 + 0) * 32 + lane], w1 = tws[(u * 2 + 1) * 32 + lane];
+      double v[2][4];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        v[x][0] = fma(hr[x][0], w0.x, -hi[x][0] * w0.y);      // Re H' at n0 = 8u+2t
+        v[x][1] = fma(hr[x][1], w1.x, -hi[x][1] * w1.y);      // Re H' at n0 = 8u+2t+1
+        v[x][2] = fma(hr[x][0], w0.y, hi[x][0] * w0.x);       // Im H' at n0 = 8u+2t
+        v[x][3] = fma(hr[x][1], w1.y, hi[x][1] * w1.x);       // Im H' at n0 = 8u+2t+1
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double* af = a2s + ((r * TS_U + u) * 4) * 32 + lane;
+        const double f0 = af[0], f1 = af[32], f2 = af[64], f3 = af[96];
+        dmma(acc[0][r][0], f0, v[0][0]);
+        dmma(acc[1][r][0], f0, v[1][0]);
+        dmma(acc[0][r][KS - 1], f1, v[0][1]);
+        dmma(acc[1][r][KS - 1], f1, v[1][1]);
+        dmma(acc[0][r][0], f2, v[0][2]);
+        dmma(acc[1][r][0], f2, v[1][2]);
+        dmma(acc[0][r][KS - 1], f3, v[0][3]);
+        dmma(acc[1][r][KS - 1], f3, v[1][3]);
+      }
+    }
+    // bins of this q tile: lane holds rows j1 = 8r + gq, columns q = 8 qt + 2t + e
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = 8 * qt + 2 * t + e, j = q + Q * (8 * r + gq);
+        if (q < Q && j >= 1 && j <= jn) {
+          const double rk = __ldg(p.rkt + j);
+          const double v0 = (KS == 2 ? acc[0][r][0][e] + acc[0][r][KS - 1][e] : acc[0][r][0][e]) * (sc0 * rk);
+          const double v1 = (KS == 2 ? acc[1][r][0][e] + acc[1][r][KS - 1][e] : acc[1][r][0][e]) * (sc1 * rk);
+          U0[j] = v0;
+          U1[j] = v1;
+          if (j == 1) { u1_out[2 * warp] = v0; u1_out[2 * warp + 1] = v1; }
+        }
+      }
+    group_bar(g_id);                     // everyone is done reading this tile's slice
+    if (qt + 1 < QT) {
+#pragma unroll
+      for (int i = 0; i < (TS_SLICE + WS_GT - 1) / WS_GT; ++i) {
+        const int idx = gt + i * WS_GT;
+        if (idx < TS_SLICE) slice[idx] = nx[i];
+      }
+      group_bar(g_id);
+    }
+  }
+}
+
 #ifndef HMV_K1_STORE
 #define HMV_K1_STORE 0
 #endif
@@ -502,6 +678,11 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   const int tid = threadIdx.x;
   if (tid < WS_NG) gsh[tid].nxt_item = atomicAdd(work_counter, 1);
   gnfw_tables_init(tabs, tid, WS_NG * WS_GT);
+  if (tid < WS_PAGE) smem[(size_t)WS_NG * WS_GS_DOUBLES + tid] = 0.0;
+  if (p.ts_Q > 0)
+    for (int i = tid; i < TS_A2_DOUBLES; i += WS_NG * WS_GT)
+      smem[(size_t)WS_NG * WS_GS_DOUBLES + WS_PAGE * (1 + WS_NG) + i] = __ldg(p.ts_a2 + i);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero page is read by bulk copies
   int ascending = 1;
   for (int k = tid; k + 1 < p.nk; k += WS_NG * WS_GT)
     if (!(__ldg(p.ks + k) <= __ldg(p.ks + k + 1))) ascending = 0;
@@ -511,6 +692,10 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   const int g = tid / WS_GT, gt = tid - g * WS_GT;
   WsGroupShared& G = gsh[g];
   double* gs = smem + (size_t)g * WS_GS_DOUBLES;
+  double* zpage = smem + (size_t)WS_NG * WS_GS_DOUBLES;                   // 2 KB of zeros, then one 2 KB fill page per group
+  double* page = zpage + WS_PAGE * (1 + g);                               // (sources of the bulk-store fills of phase 2)
+  double* a2s = zpage + WS_PAGE * (1 + WS_NG);                            // two-stage form: A2 table, then one slice
+  double* slice = a2s + TS_A2_DOUBLES + (size_t)g * TS_SLICE;            // per group (present only when ts_Q > 0)
   double* U = ring + ((size_t)blockIdx.x * WS_NG + g) * WS_HB * JS;        // this group's bin table (L2-resident)
   const double2* T = reinterpret_cast<const double2*>(p.sintab);
   const int warp = gt >> 5, lane = gt & 31, hoff = (gt & 1) << 3;
@@ -570,6 +755,17 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     const bool single = nb > 0 && nb <= NCH_MMA;
     if (nb == 0)
       for (int i = gt; i < WS_HB * (jn + 1); i += WS_GT) U[(size_t)(i / (jn + 1)) * JS + 1 + i % (jn + 1)] = 0.0;
+    // two-stage form when it needs clearly fewer DMMAs than the direct one (both counted for the whole item)
+    const int ts_k = (((nb + TS_P - 1) / TS_P) + 3) >> 2;                       // stage-1 k-steps: n1 < 4 ts_k
+    const int ts_r = p.ts_Q > 0 ? ((jn / p.ts_Q + 1) + 7) >> 3 : 0;             // j1 tiles
+    bool two = false;
+#if !(HMV_K1_ABL & 32)
+    if (single && p.ts_Q > 0 && ts_k <= TS_S && ts_r <= TS_RMAX) {
+      const long long direct = 2LL * ((nb + 3) >> 2) * ((jn + 7) >> 3);
+      const long long staged = (long long)WS_HB * p.ts_QT * (2 * TS_U * ts_k + 4 * TS_U * ts_r);
+      two = 5 * staged < 4 * direct;
+    }
+#endif
 
     double msum[8];                          // this lane's half of the halos (hoff ...)
 #pragma unroll
@@ -593,7 +789,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             const long long row = (long long)z * p.nm + min(m0 + h, p.nm - 1);
             const double v = (n < p.N && x <= G.h_cmax[h]) ? x * __ldg(p.rho + row * p.N + n) : 0.0;
             msum[hh] = fma(wx, v, msum[hh]);
-            gs[ws_gs_index(sn, h)] = v;
+            gs[two ? h * NCH_MMA + sn : ws_gs_index(sn, h)] = v;
           }
         }
       } else
@@ -620,7 +816,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
           const double v = (n < p.N && x <= G.h_cmax[h]) ? (x * G.h_amp[h]) * f[hh] : 0.0;   // x * rho(x) inside the cut
           msum[hh] = fma(wx, v, msum[hh]);
           HMV_DEV_ASSERT(ws_gs_index(sn, h) >= 0 && ws_gs_index(sn, h) < WS_GS_DOUBLES);
-          gs[ws_gs_index(sn, h)] = v;
+          gs[two ? h * NCH_MMA + sn : ws_gs_index(sn, h)] = v;
         }
       }
 #else
@@ -651,6 +847,21 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       const int ntile = (jn + 7) >> 3;
 #define HMV_WS_ACC(NTV) accum_mma_ws<NTV>(T, gs, U, JS, p.N, n0, nlen, jw, jn, lane, first, single, scale0, scale1, p.rkt, G.u1)
       const bool first = n0 == 0;
+      if (two) {
+        // scale of this warp's two halos (the direct form applies them per lane row instead)
+        double m0 = 1.0, m1 = 1.0;
+        if (p.do_mass_norm) {
+          m0 = 0.0; m1 = 0.0;
+#pragma unroll
+          for (int w8 = 0; w8 < WS_GT / 32; ++w8) { m0 += G.redm[w8][2 * warp]; m1 += G.redm[w8][2 * warp + 1]; }
+        }
+        const double s0 = p.step / m0 * G.h_oscale[2 * warp], s1 = p.step / m1 * G.h_oscale[2 * warp + 1];
+        switch (ts_r) {
+          case 1: accum_two_stage<1>(p, gs, nfill, ts_k, a2s, slice, U, JS, jn, g, gt, s0, s1, G.u1); break;
+          case 2: accum_two_stage<2>(p, gs, nfill, ts_k, a2s, slice, U, JS, jn, g, gt, s0, s1, G.u1); break;
+          default: accum_two_stage<3>(p, gs, nfill, ts_k, a2s, slice, U, JS, jn, g, gt, s0, s1, G.u1); break;
+        }
+      } else {
       // bin tiles split evenly over the warps (counts differ by at most one), each warp's share in passes of up to
       // four tiles of equal size (5 tiles: 3 + 2, not 4 + 1, so that no pass runs on two accumulator chains)
       int rem = ntile / NW + (warp < ntile % NW);
@@ -666,6 +877,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
         }
         tb += ntc;
         rem -= ntc;
+      }
       }
 #undef HMV_WS_ACC
 #else
@@ -706,7 +918,43 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       const int nvalid = min(WS_HB, p.nm - m0);
       double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
       const int jcap = min(p.J - 1, jn);
-      for (int blk = warp; blk < nblk; blk += WS_GT / 32) {
+      // Sorted ks: the blocks of a row below the first bin are a prefix (hold u_1), those above the last bin a suffix
+      // (zero).  The group's last warp turns them into bulk stores, one row at a time (the page is rewritten per row
+      // once the copy engine has read it); the other seven interpolate the blocks in between.
+      const bool tma_fill = HMV_K1_TMAFILL && sorted && !(HMV_K1_ABL & 8);
+      const int nw_int = tma_fill ? WS_GT / 32 - 1 : WS_GT / 32;
+      if (tma_fill && warp == WS_GT / 32 - 1) {
+        const int nwhole = npair >> 7;
+        int nA = 0, nB = nwhole;
+        {
+          const double inv_r = G.h_inv[lane & 15];
+          int lo = 0, hi = nwhole;                       // first block whose last k is not below the first bin
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(p.ks + 256 * mid + 255) * inv_r < 1.0) lo = mid + 1; else hi = mid; }
+          nA = lo;
+          lo = 0; hi = nwhole;                           // first block whose first k is above the last bin
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(p.ks + 256 * mid) * inv_r > tJ) hi = mid; else lo = mid + 1; }
+          nB = max(lo, nA);
+        }
+        for (int row = 0; row < nvalid; ++row) {
+          const int a = __shfl_sync(0xffffffffu, nA, row), bz = __shfl_sync(0xffffffffu, nB, row);
+          double* orow = out0 + (long long)row * p.ldk;
+          if (a > 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous row's copies have read the page
+            __syncwarp();
+            const double fv = G.u1[row];
+            const double2 v2 = make_double2(fv, fv);
+#pragma unroll
+            for (int i = 0; i < WS_PAGE / 64; ++i) reinterpret_cast<double2*>(page)[lane + 32 * i] = v2;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            for (int b = lane; b < a; b += 32) bulk_fill(orow + 256 * b, page);
+          }
+          for (int b = bz + lane; b < nwhole; b += 32) bulk_fill(orow + 256 * b, zpage);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      } else
+      for (int blk = warp; blk < nblk; blk += nw_int) {
         const int base = blk << 7;                       // first pair of the block
         const bool whole = base + 128 <= npair;
         double2 kk[4];
@@ -727,6 +975,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
         for (int row = 0; row < nvalid; ++row) {
           const int c = __shfl_sync(0xffffffffu, cls, row);
           double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk) + base + lane;
+          if (c < 2 && tma_fill) continue;               // the fill warp's bulk stores cover this block
           if (c < 2) {
             const double fv = c ? 0.0 : G.u1[row];
             const double2 v = make_double2(fv, fv);
@@ -810,7 +1059,8 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int stride = (int)(0.381966 * q.nmg);
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
-  const size_t smem = (size_t)WS_NG * WS_GS_DOUBLES * sizeof(double);
+  size_t smem = ((size_t)WS_NG * WS_GS_DOUBLES + (size_t)WS_PAGE * (1 + WS_NG)) * sizeof(double);
+  if (q.ts_Q > 0) smem += (size_t)(TS_A2_DOUBLES + WS_NG * TS_SLICE) * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
   profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride);
@@ -840,11 +1090,18 @@ static int launch_transform(const TParams& p, int jlo, int jhi, int JS, cudaStre
 }  // namespace hmv
 using namespace hmv;
 
+// two-stage form available: N divisible by TS_P (tables: QT q tiles)
+static int ts_qtiles(int nxs) { return (nxs % TS_P == 0 && nxs / TS_P >= 16) ? (nxs / TS_P + 7) / 8 : 0; }
+static long long ts_table_doubles(int nxs) {
+  const int QT = ts_qtiles(nxs);
+  return QT ? 2 + (long long)QT * (TS_A1_SLICE + TS_TW_SLICE) + TS_A2_DOUBLES : 0;
+}
+
 extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
   // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
   long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2 + (nxs / 2 + 2);   // ..., queue head, 1/kt_j
-  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NG * WS_HB * (nxs / 2 + 2);   // bin-table rings of the persistent kernel
+  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NG * WS_HB * (nxs / 2 + 2) + ts_table_doubles(nxs);   // bin tables of the persistent kernel + two-stage twiddles
   return n;
 }
 
@@ -882,6 +1139,7 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
   double* rkt = after_jn + 2;
   double* ring = rkt + (nxs / 2 + 2);
   p.rkt = rkt;
+  p.ts_Q = 0; p.ts_QT = 0; p.ts_a1 = p.ts_tw = p.ts_a2 = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   auto bin_counts = [&](int HB) {
     const int nmg = cdiv(nm, HB);
@@ -897,6 +1155,18 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
     if (rc) return rc;
     rc = bin_counts(WS_HB);
     if (rc) return rc;
+    const int QT = ts_qtiles(nxs);
+    if (QT) {
+      double* tabs = ring + (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)(nxs / 2 + 2);
+      tabs += ((size_t)(tabs - ws_d) & 1);              // 16-byte alignment of the double2 twiddles
+      p.ts_Q = nxs / TS_P; p.ts_QT = QT;
+      p.ts_a1 = tabs; p.ts_tw = tabs + (size_t)QT * TS_A1_SLICE; p.ts_a2 = tabs + (size_t)QT * (TS_A1_SLICE + TS_TW_SLICE);
+      const int nthr = QT * TS_U * 2 * 32 > TS_A2_DOUBLES ? QT * TS_U * 2 * 32 : TS_A2_DOUBLES;
+      twostage_tables_kernel<<<cdiv(nthr, 256), 256, 0, st>>>(nxs, p.ts_Q, QT, tabs, tabs + (size_t)QT * TS_A1_SLICE,
+                                                             tabs + (size_t)QT * (TS_A1_SLICE + TS_TW_SLICE));
+      rc = check_launch("twostage_tables_kernel");
+      if (rc) return rc;
+    }
     return launch_transform_ws(p, ring, counter, st);
   }
   if (rho_d)
