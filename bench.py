@@ -160,7 +160,7 @@ def run_reference(a):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -225,7 +225,8 @@ def api_step(hm, zc, zs, ms, ks, ells, ngal):
         h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
         h.add_hod("g", ngal=ngal[sl])
         P = {p: h.get_power(*p) for p in PAIRS}
-    full = (lambda x: zc.all_gather_host(x)) if zc is not None else (lambda x: x)
+    # sharded: the gathered tables stay on the device (C_kk & co. accept CUDA tensors), no round trip through the host
+    full = (lambda x: zc.all_gather_host(x, to_host=False)) if zc is not None else (lambda x: x)
     Pmm, Pgm, Pyy = full(P[("nfw", "nfw")]), full(P[("g", "nfw")]), full(P[("y", "y")])
     ckk = h.C_kk(ells, zs, ks, Pmm, lzs1=2.5, lzs2=2.5)
     ckg = h.C_kg(ells, zs, ks, Pgm, gzs=0.8, lzs=2.5)
@@ -479,7 +480,7 @@ def run_b200(a):
                                           "Limber, single numpy thread, %s" % (
                                               a.cpu_nz, a.nz, a.nm, a.nk,
                                               "unmodified reference from oracle/_ref" if kind == "reference" else "oracle port")}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

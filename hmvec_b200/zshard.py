@@ -60,9 +60,10 @@ class ZComm(object):
             out.copy_(self.all_gather_z(local))
         return out
 
-    def all_gather_host(self, local):
-        """numpy [nz_local, n] slab -> numpy [nz_total, n] on every rank (what a user of the drop-in API does with the
-        per-rank get_power results before the Limber integral): upload, one all-gather over NVLink, download."""
+    def all_gather_host(self, local, to_host=True):
+        """numpy [nz_local, n] slab -> [nz_total, n] on every rank (what a user of the drop-in API does with the per-rank
+        get_power results before the Limber integral): upload, one all-gather over NVLink, download.  to_host=False
+        skips the download and returns the CUDA tensor, which C_kk / C_kg / C_yy accept in place of a numpy table."""
         from . import _capi as capi
         h = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
         dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
@@ -72,6 +73,8 @@ class ZComm(object):
         if dev.type != "cuda":
             return out.numpy()
         capi.count_h2d(h.numel() * 8)
+        if not to_host:
+            return out
         capi.count_d2h(out.numel() * 8)
         res = torch.empty(out.shape, dtype=torch.float64, pin_memory=True)
         res.copy_(out, non_blocking=True)
