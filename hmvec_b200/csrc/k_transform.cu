@@ -328,18 +328,6 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 #endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill
 constexpr int WS_HB = 16, WS_NG = 2, WS_GT = 256, WS_MAXCTA = 192;
 constexpr int WS_GS_DOUBLES = (NCH_MMA / 4) * 64;      // one sample buffer: 16 halos x NCH_MMA samples
-constexpr int WS_PAGE = 256;                           // doubles per fill page = one 256-wide k block of a row (2 KB)
-#ifndef HMV_K1_TMAFILL
-#define HMV_K1_TMAFILL 0   // 1: fills of sorted rows leave as bulk async stores from a constant page.  Measured SLOWER (3.70 vs
-#endif                     // 3.26 ms on a 64-z slab): one warp pacing 800 KB per item through the copy engine is the straggler
-
-// 2 KB of a row <- the constant page in shared memory: one bulk async store (SASS UBLKCP.G.S), issued by one lane and
-// carried out by the copy engine, so the hold-u_1 / zero spans (63 % of the bytes) cost the SM one instruction per 2 KB
-__device__ __forceinline__ void bulk_fill(double* dst, const double* page) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst), "r"(smem_u32(page)), "n"(WS_PAGE * 8) : "memory");
-}
-
 // sum over the lanes of the caller's parity (even lanes hold halos 0-7, odd lanes halos 8-15)
 __device__ __forceinline__ double warp_sum_parity(double v) {
 #pragma unroll
@@ -563,6 +551,14 @@ __device__ __forceinline__ void accum_two_stage(const TParams& p, const double* 
                                       : __ldg(twg + (size_t)(qt + 1) * TS_TW_SLICE + (idx - TS_A1_SLICE));
       }
     }
+    double rk[R][2];                     // 1/kt_j of this lane's bins, in flight behind the tile's DMMAs
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int q = 8 * qt + 2 * t + e, j = q + Q * (8 * r + gq);
+        rk[r][e] = (q < Q && j >= 1 && j <= jn) ? __ldg(p.rkt + j) : 0.0;
+      }
     double a1c[TS_S], a1s[TS_S];
 #pragma unroll
     for (int s = 0; s < TS_S; ++s) { a1c[s] = slice[(s * 2 + 0) * 32 + lane]; a1s[s] = slice[(s * 2 + 1) * 32 + lane]; }
@@ -622,9 +618,8 @@ __device__ __forceinline__ void accum_two_stage(const TParams& p, const double* 
       for (int e = 0; e < 2; ++e) {
         const int q = 8 * qt + 2 * t + e, j = q + Q * (8 * r + gq);
         if (q < Q && j >= 1 && j <= jn) {
-          const double rk = __ldg(p.rkt + j);
-          const double v0 = (KS == 2 ? acc[0][r][0][e] + acc[0][r][KS - 1][e] : acc[0][r][0][e]) * (sc0 * rk);
-          const double v1 = (KS == 2 ? acc[1][r][0][e] + acc[1][r][KS - 1][e] : acc[1][r][0][e]) * (sc1 * rk);
+          const double v0 = (KS == 2 ? acc[0][r][0][e] + acc[0][r][KS - 1][e] : acc[0][r][0][e]) * (sc0 * rk[r][e]);
+          const double v1 = (KS == 2 ? acc[1][r][0][e] + acc[1][r][KS - 1][e] : acc[1][r][0][e]) * (sc1 * rk[r][e]);
           U0[j] = v0;
           U1[j] = v1;
           if (j == 1) { u1_out[2 * warp] = v0; u1_out[2 * warp + 1] = v1; }
@@ -667,6 +662,7 @@ struct WsGroupShared {                        // per group
   double u1[WS_HB];                           // bin 1 of the finished table (np.interp's left value)
   double redm[WS_GT / 32][WS_HB];
   int nxt_item;
+  int blk_next, blk_rot;                      // phase 2: next k block to hand out, first block that is not a pure hold-u_1 fill
 };
 
 __global__ void __launch_bounds__(WS_NG * WS_GT, 1)
@@ -678,11 +674,9 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   const int tid = threadIdx.x;
   if (tid < WS_NG) gsh[tid].nxt_item = atomicAdd(work_counter, 1);
   gnfw_tables_init(tabs, tid, WS_NG * WS_GT);
-  if (tid < WS_PAGE) smem[(size_t)WS_NG * WS_GS_DOUBLES + tid] = 0.0;
   if (p.ts_Q > 0)
     for (int i = tid; i < TS_A2_DOUBLES; i += WS_NG * WS_GT)
-      smem[(size_t)WS_NG * WS_GS_DOUBLES + WS_PAGE * (1 + WS_NG) + i] = __ldg(p.ts_a2 + i);
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero page is read by bulk copies
+      smem[(size_t)WS_NG * WS_GS_DOUBLES + i] = __ldg(p.ts_a2 + i);
   int ascending = 1;
   for (int k = tid; k + 1 < p.nk; k += WS_NG * WS_GT)
     if (!(__ldg(p.ks + k) <= __ldg(p.ks + k + 1))) ascending = 0;
@@ -692,9 +686,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   const int g = tid / WS_GT, gt = tid - g * WS_GT;
   WsGroupShared& G = gsh[g];
   double* gs = smem + (size_t)g * WS_GS_DOUBLES;
-  double* zpage = smem + (size_t)WS_NG * WS_GS_DOUBLES;                   // 2 KB of zeros, then one 2 KB fill page per group
-  double* page = zpage + WS_PAGE * (1 + g);                               // (sources of the bulk-store fills of phase 2)
-  double* a2s = zpage + WS_PAGE * (1 + WS_NG);                            // two-stage form: A2 table, then one slice
+  double* a2s = smem + (size_t)WS_NG * WS_GS_DOUBLES;                    // two-stage form: A2 table, then one slice
   double* slice = a2s + TS_A2_DOUBLES + (size_t)g * TS_SLICE;            // per group (present only when ts_Q > 0)
   double* U = ring + ((size_t)blockIdx.x * WS_NG + g) * WS_HB * JS;        // this group's bin table (L2-resident)
   const double2* T = reinterpret_cast<const double2*>(p.sintab);
@@ -913,48 +905,59 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     group_bar(g);                            // table complete and visible to the whole group
 
     // ======================== phase 2: interpolate the 16 rows onto ks, store them ========================
+    // The finished table moves from L2 into the (now dead) sample buffer, as many rows per pass as fit (all 16 for
+    // jn <= 702: four fifths of the items of the LARGE grid; at least 4 for N <= 5000), so the two table reads of every
+    // interpolated element are shared-memory loads instead of L2 round trips -- with eight warps a group cannot keep
+    // enough of those in flight (ncu: long_scoreboard was the top stall of this phase).  k blocks are handed out
+    // through a counter in shared memory, starting at the first block that is not a pure hold-u_1 fill: the expensive
+    // (interpolated) blocks go first and the group's warps finish within one cheap fill block of each other.
 #if !(HMV_K1_ABL & 4)
     {
       const int nvalid = min(WS_HB, p.nm - m0);
       double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
       const int jcap = min(p.J - 1, jn);
-      // Sorted ks: the blocks of a row below the first bin are a prefix (hold u_1), those above the last bin a suffix
-      // (zero).  The group's last warp turns them into bulk stores, one row at a time (the page is rewritten per row
-      // once the copy engine has read it); the other seven interpolate the blocks in between.
-      const bool tma_fill = HMV_K1_TMAFILL && sorted && !(HMV_K1_ABL & 8);
-      const int nw_int = tma_fill ? WS_GT / 32 - 1 : WS_GT / 32;
-      if (tma_fill && warp == WS_GT / 32 - 1) {
-        const int nwhole = npair >> 7;
-        int nA = 0, nB = nwhole;
-        {
-          const double inv_r = G.h_inv[lane & 15];
-          int lo = 0, hi = nwhole;                       // first block whose last k is not below the first bin
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(p.ks + 256 * mid + 255) * inv_r < 1.0) lo = mid + 1; else hi = mid; }
-          nA = lo;
-          lo = 0; hi = nwhole;                           // first block whose first k is above the last bin
-          while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(p.ks + 256 * mid) * inv_r > tJ) hi = mid; else lo = mid + 1; }
-          nB = max(lo, nA);
-        }
-        for (int row = 0; row < nvalid; ++row) {
-          const int a = __shfl_sync(0xffffffffu, nA, row), bz = __shfl_sync(0xffffffffu, nB, row);
-          double* orow = out0 + (long long)row * p.ldk;
-          if (a > 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the previous row's copies have read the page
-            __syncwarp();
-            const double fv = G.u1[row];
-            const double2 v2 = make_double2(fv, fv);
-#pragma unroll
-            for (int i = 0; i < WS_PAGE / 64; ++i) reinterpret_cast<double2*>(page)[lane + 32 * i] = v2;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            for (int b = lane; b < a; b += 32) bulk_fill(orow + 256 * b, page);
+      const int tw = (jn + 3) & ~1;                      // bins 0 .. jn+1, rounded up to whole 16-byte words
+      const bool staged = tw <= WS_GS_DOUBLES;           // a row longer than the buffer (N > 22500) is read from L2
+      const int rpp = staged ? min(WS_HB, WS_GS_DOUBLES / tw) : WS_HB;    // rows per pass
+      const int nwhole = npair >> 7;
+      if (warp == 0) {
+        int rot = 0;
+        if (sorted) {
+          double invmax = 0.0;
+          for (int h = 0; h < nvalid; ++h) invmax = fmax(invmax, G.h_inv[h]);
+          for (int b0 = 0; b0 < nwhole; b0 += 32) {
+            const int b = b0 + lane;
+            const unsigned hold = __ballot_sync(0xffffffffu, b < nwhole && __ldg(p.ks + 256 * b + 255) * invmax < 1.0);
+            rot += __popc(hold);
+            if (hold != 0xffffffffu) break;
           }
-          for (int b = bz + lane; b < nwhole; b += 32) bulk_fill(orow + 256 * b, zpage);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      } else
-      for (int blk = warp; blk < nblk; blk += nw_int) {
+        if (lane == 0) G.blk_rot = rot < nblk ? rot : 0;
+      }
+      for (int r0 = 0; r0 < nvalid; r0 += rpp) {
+        const int r1 = min(nvalid, r0 + rpp);
+        if (r0 > 0) group_bar(g);                        // the previous pass is done with the staged rows
+        if (staged) {
+          const int hw = tw >> 1;
+          double2* dst = reinterpret_cast<double2*>(gs);
+          for (int row = r0 + warp; row < r1; row += WS_GT / 32) {
+            const double2* src = reinterpret_cast<const double2*>(U + (size_t)row * JS);
+            double2* d = dst + (size_t)(row - r0) * hw;
+            for (int i = lane; i < hw; i += 32) d[i] = src[i];
+          }
+        }
+        if (gt == 0) G.blk_next = 0;
+        group_bar(g);
+        const int rot = G.blk_rot;
+      // (the two callers differ in the table pointer's address space: shared-memory loads for staged rows)
+      auto blocks = [&](const double* __restrict__ tabbase, const int tabstride) {
+      for (;;) {
+        int blk = 0;
+        if (lane == 0) blk = atomicAdd(&G.blk_next, 1);
+        blk = __shfl_sync(0xffffffffu, blk, 0);
+        if (blk >= nblk) break;
+        blk += rot;
+        if (blk >= nblk) blk -= nblk;
         const int base = blk << 7;                       // first pair of the block
         const bool whole = base + 128 <= npair;
         double2 kk[4];
@@ -972,10 +975,10 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
 #if HMV_K1_ABL & 8
         cls = 0;
 #endif
-        for (int row = 0; row < nvalid; ++row) {
+        for (int row = r0; row < r1; ++row) {
           const int c = __shfl_sync(0xffffffffu, cls, row);
           double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk) + base + lane;
-          if (c < 2 && tma_fill) continue;               // the fill warp's bulk stores cover this block
+          const double* Uh = tabbase + (size_t)(row - r0) * tabstride;
           if (c < 2) {
             const double fv = c ? 0.0 : G.u1[row];
             const double2 v = make_double2(fv, fv);
@@ -984,7 +987,6 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
               if (whole || base + lane + 32 * u < npair) ws_store(orow + 32 * u, v);
           } else if (c == 2) {
             const double inv = G.h_inv[row];
-            const double* Uh = U + (size_t)row * JS;
             unsigned jc[8], jo[8];
             double af[8];
 #pragma unroll
@@ -995,7 +997,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
             double ua[8], uo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              HMV_DEV_ASSERT(jc[i] >= 1u && jc[i] <= (unsigned)(jn + 1) && jo[i] <= (unsigned)(JS - 1));
+              HMV_DEV_ASSERT(jc[i] >= 1u && jc[i] <= (unsigned)(jn + 1) && jo[i] <= (unsigned)(jn + 1));
               ua[i] = Uh[jc[i]]; uo[i] = Uh[jo[i]];
             }
 #pragma unroll
@@ -1004,7 +1006,6 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
                                                   fma(af[2 * u + 1], uo[2 * u + 1] - ua[2 * u + 1], ua[2 * u + 1])));
           } else {
             const double inv = G.h_inv[row], u1 = G.u1[row];
-            const double* Uh = U + (size_t)row * JS;
             WsLerp e[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -1026,9 +1027,12 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
           }
         }
       }
-      if ((p.nk & 1) && warp == 0 && lane < nvalid) {      // odd nk: the last wavenumber, one row per lane
-        const int k = p.nk - 1;
-        out0[(long long)lane * p.ldk + k] = ws_interp(U + (size_t)lane * JS, __ldg(p.ks + k) * G.h_inv[lane], G.u1[lane], tJ, jcap);
+      };
+      if (staged) blocks(gs, tw); else blocks(U + (size_t)r0 * JS, JS);
+        if ((p.nk & 1) && warp == 0 && lane >= r0 && lane < r1) {   // odd nk: the last wavenumber, one row per lane
+          const int k = p.nk - 1;
+          out0[(long long)lane * p.ldk + k] = ws_interp(staged ? gs + (size_t)(lane - r0) * tw : U + (size_t)lane * JS, __ldg(p.ks + k) * G.h_inv[lane], G.u1[lane], tJ, jcap);
+        }
       }
     }
 #endif
@@ -1038,8 +1042,10 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   }
 }
 
+// row stride of the persistent kernel's bin tables: bins 0 .. J+1, rounded up to whole 16-byte words
+static int ws_js(int nxs) { return (nxs / 2 + 3) & ~1; }
 static bool ws_ring_fits(int nxs) {
-  return (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)(nxs / 2 + 2) * sizeof(double) <= ((size_t)8 << 30);   // only the bins a group needs are ever touched; covers every N the phase index allows (N < 65536)
+  return (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)ws_js(nxs) * sizeof(double) <= ((size_t)8 << 30);   // only the bins a group needs are ever touched; covers every N the phase index allows (N < 65536)
 }
 
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
@@ -1051,7 +1057,7 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform: %s", cudaGetErrorString(e));
   TParams q = p;
   q.nmg = cdiv(p.nm, WS_HB);
-  q.jlo = 0; q.jhi = p.J; q.JS = p.J + 2;
+  q.jlo = 0; q.jhi = p.J; q.JS = ws_js(p.N);
   const int nitems = q.nz * q.nmg;
   const int grid = nitems < nsm ? nitems : (nsm < WS_MAXCTA ? nsm : WS_MAXCTA);
   // stride through the mass groups with a step near nmg/phi^2 that is coprime to nmg (a permutation of 0..nmg-1)
@@ -1059,7 +1065,7 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int stride = (int)(0.381966 * q.nmg);
   if (stride < 1) stride = 1;
   while (gcd(stride, q.nmg) != 1) ++stride;
-  size_t smem = ((size_t)WS_NG * WS_GS_DOUBLES + (size_t)WS_PAGE * (1 + WS_NG)) * sizeof(double);
+  size_t smem = (size_t)WS_NG * WS_GS_DOUBLES * sizeof(double);
   if (q.ts_Q > 0) smem += (size_t)(TS_A2_DOUBLES + WS_NG * TS_SLICE) * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
@@ -1101,7 +1107,7 @@ extern "C" long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs) {
   if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
   // {sin,cos} table (2 doubles per phase) + one int per CTA (bin counts; a CTA holds at least one halo)
   long long n = 2LL * nxs + 2 + ((long long)nz * nm + 1) / 2 + 2 + 2 + (nxs / 2 + 2);   // ..., queue head, 1/kt_j
-  if (ws_ring_fits(nxs)) n += (long long)WS_MAXCTA * WS_NG * WS_HB * (nxs / 2 + 2) + ts_table_doubles(nxs);   // bin tables of the persistent kernel + two-stage twiddles
+  if (ws_ring_fits(nxs)) n += 1 + (long long)WS_MAXCTA * WS_NG * WS_HB * ws_js(nxs) + ts_table_doubles(nxs);   // bin tables of the persistent kernel + two-stage twiddles
   return n;
 }
 
@@ -1138,6 +1144,7 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
   int* counter = reinterpret_cast<int*>(after_jn);
   double* rkt = after_jn + 2;
   double* ring = rkt + (nxs / 2 + 2);
+  ring += ((size_t)(ring - ws_d) & 1);                  // 16-byte aligned rows (ws_d is): phase 2 copies them as double2
   p.rkt = rkt;
   p.ts_Q = 0; p.ts_QT = 0; p.ts_a1 = p.ts_tw = p.ts_a2 = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1157,7 +1164,7 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
     if (rc) return rc;
     const int QT = ts_qtiles(nxs);
     if (QT) {
-      double* tabs = ring + (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)(nxs / 2 + 2);
+      double* tabs = ring + (size_t)WS_MAXCTA * WS_NG * WS_HB * (size_t)ws_js(nxs);
       tabs += ((size_t)(tabs - ws_d) & 1);              // 16-byte alignment of the double2 twiddles
       p.ts_Q = nxs / TS_P; p.ts_QT = QT;
       p.ts_a1 = tabs; p.ts_tw = tabs + (size_t)QT * TS_A1_SLICE; p.ts_a2 = tabs + (size_t)QT * (TS_A1_SLICE + TS_TW_SLICE);
