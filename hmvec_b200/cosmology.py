@@ -110,9 +110,10 @@ class Cosmology(object):
         return self._device
 
     def _dev(self, a):
-        a = np.array(a, dtype=np.float64, order='C')
-        capi.count_h2d(a.nbytes)
-        return torch.as_tensor(a, device=self.device)
+        """numpy -> device through a pinned staging block, asynchronously on the current stream: a pageable copy
+        would block the host until every kernel queued before it has finished (torch's caching host allocator keeps
+        the block alive until the copy has been carried out)."""
+        return _upload(a, self.device)
 
     def _empty(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=self.device)
@@ -426,6 +427,15 @@ def a2z(a):
     return (1.0 / np.atleast_1d(a)) - 1.0
 
 
+def _upload(a, device):
+    a = np.asarray(a, dtype=np.float64)
+    h = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    if a.size:
+        np.copyto(h.numpy(), a)
+    capi.count_h2d(a.nbytes)
+    return h.to(device, non_blocking=True)
+
+
 def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None):
     r"""C(ell) = \int dz (H(z)/c) W1(z) W2(z) P(z, k=(ell+1/2)/chi) / chi^2   (cosmology.py:867-904) on the device.
 
@@ -440,10 +450,7 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
     with np.errstate(all="ignore"):
         pref = hzs * np.array(Wz1s, dtype=np.float64).reshape(-1) * np.array(Wz2s, dtype=np.float64).reshape(-1) / chis ** 2.
     pref = np.broadcast_to(pref, gzs.shape)
-    def dev(a):
-        a = np.array(a, dtype=np.float64, order='C')
-        capi.count_h2d(a.nbytes)
-        return torch.as_tensor(a, device=device)
+    dev = lambda a: _upload(a, device)
 
     if isinstance(Pzks, torch.Tensor):
         P_d = Pzks.to(device=device, dtype=torch.float64).contiguous()
@@ -463,4 +470,7 @@ def limber_integral(ells, zs, ks, Pzks, gzs, Wz1s, Wz2s, hzs, chis, device=None)
                                    capi.ptr(ks_d), capi.ptr(P_d), None, gzs.size, capi.ptr(gzs_d), capi.ptr(pref_d),
                                    capi.ptr(chis_d), capi.ptr(out), capi.stream()), "hmv_limber")
     capi.count_d2h(out.numel() * 8)
-    return out.cpu().numpy()
+    h = torch.empty(out.shape, dtype=torch.float64, pin_memory=True)
+    h.copy_(out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()

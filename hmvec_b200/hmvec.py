@@ -128,17 +128,49 @@ def _lazy_host(name, dev_attr):
     return property(fget, fset)
 
 
+_side_streams = {}
+
+
+def _side_stream(device, which):
+    """One HOD stream and one download stream per device, shared by every object (creating a stream per HaloModel
+    costs a millisecond while kernels are running)."""
+    key = (str(device), which)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 class HodRecord(dict):
     """hods[name] (hmvec.py:452-460): 'Nc','Ns','NsNsm1','NcNs' [nz,nm], 'ngal','bg' [nz], 'log10mthresh' [nz,1] plus
     the profile names.  The arrays live on the device; each one is downloaded the first time it is read."""
 
-    def __init__(self, owner, dev, **plain):
+    def __init__(self, owner, dev, pending=None, **plain):
         dict.__init__(self, **plain)
         self._owner, self._dev = weakref.proxy(owner), dev
+        self._pending = pending                 # (pinned int32 tensor, event): iteration count of the ngal bisection
+
+    def _resolve(self):
+        """Iteration count of the all-z bisection, read when first needed (add_hod itself does not wait for the
+        device).  0 means the search never met rtol: HmvError, as the reference's convergence loop would never end."""
+        if self._pending is not None:
+            h, ev = self._pending
+            ev.synchronize()
+            self._pending = None
+            iters = int(h.item())
+            dict.__setitem__(self, 'iterations', iters)
+            if iters == 0:
+                raise capi.HmvError("mthresh<->ngal bisection did not converge within %d iterations"
+                                    % capi.HMV_BISECT_MAXIT)
+            print("Bisection search converged in ", iters, " iterations.")   # utils.py:41
+        return dict.__getitem__(self, 'iterations')
 
     def __missing__(self, key):
+        if key == 'iterations' and self._pending is not None:
+            return self._resolve()
         if key in self._dev:
             v = self._owner._host(self._dev[key])
+            if self._pending is not None:
+                self._resolve()                  # the download has waited for the solve: check it converged
             if key == 'log10mthresh':
                 v = v[:, None]
             dict.__setitem__(self, key, v)
@@ -148,13 +180,15 @@ class HodRecord(dict):
     def _all(self):
         for k in self._dev:
             self[k]
+        if self._pending is not None:
+            self._resolve()
         return self
 
     def get(self, key, default=None):
         return self[key] if key in self else default
 
     def __contains__(self, key):
-        return dict.__contains__(self, key) or key in self._dev
+        return dict.__contains__(self, key) or key in self._dev or (key == 'iterations' and self._pending is not None)
 
     def keys(self):
         return dict.keys(self._all())
@@ -188,6 +222,7 @@ class HaloModel(Cosmology):
         `zshard.ZComm` when `zs` is this rank's slab of a redshift axis sharded over several GPUs."""
         self._hostc = {}
         self._six = {}
+        self._six_host = {}
         self._pairs = {}
         self._ws = {}
         self.zs = np.asarray(zs, dtype=np.float64).reshape(-1)
@@ -198,6 +233,7 @@ class HaloModel(Cosmology):
         self._zcomm = zcomm
         self._nz, self._nk = self.zs.size, self._ks64.size
         self._ldk = ((self._nk + 15) // 16) * 16
+        self._defer_pzk = True                  # the linear power is formed after the NFW cube kernel has been queued
         Cosmology.__init__(self, params, halofit, accuracy=accuracy, engine=engine, device=device)
         if mdef not in ('vir', 'mean'):
             raise ValueError("mdef must be 'vir' or 'mean'")
@@ -212,11 +248,21 @@ class HaloModel(Cosmology):
         self._ev_mf = self._ev_hod = None
         self.uk_profiles = DeviceCubes(self)
         self.pk_profiles = DeviceCubes(self)
+        # Launch order: per-halo geometry and the NFW cube first (they need only zs, ms and the background), so that
+        # the host-side preparation of the linear power and of the sigma^2 integral (EH98 transfer function, growth,
+        # Simpson weights: a few ms of numpy) runs while the GPU is already busy.  The reference's order
+        # (hmvec.py:98-131: P(z,k), mass function, NFW) yields the same state.
         if ms is not None:
             self.ms = np.asarray(ms, dtype=np.float64).reshape(-1)
-            self.init_mass_function(self.ms)
-        if not skip_nfw:
-            self.add_nfw_profile("nfw", numeric=nfw_numeric)
+            self._init_geometry(self.ms)
+            if not skip_nfw:
+                self.add_nfw_profile("nfw", numeric=nfw_numeric)
+        self._defer_pzk = False
+        self._make_pzk(halofit)
+        if ms is not None:
+            self._init_sigma2_massfn()
+        elif not skip_nfw:
+            self.add_nfw_profile("nfw", numeric=nfw_numeric)      # raises as the reference does without a mass grid
 
     # ------------------------------------------------------------------ host-side inputs
     def _plin_device(self, ks, zs):
@@ -231,6 +277,10 @@ class HaloModel(Cosmology):
 
     def _init_cosmology(self, params, halofit):
         Cosmology._init_cosmology(self, params, halofit)
+        if not self._defer_pzk:
+            self._make_pzk(halofit)
+
+    def _make_pzk(self, halofit):
         if self._Pzk_in is not None:
             P = np.array(self._Pzk_in, dtype=np.float64)
             if P.shape != (self.zs.size, self._ks64.size):
@@ -307,6 +357,7 @@ class HaloModel(Cosmology):
 
     def _invalidate_spectra(self):
         self._six = {}
+        self._six_host = {}
         self._pairs = {}
 
     def _duffy(self):
@@ -320,12 +371,25 @@ class HaloModel(Cosmology):
     def init_mass_function(self, ms):
         """sigma^2 -> n(M,z), b(M,z) and the per-halo geometry, all on the device (hmvec.py:127-185).  The numpy
         attributes `sigma2`, `nzm`, `bh` are downloaded when first read."""
+        self._init_geometry(ms)
+        self._init_sigma2_massfn()
+
+    def _init_geometry(self, ms):
+        """c(M,z) and r_vir(M,z) (hmvec.py:148-165): everything the profile kernels need of the mass grid."""
         if self.mode not in ("sheth-torman", "tinker"):
             raise NotImplementedError("mass_function=%r" % (self.mode,))
         self.ms = np.asarray(ms, dtype=np.float64).reshape(-1)
         self._nm = self.ms.size
         self._ms_d = self._dev(self.ms)
         self._invalidate_spectra()
+        A, alpha, beta = self._duffy()
+        self._drho1_d = self._dev(self._delta_rhos1())
+        self._cs_d, self._rvir_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
+        capi.check(capi.lib.hmv_halo_geometry(self._nz, self._nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d),
+                                              capi.ptr(self._drho1_d), A, alpha, beta, self.h, capi.ptr(self._cs_d),
+                                              capi.ptr(self._rvir_d), capi.stream()), "hmv_halo_geometry")
+
+    def _init_sigma2_massfn(self):
         for k in ('sigma2', 'nzm', 'bh'):
             self._hostc.pop(k, None)
         ks_sig, kw = self._sigma2_inputs(self.zs)
@@ -347,12 +411,6 @@ class HaloModel(Cosmology):
                        "hmv_mass_function")
         self._ev_mf = torch.cuda.Event()
         self._ev_mf.record()                                                  # the HOD side stream starts from here
-        A, alpha, beta = self._duffy()
-        self._drho1_d = self._dev(self._delta_rhos1())
-        self._cs_d, self._rvir_d = self._empty(self._nz, self._nm), self._empty(self._nz, self._nm)
-        capi.check(capi.lib.hmv_halo_geometry(self._nz, self._nm, capi.ptr(self._zs_d), capi.ptr(self._ms_d),
-                                              capi.ptr(self._drho1_d), A, alpha, beta, self.h, capi.ptr(self._cs_d),
-                                              capi.ptr(self._rvir_d), capi.stream()), "hmv_halo_geometry")
 
     def get_nzm(self):
         return self._host(self._nzm_d)
@@ -497,10 +555,10 @@ class HaloModel(Cosmology):
         # The HOD solve needs only n(M,z) and b(M,z) and is latency-bound: it runs on a side stream that forks after
         # the mass function, next to the profile-cube kernels of the main stream, and rejoins in front of the spectra.
         if self._hod_stream is None:
-            self._hod_stream = torch.cuda.Stream(device=self.device)
+            self._hod_stream = _side_stream(self.device, 'hod')
         main = torch.cuda.current_stream()
         hs = self._hod_stream
-        iters = 0
+        pending = None
         with torch.cuda.stream(hs):
             hs.wait_event(self._ev_mf)
             if ngal is not None:
@@ -508,8 +566,7 @@ class HaloModel(Cosmology):
                 if ngal.size != nz:
                     raise ValueError("ngal has to be a vector of size self.zs")
                 assert mthresh is None
-                l10_d, iters = self._solve_mthresh(self._dev(ngal.reshape(-1)), hodp, pp)
-                print("Bisection search converged in ", iters, " iterations.")   # utils.py:41
+                l10_d, pending = self._solve_mthresh(self._dev(ngal.reshape(-1)), hodp, pp)
             else:
                 mthresh = np.asarray(mthresh, dtype=np.float64)
                 if mthresh.size != nz:
@@ -528,8 +585,11 @@ class HaloModel(Cosmology):
             ev.record(hs)
         main.wait_event(ev)                    # later work on the main stream (spectra, downloads) sees the HOD arrays
         self._hod_d[name] = d
-        self.hods[name] = HodRecord(self, d, satellite_profile=satellite_profile_name,
-                                    central_profile=central_profile_name, iterations=iters)
+        rec = HodRecord(self, d, pending, satellite_profile=satellite_profile_name,
+                        central_profile=central_profile_name)
+        if pending is None:
+            rec['iterations'] = 0
+        self.hods[name] = rec
 
     def _solve_mthresh(self, target_d, hodp, pp):
         """All-z bisection (utils.py:9-42): every redshift bisects on the device and records, per iteration,
@@ -554,11 +614,13 @@ class HaloModel(Cosmology):
         capi.check(capi.lib.hmv_hod_pick(nz, capi.ptr(ws), C.c_void_p(mask_d.data_ptr()),
                                          float(pp['hod_A_log10mthresh']), capi.ptr(l10_d), capi.ptr(iters_d),
                                          capi.stream()), "hmv_hod_pick")
-        iters = int(iters_d.item())            # waits for the side stream only (mass function + bisection)
-        if iters == 0:
-            raise capi.HmvError("mthresh<->ngal bisection did not converge within %d iterations"
-                                % capi.HMV_BISECT_MAXIT)
-        return l10_d, iters
+        # the count goes to pinned memory behind the solve; nobody waits for it here: it is read (and a search that
+        # never converged raises) when the HOD is first consumed -- get_power & co., hods[name]['iterations']
+        h = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        h.copy_(iters_d, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return l10_d, (h, ev)
 
     def get_ngal(self, Nc, Ns):
         return _trapz(self.nzm * (Nc + Ns), self.ms, axis=-1)
@@ -609,7 +671,12 @@ class HaloModel(Cosmology):
         if bA is None and bB is None:
             six = self._six_lookup(name, name2, kA, kB)
             if six is not None:
-                p1, p2 = six
+                p1, p2, tag = six
+                if add and to_host and tag in self._six_host:
+                    h, ev = self._six_host.pop(tag)           # handed out once: the caller owns the memory
+                    ev.synchronize()
+                    self._check_hods()
+                    return h
                 return self._power_out(p1 if want1 else None, p2 if want2 else None, to_host, add)
             hit = self._pairs.get((name, kA, name2, kB))             # prefetched next to the six-spectra pass
             if hit is not None:
@@ -631,15 +698,29 @@ class HaloModel(Cosmology):
                                       capi.stream()), "hmv_power")
         return p1, p2
 
+    def _check_hods(self):
+        """Called after a download has synchronised the stream: every ngal bisection queued before it has finished,
+        so its iteration count is read for free here -- and a search that did not converge raises before any
+        spectrum built on it is handed out."""
+        for rec in self.hods.values():
+            if rec._pending is not None:
+                rec._resolve()
+
     def _power_out(self, p1, p2, to_host, add):
         if add:                                  # get_power: P1h + P2h formed on the device, one download
             out = self._empty(self._nz, self._nk)
             capi.check(capi.lib.hmv_sum2(out.numel(), capi.ptr(p1), capi.ptr(p2), capi.ptr(out), capi.stream()),
                        "hmv_sum2")
-            return self._host(out) if to_host else out
+            if not to_host:
+                return out
+            res = self._host(out)
+            self._check_hods()
+            return res
         if not to_host:
             return p1, p2
-        return (self._host(p1) if p1 is not None else None), (self._host(p2) if p2 is not None else None)
+        res = (self._host(p1) if p1 is not None else None), (self._host(p2) if p2 is not None else None)
+        self._check_hods()
+        return res
 
     # The usual workflow asks for the six auto/cross spectra of (matter, electron, galaxies) one after the other
     # (README.rst:75-100); each of them alone streams one or two 32 GB cubes.  The first such request runs ONE pass
@@ -670,6 +751,9 @@ class HaloModel(Cosmology):
         key = (m, e, g)
         if key not in self._six:
             self._six = {key: self.get_power_six(m, e, g, to_host=False, stacked=True)}
+            # P = P1h + P2h of all six goes to pinned host memory on the download stream, behind the pass but beside
+            # whatever the main stream runs next (the tSZ pair below): get_power then finds its array on the host
+            self._prefetch_six_totals(*self._six[key])
             # The caller is about to block on a download of one of these spectra; whatever is launched now runs behind
             # that wait for free.  A Compton-y profile next to the six tracers means the tSZ auto spectrum follows
             # (BASELINE configs[4]): queue it now, the request for it then finds it ready.
@@ -679,7 +763,25 @@ class HaloModel(Cosmology):
                     y, _KIND_PRESSURE, None, y, _KIND_PRESSURE, None)
         p1, p2 = self._six[key]
         i = self._SIX.index(tag)
-        return p1[i], p2[i]
+        return p1[i], p2[i], tag
+
+    def _prefetch_six_totals(self, p1, p2):
+        tot = self._empty(6, self._nz, self._nk)
+        capi.check(capi.lib.hmv_sum2(tot.numel(), capi.ptr(p1), capi.ptr(p2), capi.ptr(tot), capi.stream()), "hmv_sum2")
+        ready = torch.cuda.Event()
+        ready.record()
+        cs = _side_stream(self.device, 'd2h')
+        self._six_host = {}
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            for i, tag in enumerate(self._SIX):
+                h = torch.empty((self._nz, self._nk), dtype=torch.float64, pin_memory=True)
+                h.copy_(tot[i], non_blocking=True)
+                capi.count_d2h(h.numel() * 8)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                self._six_host[tag] = (h.numpy(), ev)
+        tot.record_stream(cs)
 
     # 1-halo looks names up as HOD first (hmvec.py:510-523); 2-halo as matter profile first (hmvec.py:536-550)
     def _kinds_1h(self, name, name2):
@@ -735,6 +837,7 @@ class HaloModel(Cosmology):
         if not to_host:
             return {t: p1[i] for i, t in enumerate(tags)}, {t: p2[i] for i, t in enumerate(tags)}
         h1, h2 = self._host(p1), self._host(p2)
+        self._check_hods()
         return {t: h1[i] for i, t in enumerate(tags)}, {t: h2[i] for i, t in enumerate(tags)}
 
 
