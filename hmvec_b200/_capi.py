@@ -55,6 +55,7 @@ _SIGS = {
                              _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_set_transform_mode": (_i, [_i]),
+    "hmv_set_nfw_mode": (_i, [_i]),
     "hmv_profile_transform": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_profile_transform_samples": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _d, _i, _i, _p, _p, _p]),
     "hmv_hod": (_i, [_i, _i, _p, _p, _p, C.POINTER(_d), _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -89,6 +90,9 @@ EXPORTS = tuple(_SIGS)
 if os.environ.get("HMV_TRANSFORM_MODE"):       # A/B measurements of the transform's launch plan (see the header)
     if lib.hmv_set_transform_mode(int(os.environ["HMV_TRANSFORM_MODE"])) != 0:
         raise ImportError("hmvec_b200: bad HMV_TRANSFORM_MODE=%r" % os.environ["HMV_TRANSFORM_MODE"])
+if os.environ.get("HMV_NFW_MODE"):             # A/B measurements of the NFW evaluation (see the header)
+    if lib.hmv_set_nfw_mode(int(os.environ["HMV_NFW_MODE"])) != 0:
+        raise ImportError("hmvec_b200: bad HMV_NFW_MODE=%r" % os.environ["HMV_NFW_MODE"])
 
 
 def last_error():

@@ -67,6 +67,35 @@ __device__ __forceinline__ void sici_fg_r(double rx, double& f, double& g) {
 
 __device__ __forceinline__ void sici_fg(double x, double& f, double& g) { sici_fg_r(1.0 / x, f, g); }
 
+// g(x) alone (x > 4), from rx = 1/x
+__device__ __forceinline__ double sici_g_r(double rx) {
+  const double rx2 = rx * rx;
+  const double t = (16.0 * HMV_SICI_NSEG) * rx2;
+  const int seg = min(HMV_SICI_NSEG - 1, (int)t);
+  const double u = fma(2.0, t - (double)seg, -1.0);
+  const double2* co = g_sici_FG + seg * (HMV_SICI_DEG + 1);
+  double G = __ldg(co + HMV_SICI_DEG).y;
+#pragma unroll
+  for (int i = HMV_SICI_DEG - 1; i >= 0; --i) G = fma(G, u, __ldg(co + i).y);
+  return G * rx2;
+}
+
+// f(X), g(X) for X >= 64 from their asymptotic series in w = 1/X^2 (7 and 8 terms: the first omitted terms are
+// 8.7e10 w^7 and 3.6e14 w^8, < 5e-15 relative at X = 64): no table, no conversions
+__device__ __forceinline__ void sici_fg_far(double rX, double& f, double& g) {
+  const double w = rX * rX;
+  double F = 479001600.0, G = -1307674368000.0;
+  F = fma(F, w, -3628800.0);  G = fma(G, w, 6227020800.0);
+  F = fma(F, w, 40320.0);     G = fma(G, w, -39916800.0);
+  F = fma(F, w, -720.0);      G = fma(G, w, 362880.0);
+  F = fma(F, w, 24.0);        G = fma(G, w, -5040.0);
+  F = fma(F, w, -2.0);        G = fma(G, w, 120.0);
+  F = fma(F, w, 1.0);         G = fma(G, w, -6.0);
+  G = fma(G, w, 1.0);
+  f = F * rX;
+  g = G * w;
+}
+
 // General-purpose pair (used by tests through hmv_sici_test): Si(x), Ci(x) for x > 0.
 __device__ __forceinline__ void sici(double x, double& si, double& ci) {
   if (x <= 4.0) {
@@ -99,6 +128,18 @@ __device__ __forceinline__ double rcp_fast(double x) {
 //   x > 4      :  f(X) sin(cx) - g(X) cos(cx) + g(x) - sin(cx)/X         (exact identity, one sincos)
 //   x <= 4 < X :  series at x, f/g at X
 //   X <= 4     :  series at both, Ci X - Ci x = ln(1+c) + Z C(Z) - z C(z)
+// the x > 4 branch when also X >= 64 (every element beyond the polynomial range of k_nfw.cu): f, g at X from the
+// asymptotic series, only g at x from the table
+__device__ __forceinline__ double nfw_bracket_far(double x, double c) {
+  const double X = (1.0 + c) * x;
+  const double rX = rcp_fast(X);
+  double fX, gX, scx, ccx;
+  sici_fg_far(rX, fX, gX);
+  const double gx = sici_g_r((1.0 + c) * rX);
+  sincos_cw(c * x, scx, ccx);
+  return fX * scx - gX * ccx + gx - scx * rX;
+}
+
 __device__ __forceinline__ double nfw_bracket(double x, double c, double ln1pc) {
   const double X = (1.0 + c) * x;
   const double rX = rcp_fast(X);

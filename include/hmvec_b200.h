@@ -62,8 +62,12 @@ int hmv_mdelta(int nz, int nm, const double* ms_d, const double* cs_d, const dou
                const double* drho2_d, double* m2_d, void* stream);
 
 /* ---- a4: analytic NFW u(k|M,z)  (hmvec.py:346-353) --------------------------------------------------
- * ws_d: workspace of hmv_uk_nfw_ws_doubles() doubles (per-halo series coefficients, see k_nfw.cu). */
+ * ws_d: workspace of hmv_uk_nfw_ws_doubles() doubles (per-halo series and polynomial coefficients, see k_nfw.cu). */
 long long hmv_uk_nfw_ws_doubles(int nz, int nm, int nk);
+/* Process-wide choice of the evaluation: 0 (default) = per-halo piecewise polynomials in (x c)^2 up to x c = 64 and the
+ * closed form's asymptotic branch beyond; 1 = the earlier Maclaurin series up to x c = 16 + Si/Ci closed form (kept for
+ * A/B measurements and as the cross-check of the polynomial tables).  Both agree to ~1e-11 of max|u|. */
+int hmv_set_nfw_mode(int mode);
 int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
                double kmax /* >= max(ks): lets whole rows skip the Si/Ci pass */, const double* cs_d,
                const double* rvir_d, double* ws_d, double* uk_d, void* stream);
