@@ -153,6 +153,7 @@ __global__ void nfw_chunk_kernel(int nk, const double* __restrict__ ks, double* 
 // per lane and 37 x 16 x 2 mma.sync m8n8k4 (SASS DMMA) with W resident in shared memory.  Checked against mpmath for
 // 0.6 <= c <= 25: same error as exact node values (< 2e-11 of an interval's max|u|, the truncation error).
 // Also writes the per-halo constants {c, a = r_s (1+z), a c, ln(1+c), 1/m_c} into slots 42..46 of the 48-double record.
+constexpr int NFWP_MAXCH = 128;                          // chunks whose min/max the cube kernel keeps in shared memory
 constexpr int NFWP_NT = (NFWP_REC + 7) / 8;              // 8-wide coefficient tiles
 constexpr size_t NFWP_GEMM_SMEM = ((size_t)NFWP_Q * NFWP_WLD + 2 * NFWP_Q) * sizeof(double);
 
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
                                                                 double* __restrict__ uk) {
   __shared__ __align__(16) double Rall[NFW_T / 32][NFWP_REC + 6];      // record, then {c, a, a c, ln(1+c), 1/m_c, 0}
   __shared__ NfwpTables T;
+  __shared__ double2 cmm[NFWP_MAXCH];                       // {min, max} of ks per chunk (when they fit)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row = (long long)blockIdx.x * (NFW_T / 32) + warp;
   double* Rr = Rall[warp];
@@ -298,13 +300,16 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
   if (tid < NFWP_NI) { T.map[tid] = g_nfwp_map[tid]; T.deg[tid] = g_nfwp_deg[tid]; }
   if (tid <= NFWP_NI) T.hi[tid] = tid < NFWP_NI ? g_nfwp_hix[tid] : 1.0e300;
   if (tid < 72) T.idx[tid] = (unsigned char)(tid < 64 ? nfwp_interval((double)tid + 0.5) : NFWP_NI);
+  const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
+  const bool cmm_sm = nchunks <= NFWP_MAXCH;
+  if (cmm_sm)
+    for (int i = tid; i < nchunks; i += NFW_T) cmm[i] = make_double2(__ldg(kcmin + i), __ldg(kcmax + i));
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (row >= rows) return;
   const double c = Rr[NFWP_REC], a = Rr[NFWP_REC + 1], ac = Rr[NFWP_REC + 2], ln1pc = Rr[NFWP_REC + 3],
                inv_mc = Rr[NFWP_REC + 4];
   const double ac2 = ac * ac;
-  const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
   const int npair = nk >> 1;
   const double2* ks2 = reinterpret_cast<const double2*>(ksp);
   const double2* kq2 = reinterpret_cast<const double2*>(k2p);
@@ -315,7 +320,8 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
   int nA = 0;
   for (int b0 = 0; b0 < nchunks - 1; b0 += 32) {            // the last (possibly partial) chunk is left to the general loop
     const int b = b0 + lane;
-    const unsigned in0 = __ballot_sync(0xffffffffu, b < nchunks - 1 && __ldg(kcmax + min(b, nchunks - 1)) * ac < T.hi[0]);
+    const double bmax = cmm_sm ? cmm[min(b, nchunks - 1)].y : __ldg(kcmax + min(b, nchunks - 1));
+    const unsigned in0 = __ballot_sync(0xffffffffu, b < nchunks - 1 && bmax * ac < T.hi[0]);
     const int run = in0 == 0xffffffffu ? 32 : __ffs(~in0) - 1;
     nA += run;
     if (run < 32) break;
@@ -342,13 +348,14 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
       HMV_STEP(m3) HMV_STEP(m2) HMV_STEP(m1) HMV_STEP(m0)
 #undef HMV_STEP
 #pragma unroll
-      for (int q = 0; q < 4; ++q) out2[pbase + 32 * q] = u[q];
+      for (int q = 0; q < 4; ++q) __stcs(out2 + pbase + 32 * q, u[q]);   // streaming: keeps k, k^2 in L1
     }
   }
 
   // ---- the other chunks ----
   for (int chunk = nA; chunk < nchunks; ++chunk) {
-    const double smin = __ldg(kcmin + chunk) * ac, smax = __ldg(kcmax + chunk) * ac;
+    const double2 mm = cmm_sm ? cmm[chunk] : make_double2(__ldg(kcmin + chunk), __ldg(kcmax + chunk));
+    const double smin = mm.x * ac, smax = mm.y * ac;
     const int pbase = chunk * (NFW_CH / 2) + lane;        // pair index of this lane's first pair
     double2 u[4];
     if (smin >= NFWP_SMAX) {                              // the whole chunk is beyond the polynomials: closed form
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int pp = pbase + 32 * q;
-      if (pp < npair) out2[pp] = u[q];
+      if (pp < npair) __stcs(out2 + pp, u[q]);
       else if (2 * pp < nk) out[2 * pp] = u[q].x;          // odd nk: the last wavenumber
     }
   }
