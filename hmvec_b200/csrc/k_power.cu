@@ -437,6 +437,176 @@ __global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// The six spectra with the ELECTRON profile interpolated from its bin tables inside the reduction (hmv_profile_tables:
+// the transform's result before the expansion onto ks) instead of read from a cube: the 32 GB cube is neither written
+// nor re-read, the kernel streams the matter cube plus ~1 GB of table segments.  A CTA (z, 512-wide k tile) needs of
+// halo m only the bins between floor(kmin_tile * inv_m) and floor(kmax_tile * inv_m) + 1: the producer warp works
+// out those segments for up to four rows per stage (one lane per row), packs them behind the rows' matter segments
+// and coefficient records, and describes them in a small header; rows whose whole tile lies below the first bin
+// (u_e = u_1) or above the last one (u_e = 0) need no table data at all.  Consumers interpolate exactly as the
+// transform's own expansion does (np.interp semantics of fft.py:102-107).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TAB_R = 4, TAB_CT = 256, TAB_NST = 6;
+constexpr int TAB_STAGE_DOUBLES = TAB_R * SIX_K + TAB_R * 8 + TAB_R * 4;       // matter rows, coefficient records, table parameters
+constexpr size_t TAB_SMEM = (size_t)TAB_NST * TAB_STAGE_DOUBLES * sizeof(double) + 2 * TAB_NST * sizeof(unsigned long long);
+
+struct SixTabArgs {
+  int nz, nm, nk, ldk, nmp, JS, J;
+  long long spec_stride;
+  const double *um, *coef, *zoff, *ks, *Pzk, *tab, *tmeta;
+  double kstar;
+  double *p1h, *p2h;
+};
+
+// what a thread keeps of one (row, wavenumber) between issuing the two table loads and using them
+struct TabLerp { double ua, ub, fr; };   // fr: t - j inside [1, J]; -1: below the first bin (hold u_1); -2: above the last (zero)
+
+__device__ __forceinline__ TabLerp tab_fetch(const double* __restrict__ row, double inv, int jcap, double k, double tJ) {
+  const double t = k * inv;
+  const int jj = min(max(__double2int_rz(fmin(t, tJ)), 1), jcap);       // always inside the bins the transform wrote
+  TabLerp r;
+  r.fr = (t >= 1.0) ? ((t > tJ) ? -2.0 : t - (double)jj) : -1.0;
+  r.ua = 0.0; r.ub = 0.0;
+  if (r.fr >= 0.0) { r.ua = row[jj]; r.ub = row[jj + 1]; }              // plain loads: the tables of a redshift live in L2
+  return r;
+}
+__device__ __forceinline__ double tab_value(const TabLerp& r, double u1) {
+  const double v = fma(r.fr, r.ub - r.ua, r.ua);
+  return (r.fr >= 0.0) ? v : ((r.fr > -1.5) ? u1 : 0.0);                // np.interp left=puks[0], right=0 (fft.py:102-107)
+}
+
+__global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const SixTabArgs a) {
+  extern __shared__ __align__(128) unsigned char tab_smem[];
+  double* ring = reinterpret_cast<double*>(tab_smem);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)TAB_NST * TAB_STAGE_DOUBLES);
+  unsigned long long* empty = full + TAB_NST;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.y, k0 = blockIdx.x * SIX_K;
+  const int segk = min(SIX_K, a.ldk - k0);
+  const long long zrow = (long long)z * a.nm, zrowp = (long long)z * a.nmp;
+  const double tJ = (double)a.J;
+  const int nit = (a.nm + TAB_R - 1) / TAB_R;
+  if (tid == 0) {
+    for (int s = 0; s < TAB_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, TAB_CT / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == TAB_CT / 32) {            // ---- producer warp: one elected lane drives the TMA unit ----
+    if (lane == 0) {
+      const unsigned segb = (unsigned)segk * 8u;
+      for (int it = 0; it < nit; ++it) {
+        const int s = it % TAB_NST;
+        const unsigned ph = (unsigned)(it / TAB_NST) & 1u;
+        mbar_wait(empty + s, ph ^ 1u);
+        const int m0 = it * TAB_R, rows = min(TAB_R, a.nm - m0);
+        double* st = ring + (size_t)s * TAB_STAGE_DOUBLES;
+        mbar_expect_tx(full + s, (unsigned)rows * (segb + 64u + 32u));
+        for (int r = 0; r < rows; ++r)
+          bulk_g2s(st + r * SIX_K, a.um + (zrow + m0 + r) * (long long)a.ldk + k0, segb, full + s);
+        bulk_g2s(st + TAB_R * SIX_K, a.coef + (zrow + m0) * 8, (unsigned)rows * 64u, full + s);
+        bulk_g2s(st + TAB_R * SIX_K + TAB_R * 8, a.tmeta + (zrowp + m0) * 4, (unsigned)rows * 32u, full + s);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers: thread owns k = k0 + 2 tid, +1 over the whole mass axis.  The table reads of stage i+1 are issued
+  //      (from the stage's parameter records, as soon as they have landed) before stage i is accumulated ----
+  const bool active = 2 * tid < segk;
+  const int kc = min(k0 + 2 * tid, a.nk - 1), kc1 = min(k0 + 2 * tid + 1, a.nk - 1);
+  const double kx = a.ks[kc], ky = a.ks[kc1];
+  double2 acc[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) acc[q] = make_double2(0.0, 0.0);
+  TabLerp cur[TAB_R][2], nxt[TAB_R][2];
+  auto issue = [&](int it, TabLerp (&dst)[TAB_R][2]) {
+    const int s = it % TAB_NST;
+    const unsigned ph = (unsigned)(it / TAB_NST) & 1u;
+    mbar_wait(full + s, ph);
+    const double4* pm = reinterpret_cast<const double4*>(ring + (size_t)s * TAB_STAGE_DOUBLES + TAB_R * SIX_K + TAB_R * 8);
+    const int m0 = it * TAB_R, rows = min(TAB_R, a.nm - m0);
+#pragma unroll
+    for (int r = 0; r < TAB_R; ++r) {
+      const double4 mt = pm[r < rows ? r : 0];
+      const double* row = a.tab + (zrowp + m0 + (r < rows ? r : 0)) * (long long)a.JS;
+      const int jcap = min(a.J - 1, (int)mt.z);
+      dst[r][0] = tab_fetch(row, mt.x, jcap, kx, tJ);
+      dst[r][1] = tab_fetch(row, mt.x, jcap, ky, tJ);
+    }
+  };
+  if (active) issue(0, cur);
+  for (int it = 0; it < nit; ++it) {
+    const int s = it % TAB_NST;
+    const unsigned ph = (unsigned)(it / TAB_NST) & 1u;
+    const int rows = min(TAB_R, a.nm - it * TAB_R);
+    const double* st = ring + (size_t)s * TAB_STAGE_DOUBLES;
+    if (active) {
+      if (it + 1 < nit) issue(it + 1, nxt);
+    } else {
+      mbar_wait(full + s, ph);
+    }
+    if (active) {
+      const double4* pm = reinterpret_cast<const double4*>(st + TAB_R * SIX_K + TAB_R * 8);
+#pragma unroll
+      for (int r = 0; r < TAB_R; ++r) {
+        if (r < rows) {
+          const double2 um = *reinterpret_cast<const double2*>(st + r * SIX_K + 2 * tid);
+          const double u1 = pm[r].y;
+          const double2 ue = make_double2(tab_value(cur[r][0], u1), tab_value(cur[r][1], u1));
+          const double2* c = reinterpret_cast<const double2*>(st + TAB_R * SIX_K + r * 8);
+          const double2 c01 = c[0], c23 = c[1], c45 = c[2], c67 = c[3];
+          const double A1 = c01.x, c1 = c01.y, c2 = c23.x, B1 = c23.y, B2 = c45.x, D1 = c45.y, D2 = c67.x;
+#define HMV_SIX(c)                                                          \
+  {                                                                         \
+    const double q1 = um.c * um.c, q2 = ue.c * ue.c, q3 = um.c * ue.c;      \
+    acc[0].c = fma(A1, q1, acc[0].c);                                       \
+    acc[1].c = fma(A1, q2, acc[1].c);                                       \
+    acc[2].c = fma(A1, q3, acc[2].c);                                       \
+    acc[3].c = fma(c1, um.c, fma(c2, q1, acc[3].c));                        \
+    acc[4].c = fma(B1, um.c, fma(B2, q1, acc[4].c));                        \
+    acc[5].c = fma(B1, ue.c, fma(B2, q3, acc[5].c));                        \
+    acc[6].c = fma(D1, um.c, acc[6].c);                                     \
+    acc[7].c = fma(D1, ue.c, acc[7].c);                                     \
+    acc[8].c = fma(D2, um.c, acc[8].c);                                     \
+  }
+          HMV_SIX(x)
+          HMV_SIX(y)
+#undef HMV_SIX
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TAB_R; ++r) { cur[r][0] = nxt[r][0]; cur[r][1] = nxt[r][1]; }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  if (!active) return;
+  const long long S = a.spec_stride;
+  const double zo0 = a.zoff[2 * z], zo1 = a.zoff[2 * z + 1];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + 2 * tid + e;
+    if (k >= a.nk) break;
+    double sv[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) sv[q] = e ? acc[q].y : acc[q].x;
+    const long long o = (long long)z * a.nk + k;
+    if (a.p1h) {
+      const double r = a.ks[k] / a.kstar, damp = 1.0 - exp(-r * r);          // hmvec.py:526
+#pragma unroll
+      for (int q = 0; q < 6; ++q) a.p1h[q * S + o] = sv[q] * damp;
+    }
+    if (a.p2h) {                                                           // hmvec.py:572
+      const double P = a.Pzk[o];
+      const double Lm = sv[6] + zo0, Le = sv[7] + zo0, Lg = sv[8] + zo1;
+      a.p2h[0 * S + o] = P * Lm * Lm; a.p2h[1 * S + o] = P * Le * Le; a.p2h[2 * S + o] = P * Lm * Le;
+      a.p2h[3 * S + o] = P * Lg * Lg; a.p2h[4 * S + o] = P * Lg * Lm; a.p2h[5 * S + o] = P * Lg * Le;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Spectra-only fusion: the six spectra with the NFW matter profile evaluated IN the reduction instead of being read
 // from a cube.  u_NFW(k|M,z) depends on the halo only through (c, a = r_s (1+z)) and a 42-coefficient series, so a
 // 384-byte per-halo record replaces an 8*nk-byte cube row: the kernel streams only the electron cube (half the
@@ -713,6 +883,45 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
   dim3 grid(cdiv(ldk, SIX_K), nz);
   power_six_kernel<<<grid, SIX_CT + 32, SIX_SMEM, st>>>(a);
   return check_launch("power_six_kernel");
+}
+
+extern "C" long long hmv_power_six_tab_ws_doubles(int nz, int nm, int nk) {
+  if (nz <= 0 || nm <= 0 || nk <= 0) return 0;
+  return hmv_power_ws_doubles(nz, nm);
+}
+
+extern "C" int hmv_power_six_tab(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d,
+                                 const double* nzm_d, const double* bh_d, const double* Pzk_d, double rho_m0,
+                                 double kstar, const double* um_d, const double* etab_d, int nxs, const double* Nc_d,
+                                 const double* Ns_d, const double* NcNs_d, const double* NsNsm1_d, const double* ngal_d,
+                                 double* ws_d, long long spec_stride, double* p1h_d, double* p2h_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2 && nk > 0 && ldk >= nk && nxs >= 4, "hmv_power_six_tab: bad sizes");
+  HMV_REQUIRE(nz <= 65535, "hmv_power_six_tab: nz=%d exceeds grid.y limit 65535", nz);
+  HMV_REQUIRE(ms_d && ks_d && nzm_d && bh_d && um_d && etab_d && Nc_d && Ns_d && NcNs_d && NsNsm1_d && ngal_d && ws_d,
+              "hmv_power_six_tab: null pointer");
+  HMV_REQUIRE(p2h_d == nullptr || Pzk_d != nullptr, "hmv_power_six_tab: P2h requested without Pzk");
+  HMV_REQUIRE((ldk & 1) == 0 && (((unsigned long long)um_d | (unsigned long long)etab_d | (unsigned long long)ws_d) & 15ull) == 0,
+              "hmv_power_six_tab: cube, tables and workspace must be 16-byte aligned with even ldk (bulk async copies)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cs = (long long)nz * nm;
+  double* coef = ws_d;
+  double* zoff = ws_d + 8 * cs;
+  power_six_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, Nc_d, Ns_d, NcNs_d, NsNsm1_d, ngal_d, coef,
+                                            zoff);
+  int rc = check_launch("power_six_prep_kernel");
+  if (rc) return rc;
+  SixTabArgs a;
+  HMV_REQUIRE(spec_stride == 0 || spec_stride >= (long long)nz * nk, "hmv_power_six_tab: spec_stride smaller than nz*nk");
+  a.spec_stride = spec_stride ? spec_stride : (long long)nz * nk;
+  a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.um = um_d; a.coef = coef; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d;
+  a.kstar = kstar; a.p1h = p1h_d; a.p2h = p2h_d;
+  a.JS = (int)hmv_profile_table_stride(nxs); a.J = nxs / 2; a.nmp = cdiv(nm, 16) * 16;
+  a.tab = etab_d; a.tmeta = etab_d + (size_t)nz * a.nmp * (size_t)a.JS;
+  cudaError_t e = cudaFuncSetAttribute(power_six_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAB_SMEM);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_six_tab_kernel smem opt-in (%zu B): %s", TAB_SMEM, cudaGetErrorString(e));
+  dim3 grid(cdiv(ldk, SIX_K), nz);
+  power_six_tab_kernel<<<grid, TAB_CT + 32, TAB_SMEM, st>>>(a);
+  return check_launch("power_six_tab_kernel");
 }
 
 extern "C" long long hmv_power_six_nfw_ws_doubles(int nz, int nm) {

@@ -43,6 +43,10 @@ struct TParams {
   const double *ts_a1, *ts_tw, *ts_a2;   // fragment-ordered twiddle tables (global)
   const int* jn_cta;
   double* uk;
+  // table mode (persistent kernel only): the finished bin tables go to tab[z][nmp][JS] (nmp = nm rounded up to 16) with
+  // {k -> bin factor, u_1, bin count, 0} per halo in tmeta[z][nmp][4], instead of a per-CTA slot that is reused
+  double *tab, *tmeta;
+  int phases;             // bit 0: compute the tables, bit 1: interpolate + store the rows
 };
 
 // samples evaluated per chunk.  The two large bin-count classes hold 704 (every Battaglia/README halo has <= 690
@@ -688,7 +692,8 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   double* gs = smem + (size_t)g * WS_GS_DOUBLES;
   double* a2s = smem + (size_t)WS_NG * WS_GS_DOUBLES;                    // two-stage form: A2 table, then one slice
   double* slice = a2s + TS_A2_DOUBLES + (size_t)g * TS_SLICE;            // per group (present only when ts_Q > 0)
-  double* U = ring + ((size_t)blockIdx.x * WS_NG + g) * WS_HB * JS;        // this group's bin table (L2-resident)
+  double* Uslot = ring + ((size_t)blockIdx.x * WS_NG + g) * WS_HB * JS;    // this group's bin table (L2-resident)
+  const int nmp = p.nmg * WS_HB;
   const double2* T = reinterpret_cast<const double2*>(p.sintab);
   const int warp = gt >> 5, lane = gt & 31, hoff = (gt & 1) << 3;
   const int npair = p.nk >> 1;
@@ -707,8 +712,8 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
       const int m = (p.nmg - 1 - q) * WS_HB + gt;
       const bool ok = m < p.nm;
       const long long rr = (long long)z * p.nm + (ok ? m : p.nm - 1);
-      f_cmax = ok ? p.cmax[rr] : -1.0;
-      if (!p.rho) {
+      if (p.phases & 1) f_cmax = ok ? p.cmax[rr] : -1.0;
+      if (!p.rho && (p.phases & 1)) {
         f_xc = p.xc[rr];
         f_alpha = p.alpha[rr];
         f_expo = p.expo[rr];
@@ -735,11 +740,13 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     const int jn = f_jn;
     const int m0 = (p.nmg - 1 - q) * WS_HB;
     HMV_DEV_ASSERT(jn >= 2 && jn <= p.J && m0 >= 0 && m0 < p.nm && z >= 0 && z < p.nz);
+    double* U = p.tab ? p.tab + ((size_t)z * nmp + m0) * JS : Uslot;
     group_bar(g);                            // h_* of this item and nxt_item are visible
     const int nxt = G.nxt_item;
     fetch(nxt);                              // loads in flight behind the whole transform of this item
 
     // ======================== phase 1: samples -> sine sums -> bin table of the item ========================
+    if (p.phases & 1) {
     double cmx = -1.0;
 #pragma unroll
     for (int h = 0; h < WS_HB; ++h) cmx = fmax(cmx, G.h_cmax[h]);
@@ -903,6 +910,12 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     if (gt < WS_HB) U[(size_t)gt * JS + jn + 1] = 0.0;     // guard bin behind the last computed one
     __threadfence_block();
     group_bar(g);                            // table complete and visible to the whole group
+    if (p.tmeta && gt < WS_HB)               // what a later reader of the table needs to know about the halo
+      *reinterpret_cast<double4*>(p.tmeta + ((size_t)z * nmp + m0 + gt) * 4) = make_double4(G.h_inv[gt], G.u1[gt], (double)jn, 0.0);
+    } else {                                 // tables computed by an earlier launch: only u_1 has to be fetched
+      if (gt < WS_HB) G.u1[gt] = p.tmeta[((size_t)z * nmp + m0 + gt) * 4 + 1];
+      group_bar(g);
+    }
 
     // ======================== phase 2: interpolate the 16 rows onto ks, store them ========================
     // The finished table moves from L2 into the (now dead) sample buffer, as many rows per pass as fit (all 16 for
@@ -912,7 +925,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     // through a counter in shared memory, starting at the first block that is not a pure hold-u_1 fill: the expensive
     // (interpolated) blocks go first and the group's warps finish within one cheap fill block of each other.
 #if !(HMV_K1_ABL & 4)
-    {
+    if (p.phases & 2) {
       const int nvalid = min(WS_HB, p.nm - m0);
       double* out0 = p.uk + ((long long)z * p.nm + m0) * (long long)p.ldk;
       const int jcap = min(p.J - 1, jn);
@@ -1121,11 +1134,13 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
                                   double kmax, const double* rs_d, const double* cmax_d, const double* xc_d,
                                   const double* alpha_d, const double* expo_d, const double* amp_d,
                                   const double* outscale_d, const double* rho_d, double gamma, double xmax, int nxs,
-                                  int do_mass_norm, double* ws_d, double* uk_d, void* stream) {
+                                  int do_mass_norm, double* ws_d, double* uk_d, void* stream, double* tab_d = nullptr,
+                                  int phases = 3) {
   HMV_REQUIRE(nz > 0 && nm > 0 && nk > 0 && ldk >= nk, "hmv_profile_transform: bad sizes");
   HMV_REQUIRE(nxs >= 4 && xmax > 0, "hmv_profile_transform: need nxs>=4 and xmax>0");
   HMV_REQUIRE((long long)nxs * (nxs / 2) < 2147483647LL, "hmv_profile_transform: nxs=%d too large (phase index overflow)", nxs);
-  HMV_REQUIRE(zs_d && ks_d && rs_d && cmax_d && ws_d && uk_d && (rho_d || (xc_d && alpha_d && expo_d && amp_d)),
+  HMV_REQUIRE(zs_d && ks_d && rs_d && ws_d && ((phases & 2) == 0 || uk_d) &&
+              ((phases & 1) == 0 || (cmax_d && (rho_d || (xc_d && alpha_d && expo_d && amp_d)))),
               "hmv_profile_transform: null pointer");
   TParams p;
   p.nz = nz; p.nm = nm; p.nk = nk; p.ldk = ldk; p.N = nxs; p.J = nxs / 2; p.JS = p.J + 2;
@@ -1138,6 +1153,8 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
   p.zs = zs_d; p.ks = ks_d; p.rs = rs_d; p.cmax = cmax_d; p.xc = xc_d; p.alpha = alpha_d; p.expo = expo_d;
   p.amp = amp_d; p.outscale = outscale_d; p.uk = uk_d; p.nmg = 0; p.sintab = ws_d; p.jlo = 0; p.jhi = p.J;
   p.rho = rho_d;
+  p.tab = tab_d; p.phases = phases;
+  p.tmeta = tab_d ? tab_d + (size_t)nz * (size_t)(cdiv(nm, WS_HB) * WS_HB) * (size_t)ws_js(nxs) : nullptr;
   int* jn_cta = reinterpret_cast<int*>(ws_d + 2 * (size_t)nxs + 2);
   p.jn_cta = jn_cta;
   double* after_jn = ws_d + 2 * (size_t)nxs + 2 + ((size_t)nz * nm + 1) / 2 + 2;
@@ -1154,8 +1171,10 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
                                                                      counter);
     return check_launch("bin_count_kernel");
   };
-  const bool aligned16 = (((size_t)ks_d | (size_t)uk_d | (size_t)ws_d) & 15) == 0 && (ldk & 1) == 0;
-  if (g_transform_mode == 0 && ws_ring_fits(nxs) && aligned16) {
+  const bool aligned16 = (((size_t)ks_d | (size_t)uk_d | (size_t)ws_d | (size_t)tab_d) & 15) == 0 && (ldk & 1) == 0;
+  if (tab_d && !(ws_ring_fits(nxs) && aligned16))
+    return fail(HMV_E_LIMIT, "hmv_profile_tables/expand: need 16-byte aligned ks/uk/ws/tab, even ldk and nxs < 65536");
+  if ((g_transform_mode == 0 || tab_d) && ws_ring_fits(nxs) && aligned16) {
     // persistent warp-specialised kernel: sine table, bin counts, one launch
     sine_table_kernel<<<cdiv(nxs, 256), 256, 0, st>>>(nxs, reinterpret_cast<double2*>(ws_d), p.kt1, rkt);
     int rc = check_launch("sine_table_kernel");
@@ -1232,4 +1251,30 @@ extern "C" int hmv_profile_transform_samples(int nz, int nm, int nk, int ldk, co
   HMV_REQUIRE(rho_d, "hmv_profile_transform_samples: null samples");
   return profile_transform_impl(nz, nm, nk, ldk, zs_d, ks_d, kmax, rs_d, cmax_d, nullptr, nullptr, nullptr, nullptr,
                                 outscale_d, rho_d, 0.0, xmax, nxs, do_mass_norm, ws_d, uk_d, stream);
+}
+
+// ---- table mode: the transform split in two launches around a persistent table array -------------------------------
+extern "C" long long hmv_profile_table_stride(int nxs) { return nxs > 0 ? ws_js(nxs) : 0; }
+
+extern "C" long long hmv_profile_table_doubles(int nz, int nm, int nxs) {
+  if (nz <= 0 || nm <= 0 || nxs <= 0) return 0;
+  const long long nmp = (long long)cdiv(nm, WS_HB) * WS_HB;
+  return (long long)nz * nmp * (ws_js(nxs) + 4) + 2;       // tab[z][nmp][JS], tmeta[z][nmp][4], slack for 16-byte reads past a row
+}
+
+extern "C" int hmv_profile_tables(int nz, int nm, int nk, const double* zs_d, const double* ks_d, double kmax,
+                                  const double* rs_d, const double* cmax_d, const double* xc_d, const double* alpha_d,
+                                  const double* expo_d, const double* amp_d, const double* outscale_d, double gamma,
+                                  double xmax, int nxs, int do_mass_norm, double* ws_d, double* tab_d, void* stream) {
+  HMV_REQUIRE(tab_d, "hmv_profile_tables: null table array");
+  return profile_transform_impl(nz, nm, nk, (nk + 1) & ~1, zs_d, ks_d, kmax, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d,
+                                outscale_d, nullptr, gamma, xmax, nxs, do_mass_norm, ws_d, nullptr, stream, tab_d, 1);
+}
+
+extern "C" int hmv_profile_expand(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, double kmax,
+                                  const double* rs_d, double xmax, int nxs, double* ws_d, const double* tab_d,
+                                  double* uk_d, void* stream) {
+  HMV_REQUIRE(tab_d, "hmv_profile_expand: null table array");
+  return profile_transform_impl(nz, nm, nk, ldk, zs_d, ks_d, kmax, rs_d, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, 0.0, xmax, nxs, 0, ws_d, uk_d, stream, const_cast<double*>(tab_d), 2);
 }

@@ -111,6 +111,23 @@ int hmv_profile_transform_samples(int nz, int nm, int nk, int ldk, const double*
                                   const double* outscale_d, double xmax, int nxs, int do_mass_norm, double* ws_d,
                                   double* uk_d, void* stream);
 
+/* ---- Table mode of the transform: the same persistent kernel split around a table array that stays on the device ----
+ * hmv_profile_tables runs the evaluation + sine sums only and leaves, per halo, the normalised bins u_j (j <= the bin
+ * count the k range needs) in tab_d[z][nmp][JS] (nmp = nm rounded up to 16, JS = hmv_profile_table_stride(nxs)) followed
+ * by {k -> bin factor r_s(1+z)/kt_1, u_1, bin count, 0} per halo; hmv_profile_expand interpolates such tables onto ks
+ * (fft.py:97-115) and writes the cube.  tables + expand == hmv_profile_transform bit for bit.  Consumers that only
+ * need sums over M (hmv_power_six_tab, hmv_power_tab) interpolate from the tables themselves: the 8*nk-byte row of
+ * every halo is then neither written nor re-read. */
+long long hmv_profile_table_stride(int nxs);
+long long hmv_profile_table_doubles(int nz, int nm, int nxs);
+int hmv_profile_tables(int nz, int nm, int nk, const double* zs_d, const double* ks_d, double kmax,
+                       const double* rs_d, const double* cmax_d, const double* xc_d, const double* alpha_d,
+                       const double* expo_d, const double* amp_d, const double* outscale_d, double gamma,
+                       double xmax, int nxs, int do_mass_norm, double* ws_d, double* tab_d, void* stream);
+int hmv_profile_expand(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d, double kmax,
+                       const double* rs_d, double xmax, int nxs, double* ws_d, const double* tab_d, double* uk_d,
+                       void* stream);
+
 /* ---- a9: HOD occupations and their mass integrals  (hmvec.py:634-731, 462-466, 936-957) -------------
  * hodp[8] = (sig_log_mstellar, alphasat, Bsat, betasat, Bcut, betacut, Msat_override or <=0, Mcut_override or <=0)
  * corr: 0 = "max", 1 = "min".  Outputs [nz,nm]: Nc, Ns, NsNsm1, NcNs; [nz]: ngal, bg. */
@@ -177,6 +194,15 @@ int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const dou
                   long long spec_stride /* doubles between spectra in the outputs; 0 = nz*nk.  A caller working
                                            through z in chunks passes the full-grid stride and offset pointers */,
                   double* p1h_d, double* p2h_d, void* stream);
+
+/* hmv_power_six with the electron profile given as bin tables (hmv_profile_tables, same nxs) instead of a cube:
+ * reference hmvec.py:504-572 for the six pairs, fft.py:97-115 for the interpolation done inside the reduction. */
+long long hmv_power_six_tab_ws_doubles(int nz, int nm, int nk);
+int hmv_power_six_tab(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d, const double* nzm_d,
+                      const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, const double* um_d,
+                      const double* etab_d, int nxs, const double* Nc_d, const double* Ns_d, const double* NcNs_d,
+                      const double* NsNsm1_d, const double* ngal_d, double* ws_d, long long spec_stride,
+                      double* p1h_d, double* p2h_d, void* stream);
 
 /* Spectra-only fusion of a4 + a12-a14: the same six spectra with the analytic NFW matter profile (hmvec.py:346-353,
  * from cs_d, rvir_d as in hmv_uk_nfw) evaluated inside the mass reduction instead of read from a cube; only the

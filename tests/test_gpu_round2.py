@@ -121,3 +121,53 @@ def test_device_cubes_validate_user_tensors(hm, golden_mini):
     assert_close(h.get_power_1halo("view"), h.get_power_1halo("nfw"), 1e-12)
     with pytest.raises(ValueError):
         h.uk_profiles["bad"] = torch.zeros((h._nz, h._nm + 1, h._ldk), dtype=torch.float64, device=u.device)
+
+
+def test_transform_table_mode_and_fused_six():
+    """hmv_profile_tables + hmv_profile_expand reproduce hmv_profile_transform bit for bit (ragged grid: nm not a
+    multiple of 16, odd nk), and hmv_power_six_tab -- the electron profile interpolated from the tables inside the mass
+    reduction -- gives the spectra of hmv_power_six on the expanded cube."""
+    import torch
+    from hmvec_b200 import _capi as capi, pipeline
+    zs = np.array([0.1, 1.3, 2.9]); ms = np.geomspace(1e11, 5e15, 41); ks = np.geomspace(1e-3, 30., 333)
+    g = pipeline.GridSix(pipeline.make_inputs(zs, ms, ks, ngal=np.array([1e-3, 1e-4, 1e-5])))
+    g.upload(); g.run(); torch.cuda.synchronize()
+    L, d, ptr, st = capi.lib, g.d, capi.ptr, capi.stream()
+    nz, nm, nk, ldk = g.nz, g.nm, g.nk, g.ldk
+    E = lambda n: torch.empty(int(n), dtype=torch.float64, device=g.ue.device)
+    tab = E(L.hmv_profile_table_doubles(nz, nm, g.nxs))
+    capi.check(L.hmv_profile_tables(nz, nm, nk, ptr(d["zs"]), ptr(d["ks"]), g.kmax, ptr(d["rs"]), ptr(d["cmax"]),
+                                    ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]), ptr(d["oscale"]),
+                                    g.gamma, g.xmax, g.nxs, 1, ptr(d["tr_ws"]), ptr(tab), st), "tables")
+    cube = torch.zeros_like(g.ue)
+    capi.check(L.hmv_profile_expand(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), g.kmax, ptr(d["rs"]), g.xmax, g.nxs,
+                                    ptr(d["tr_ws"]), ptr(tab), ptr(cube), st), "expand")
+    assert torch.equal(cube[..., :nk], g.ue[..., :nk])
+    p1, p2 = torch.zeros(6, nz, nk, dtype=torch.float64, device=cube.device), torch.zeros(6, nz, nk, dtype=torch.float64, device=cube.device)
+    ws = E(L.hmv_power_six_tab_ws_doubles(nz, nm, nk))
+    capi.check(L.hmv_power_six_tab(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]), ptr(d["Pzk"]),
+                                   g.rho_m0, float(g.p['kstar_damping']), ptr(g.um), ptr(tab), g.nxs, ptr(d["Nc"]),
+                                   ptr(d["Ns"]), ptr(d["NcNs"]), ptr(d["NsNsm1"]), ptr(d["ngal"]), ptr(ws), 0, ptr(p1),
+                                   ptr(p2), st), "six_tab")
+    g1, g2, _, _ = g.spectra()
+    for i, tag in enumerate(("mm", "ee", "me", "gg", "gm", "ge")):
+        assert_close(p1[i].cpu().numpy(), g1[tag], 1e-12, name="P1h_" + tag)
+        assert_close(p2[i].cpu().numpy(), g2[tag], 1e-12, name="P2h_" + tag)
+
+
+def test_nfw_polynomial_and_series_paths_agree(hm):
+    """The two evaluations of the analytic NFW profile (piecewise polynomials with the tensor-core pre-pass, the
+    default; Maclaurin series + Si/Ci) against each other and on an unsorted wavenumber axis."""
+    from hmvec_b200 import _capi as capi
+    zs = np.array([0.0, 0.7, 3.0]); ms = np.geomspace(1e10, 1e16, 37)
+    rng = np.random.default_rng(5)
+    for ks in (np.geomspace(1e-4, 300., 1001), rng.permutation(np.geomspace(1e-3, 100., 515))):
+        cubes = []
+        for mode in (1, 0):
+            capi.check(capi.lib.hmv_set_nfw_mode(mode), "hmv_set_nfw_mode")
+            try:
+                h = hm.HaloModel(zs, ks, ms=ms, accuracy='low')
+                cubes.append(h.uk_profiles['nfw'])
+            finally:
+                capi.lib.hmv_set_nfw_mode(0)
+        assert_close(cubes[1], cubes[0], 1e-9, 2e-11, name="uk_nfw poly vs series")
