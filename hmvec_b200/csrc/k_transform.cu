@@ -66,10 +66,27 @@ __global__ void sine_table_kernel(int N, double2* __restrict__ tab, double kt1, 
   }
 }
 
+// max(ks) on the device: the bin counts must cover the largest wavenumber whatever kmax the caller passed
+__global__ void kmax_kernel(int nk, const double* __restrict__ ks, double* __restrict__ out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) m = fmax(m, ks[k]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+    *out = m;
+  }
+}
+
 // bins needed by each CTA (group of HB halos): jn = floor(kmax * max_h(rs (1+z)) / kt_1) + 2, capped at N/2
-__global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double kmax, double kt1,
+__global__ void bin_count_kernel(int nz, int nm, int nmg, int HB, int J, double kmax_host, double kt1,
                                  const double* __restrict__ zs, const double* __restrict__ rs,
-                                 int* __restrict__ jn_cta, int* __restrict__ work_counter) {
+                                 int* __restrict__ jn_cta, int* __restrict__ work_counter,
+                                 const double* __restrict__ kmax_dev) {
+  const double kmax = fmax(kmax_host, *kmax_dev);
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) *work_counter = 0;                // queue head of the persistent kernel
   if (b >= nz * nmg) return;
@@ -1167,8 +1184,10 @@ static int profile_transform_impl(int nz, int nm, int nk, int ldk, const double*
   cudaStream_t st = (cudaStream_t)stream;
   auto bin_counts = [&](int HB) {
     const int nmg = cdiv(nm, HB);
+    double* kmax_dev = reinterpret_cast<double*>(counter) + 1;       // second double of the queue-head slot
+    kmax_kernel<<<1, 1024, 0, st>>>(nk, ks_d, kmax_dev);
     bin_count_kernel<<<cdiv((long long)nz * nmg, 256), 256, 0, st>>>(nz, nm, nmg, HB, p.J, kmax, p.kt1, zs_d, rs_d, jn_cta,
-                                                                     counter);
+                                                                     counter, kmax_dev);
     return check_launch("bin_count_kernel");
   };
   const bool aligned16 = (((size_t)ks_d | (size_t)uk_d | (size_t)ws_d | (size_t)tab_d) & 15) == 0 && (ldk & 1) == 0;

@@ -69,7 +69,7 @@ long long hmv_uk_nfw_ws_doubles(int nz, int nm, int nk);
  * A/B measurements and as the cross-check of the polynomial tables).  Both agree to ~1e-11 of max|u|. */
 int hmv_set_nfw_mode(int mode);
 int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
-               double kmax /* >= max(ks): lets whole rows skip the Si/Ci pass */, const double* cs_d,
+               double kmax /* used only by the series + Si/Ci mode (>= max(ks)); the default path reduces ks on the device */, const double* cs_d,
                const double* rvir_d, double* ws_d, double* uk_d, void* stream);
 
 /* ---- a6: Battaglia GNFW per-halo shape parameters  (hmvec.py:215-249,278-316,800-802,856-860,918-927)
@@ -98,7 +98,7 @@ long long hmv_profile_transform_ws_doubles(int nz, int nm, int nxs);
  * tables); 1 = the earlier four bin-count-class kernels (kept for A/B measurements).  Same results either way. */
 int hmv_set_transform_mode(int mode);
 int hmv_profile_transform(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ks_d,
-                          double kmax /* = max(ks): bounds the bins computed */, const double* rs_d,
+                          double kmax /* hint for max(ks); the kernels also reduce ks on the device and use the larger of the two */, const double* rs_d,
                           const double* cmax_d, const double* xc_d, const double* alpha_d, const double* expo_d,
                           const double* amp_d, const double* outscale_d, double gamma, double xmax, int nxs,
                           int do_mass_norm, double* ws_d, double* uk_d, void* stream);
