@@ -55,6 +55,7 @@ _SIGS = {
                              _p, _p, _p, _p, _p, _p, _p, _p]),
     "hmv_profile_transform_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_set_transform_mode": (_i, [_i]),
+    "hmv_eh98_factor": (_i, [_i, _p, _d, _d, _d, _d, _i, _d, _d, _d, _p, _p]),
     "hmv_profile_table_stride": (_ll, [_i]),
     "hmv_profile_table_doubles": (_ll, [_i, _i, _i]),
     "hmv_profile_tables": (_i, [_i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),

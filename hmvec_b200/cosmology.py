@@ -284,6 +284,21 @@ class Cosmology(object):
         pref = 8 * np.pi ** 2 * self.params['As'] / 25. / omh2 ** 2. * cspeed ** 4.
         return Dzs ** 2., pref * kfacts * tk ** 2.
 
+    def P_lin_approx_factors_device(self, ks_d, zs, type='eisenhu_osc'):
+        """The same two factors with the O(nk) one -- EH98 transfer function included -- evaluated on the device
+        (hmv_eh98_factor) from a wavenumber tensor; returns (D(z)^2 as numpy [nz], v(k) as a CUDA tensor [nk])."""
+        zs = np.atleast_1d(np.asarray(zs, dtype=np.float64))
+        Dzs = self.D_growth(1 / (1 + zs), type='anorm')
+        kp, ns = self.params['pivot_scalar'], self.params['ns']
+        omh2 = (self.params['omch2'] + self.params['ombh2']) * 100 ** 2. + self.get_Omega_nu() * self.params['H0'] ** 2.
+        pref = 8 * np.pi ** 2 * self.params['As'] / 25. / omh2 ** 2. * cspeed ** 4.
+        v_d = torch.empty(ks_d.numel(), dtype=torch.float64, device=ks_d.device)
+        capi.check(capi.lib.hmv_eh98_factor(ks_d.numel(), capi.ptr(ks_d), float(self.h), float(self.params['omch2']),
+                                            float(self.params['ombh2']), float(self.omm0), int(type == 'eisenhu_osc'),
+                                            float(pref), float(kp), float(ns), capi.ptr(v_d), capi.stream()),
+                   "hmv_eh98_factor")
+        return Dzs ** 2., v_d
+
     def P_lin_approx(self, ks, zs, type='eisenhu_osc'):
         """cosmology.py:391-402"""
         d2, v = self.P_lin_approx_factors(ks, zs, type=type)

@@ -89,6 +89,72 @@ __global__ void sum2_kernel(long long n, const double* __restrict__ a, const dou
   if (i < n) out[i] = a[i] + b[i];
 }
 
+
+// ---- Eisenstein & Hu 1998 transfer function (CDM + baryons with acoustic oscillations, eqs. 2-24; the zero-baryon
+// shape fit, eqs. 28-31, when wiggles == 0) and the k-dependent factor of the separable accuracy='low' power
+//      v(k) = pref k (k/kp)^(ns-1) T(k)^2            (reference cosmology.py:391-402 with Tk of :404-504)
+// evaluated on the device: the host then only supplies D(z)^2 and the scalars (a numpy EH98 on 2 x 10000 wavenumbers
+// costs the host 2 ms per HaloModel, more than a rank's whole device step on eight GPUs).
+__global__ void eh98_factor_kernel(int nk, const double* __restrict__ ks, double h, double omch2, double ombh2,
+                                   double omm0, int wiggles, double pref, double kp, double ns, double tcmb,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk) return;
+  const double kmpc = ks[i], k = kmpc / h;                 // h/Mpc
+  const double wm = omch2 + ombh2, wb = ombh2, fb = wb / wm, fc = omch2 / wm;
+  const double t2 = (tcmb / 2.7) * (tcmb / 2.7);
+  const double k_eq = 7.46e-2 * wm / t2 / h;               // eq. 3
+  const double z_eq = 2.50e4 * wm / (t2 * t2);             // eq. 2
+  const double zb1 = 0.313 * pow(wm, -0.419) * (1.0 + 0.607 * pow(wm, 0.674));
+  const double zb2 = 0.238 * pow(wm, 0.223);
+  const double z_d = 1291.0 * pow(wm, 0.251) / (1.0 + 0.659 * pow(wm, 0.828)) * (1.0 + zb1 * pow(wb, zb2));   // eq. 4
+  const double Rd = 31.5 * wb / (t2 * t2) * (1.0e3 / z_d);  // eq. 5
+  const double Req = 31.5 * wb / (t2 * t2) * (1.0e3 / z_eq);
+  const double s = 2.0 / (3.0 * k_eq) * sqrt(6.0 / Req) * log((sqrt(1.0 + Rd) + sqrt(Req + Rd)) / (1.0 + sqrt(Req)));   // eq. 6
+  const double k_silk = 1.6 * pow(wb, 0.52) * pow(wm, 0.73) * (1.0 + pow(10.4 * wm, -0.95)) / h;                        // eq. 7
+  double T;
+  if (!wiggles) {
+    const double ag = 1.0 - 0.328 * log(431.0 * wm) * fb + 0.38 * log(22.3 * wm) * fb * fb;                              // eq. 31
+    const double ks4 = (0.43 * k * s) * (0.43 * k * s) * (0.43 * k * s) * (0.43 * k * s);
+    const double geff = omm0 * h * (ag + (1.0 - ag) / (1.0 + ks4));                                                      // eq. 30
+    const double q = k * t2 / geff;
+    const double L = log(2.0 * M_E + 1.8 * q);
+    const double Cq = 14.2 + 731.0 / (1.0 + 62.5 * q);
+    T = L / (L + Cq * q * q);                                                                                            // eq. 29
+  } else {
+    auto T0 = [&](double alpha, double beta) {              // eqs. 10, 19, 20
+      const double q = k / (13.41 * k_eq);
+      const double L = log(M_E + 1.8 * beta * q);
+      const double Cq = 14.2 / alpha + 386.0 / (1.0 + 69.9 * pow(q, 1.08));
+      return L / (L + Cq * q * q);
+    };
+    const double a1 = pow(46.9 * wm, 0.670) * (1.0 + pow(32.1 * wm, -0.532));   // eqs. 11, 12
+    const double a2 = pow(12.0 * wm, 0.424) * (1.0 + pow(45.0 * wm, -0.582));
+    const double alpha_c = pow(a1, -fb) * pow(a2, -(fb * fb * fb));
+    const double b1 = 0.944 / (1.0 + pow(458.0 * wm, -0.708));
+    const double b2 = pow(0.395 * wm, -0.0266);
+    const double beta_c = 1.0 / (1.0 + b1 * (pow(fc, b2) - 1.0));
+    const double ksf = k * s / 5.4;
+    const double f = 1.0 / (1.0 + ksf * ksf * ksf * ksf);   // eq. 18
+    const double Tc = f * T0(1.0, beta_c) + (1.0 - f) * T0(alpha_c, beta_c);     // eq. 17
+    const double y = (1.0 + z_eq) / (1.0 + z_d);
+    const double sq = sqrt(1.0 + y);
+    const double G = y * (-6.0 * sq + (2.0 + 3.0 * y) * log((sq + 1.0) / (sq - 1.0)));   // eq. 15
+    const double alpha_b = 2.07 * k_eq * s * pow(1.0 + Rd, -0.75) * G;          // eq. 14
+    const double beta_node = 8.41 * pow(wm, 0.435);         // eq. 23
+    const double bn = beta_node / (k * s);
+    const double s_t = s / cbrt(1.0 + bn * bn * bn);        // eq. 22
+    const double beta_b = 0.5 + fb + (3.0 - 2.0 * fb) * sqrt((17.2 * wm) * (17.2 * wm) + 1.0);   // eq. 24
+    const double bb = beta_b / (k * s);
+    const double x = k * s_t;
+    const double sinc = (x == 0.0) ? 1.0 : sin(x) / x;
+    const double ks2 = (k * s / 5.2) * (k * s / 5.2);
+    const double Tb = (T0(1.0, 1.0) / (1.0 + ks2) + alpha_b / (1.0 + bb * bb * bb) * exp(-pow(k / k_silk, 1.4))) * sinc;   // eq. 21
+    T = fb * Tb + fc * Tc;                                  // eq. 16
+  }
+  out[i] = pref * pow(kmpc / kp, ns - 1.0) * kmpc * T * T;
+}
+
 }  // namespace hmv
 using namespace hmv;
 
@@ -104,6 +170,15 @@ extern "C" int hmv_pk_spline(int nz, int nk, const double* zs_d, const double* k
   pk_spline_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(nz, nk, zs_d, ks_d, nx, ny, kx, ky, tx_d, ty_d, c_d, islog,
                                                             scale, out_d);
   return check_launch("pk_spline_kernel");
+}
+
+extern "C" int hmv_eh98_factor(int nk, const double* ks_d, double h, double omch2, double ombh2, double omm0,
+                               int wiggles, double pref, double kp, double ns, double* out_d, void* stream) {
+  HMV_REQUIRE(nk > 0 && ks_d && out_d, "hmv_eh98_factor: bad arguments");
+  HMV_REQUIRE(h > 0 && omch2 > 0 && ombh2 > 0, "hmv_eh98_factor: need h, omch2, ombh2 > 0");
+  eh98_factor_kernel<<<cdiv(nk, 128), 128, 0, (cudaStream_t)stream>>>(nk, ks_d, h, omch2, ombh2, omm0, wiggles, pref, kp, ns,
+                                                                       2.726, out_d);
+  return check_launch("eh98_factor_kernel");
 }
 
 extern "C" int hmv_outer(int nz, int nk, const double* a_d, const double* b_d, double* out_d, void* stream) {

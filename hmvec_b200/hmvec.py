@@ -268,10 +268,11 @@ class HaloModel(Cosmology):
     def _plin_device(self, ks, zs):
         """accuracy='low': EH98 P(z,k) = D(z)^2 v(k) (cosmology.py:391-402) formed on the device from its two factor
         vectors -- O(nz)+O(nk) host work, no [nz,nk] array on the host or on PCIe."""
-        d2, v = self.P_lin_approx_factors(ks, zs)
-        out = self._empty(d2.size, v.size)
-        d2_d, v_d = self._dev(d2), self._dev(v)          # named: a temporary's block would be recycled at once
-        capi.check(capi.lib.hmv_outer(d2.size, v.size, capi.ptr(d2_d), capi.ptr(v_d), capi.ptr(out), capi.stream()),
+        ks_d = self._ks_d if ks is self._ks64 else self._dev(np.asarray(ks, dtype=np.float64).reshape(-1))
+        d2, v_d = self.P_lin_approx_factors_device(ks_d, zs)       # EH98 itself runs on the device too
+        out = self._empty(d2.size, v_d.numel())
+        d2_d = self._dev(d2)                             # named: a temporary's block would be recycled at once
+        capi.check(capi.lib.hmv_outer(d2.size, v_d.numel(), capi.ptr(d2_d), capi.ptr(v_d), capi.ptr(out), capi.stream()),
                    "hmv_outer")
         return out
 

@@ -249,6 +249,10 @@ int hmv_pk_spline(int nz, int nk, const double* zs_d, const double* ks_d, int nx
                   const double* tx_d, const double* ty_d, const double* c_d, int islog, double scale, double* out_d,
                   void* stream);
 
+/* v(k) = pref k (k/kp)^(ns-1) T_EH98(k)^2: the wavenumber factor of the separable accuracy='low' linear power
+ * (reference cosmology.py:391-402, Tk :404-504; Eisenstein & Hu 1998 with oscillations, or the no-wiggle fit). */
+int hmv_eh98_factor(int nk, const double* ks_d, double h, double omch2, double ombh2, double omm0, int wiggles,
+                    double pref, double kp, double ns, double* out_d, void* stream);
 /* accuracy='low' linear power (cosmology.py:391-402) is separable, P(z,k) = D(z)^2 * [pref k (k/kp)^(ns-1) T(k)^2]:
  * out[z][k] = a[z] * b[k] from the two host-side factor vectors, so that neither Pzk [nz,nk] nor the sigma^2 spectrum
  * [nz,sigma2_numks] crosses PCIe. */

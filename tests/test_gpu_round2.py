@@ -171,3 +171,18 @@ def test_nfw_polynomial_and_series_paths_agree(hm):
             finally:
                 capi.lib.hmv_set_nfw_mode(0)
         assert_close(cubes[1], cubes[0], 1e-9, 2e-11, name="uk_nfw poly vs series")
+
+
+def test_eh98_on_the_device(hm):
+    """hmv_eh98_factor (Eisenstein & Hu 1998 on the device, both the oscillating and the no-wiggle form) against the
+    host-side factors, which tests/test_host_logic.py pins to the reference's Tk / P_lin_approx."""
+    import torch
+    c = hm.Cosmology({}, None, accuracy='low')
+    ks = np.geomspace(1e-5, 300., 4001)
+    zs = np.array([0.0, 0.5, 3.0])
+    ks_d = torch.as_tensor(ks, device="cuda")
+    for typ in ('eisenhu_osc', 'eisenhu'):
+        d2h, vh = c.P_lin_approx_factors(ks, zs, type=typ)
+        d2d, vd = c.P_lin_approx_factors_device(ks_d, zs, type=typ)
+        assert_close(d2d, d2h, 1e-14, name="growth")
+        assert_close(vd.cpu().numpy(), vh, 1e-11, name="EH98 " + typ)
