@@ -267,7 +267,7 @@ def run_b200(a):
     zc = zshard.ZComm(a.nz, None) if world > 1 else None
     sl = zc.slab if zc is not None else slice(0, a.nz)
     g = pipeline.GridSix(pipeline.slab_inputs(inp, sl), device=dev, zcomm=zc, nz_total_zs=zs,
-                         fused_nfw=a.fused_nfw)
+                         fused_nfw=a.fused_nfw, tsz_tables=not a.tsz_cube)
     capi.check(capi.lib.hmv_set_transform_mode(a.transform_mode), "hmv_set_transform_mode")
     g.transform_mode = a.transform_mode
     g.upload()
@@ -345,6 +345,11 @@ def run_b200(a):
     k1_flop = k1_flops(g.d["rs"], g.d["cmax"], g.xmax, g.nxs)
     k1p_flop = k1_flops(g.d["y_rs"], g.d["y_cmax"], g.p_xmax, g.p_nxs) if g.tsz else 0.0
     fused_nfw, ldk, mode = g.fused_nfw, g.ldk, g.transform_mode
+    tsz_tables = g.tsz_tables
+    ytab_bytes = 0.0
+    if tsz_tables:      # bins the Compton-y tables actually hold: sum over halos of (bin count + 2) doubles
+        ytab_bytes = 8.0 * float(np.sum(np.minimum(g.p_nxs // 2, np.floor(g.kmax * g.d["y_rs"].cpu().numpy() *
+                                 (1.0 + g.d["zs"].cpu().numpy()[:, None]) / (2.0 * np.pi / (g.p_nxs * ((g.p_xmax - g.p_xmax / g.p_nxs) / g.p_nxs)))) + 2.0) + 2.0))
     del g
     torch.cuda.empty_cache()
 
@@ -396,12 +401,14 @@ def run_b200(a):
     alg_bytes = {
         "uk_nfw": 8.0 * nzl * nm * nk,                                  # store of the cube (K2; FP64-pipe bound)
         "uk_electron": 8.0 * nzl * nm * nk,                             # store of the cube (K1; FP64-pipe bound)
-        "uk_pressure": 8.0 * nzl * nm * nk,                             # second K1 launch (tSZ)
+        # second K1 launch (tSZ): the cube, or -- table mode -- only the bin tables (then FP64-bound, not a store)
+        "uk_pressure": ytab_bytes if tsz_tables else 8.0 * nzl * nm * nk,
         # two-cube kernel: read 2 cubes once, write 12 spectra, read Pzk.  Fused kernel: one cube + 448 B of per-halo
         # coefficient/NFW records per (z,M) for each of the ceil(nk/512) k tiles
         "power_six": (nzl * nk * (16.0 * nm + 96.0 + 8.0) if not fused_nfw else
                       nzl * nk * (8.0 * nm + 96.0 + 8.0) + 448.0 * nzl * nm * ((ldk + 511) // 512)),
-        "power_yy": nzl * nk * (8.0 * nm + 16.0 + 8.0),                 # one cube read, P1h + P2h written
+        # one cube read, P1h + P2h written; table mode: every k tile reads its segment of the tables (~ the tables once)
+        "power_yy": (ytab_bytes + nzl * nk * 24.0) if tsz_tables else nzl * nk * (8.0 * nm + 16.0 + 8.0),
         "sigma2": 8.0 * (nzl * 10000 + 2.0 * 10000 * nm + nzl * nm),    # sPzk + W2 table write/read + sigma2 out
     }
     if fused_nfw:
@@ -429,16 +436,27 @@ def run_b200(a):
         pass
     dom = max(alg_bytes, key=lambda n: kernels[n]["ms"])
     if dom in ("uk_electron", "uk_pressure"):
-        kd = kernels[dom]
-        roof = {"kernel": "%s (K1 %s, FP64 mma.sync m8n8k4)" % ("profile_transform_ws_kernel" if mode == 0 else "profile_transform_kernel", dom),
-                "bound": "tensor", "achieved": kd["tflops"], "peak": dmma_tf, "unit": "TFLOP/s",
-                "frac": kd["frac_fp64_tensor"],
+        # the transform kernel is launched once (electron) or twice (electron + pressure) per step: the roofline entry
+        # is the kernel's AVERAGE launch -- algorithmic flops per launch over the average launch duration
+        launches_k1 = [kernels[n] for n in ("uk_electron", "uk_pressure") if kernels[n].get("alg_flop")]
+        nl = len(launches_k1)
+        fl = sum(k["alg_flop"] for k in launches_k1) / nl
+        msl = sum(k["ms"] for k in launches_k1) / nl
+        tf = fl / (msl * 1e-3) / 1e12
+        roof = {"kernel": "%s (K1, FP64 mma.sync m8n8k4; average of its %d launches per step)" % (
+                    "profile_transform_ws_kernel" if mode == 0 else "profile_transform_kernel", nl),
+                "bound": "tensor", "achieved": tf, "peak": dmma_tf, "unit": "TFLOP/s", "frac": tf / dmma_tf,
                 "peak_source": "FP64 DMMA peak measured in this run (hmv_bench_dmma); MEASURED_PEAKS.json has no FP64 figure",
-                "alg_flop_per_launch": kd["alg_flop"], "hbm_store_frac": kd["frac_hbm"]}
+                "alg_flop_per_launch": fl,
+                "hbm_store_frac": kernels["uk_electron"]["frac_hbm"],     # of the launch that stores a cube
+                "launches": {n: {"ms": kernels[n]["ms"], "frac": kernels[n]["frac_fp64_tensor"]}
+                             for n in ("uk_electron", "uk_pressure") if kernels[n].get("alg_flop")}}
+        kernels_dom_ms = msl
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_hbm"], "peak_source": peak_src, "alg_bytes_per_launch": alg_bytes[dom]}
-    roof.update(ms_per_launch=kernels[dom]["ms"], traffic=traffic.get(dom) if world == 1 else None,
+    roof.update(ms_per_launch=kernels_dom_ms if dom in ("uk_electron", "uk_pressure") else kernels[dom]["ms"],
+                traffic=traffic.get(dom) if world == 1 else None,
                 fp64_dfma_peak_tflops_measured=fp64_tf, fp64_dmma_peak_tflops_measured=dmma_tf)
     # the HBM-bound kernel of the path, for reference beside the dominant one
     roof["hbm_kernel"] = {"kernel": "power_six_nfw_kernel (K5+K2 fused)" if fused_nfw else "power_six_kernel (K5)", "achieved": kernels["power_six"]["gbs"], "peak": hbm_peak,
@@ -447,11 +465,12 @@ def run_b200(a):
 
     # SURVEY 8(d) whole-workload traffic, extended by the tSZ leg: 3 cubes written once; NFW + electron read once by the
     # six-spectra pass, pressure read once by the yy pass; 14 spectra written
-    wl_bytes = 8.0 * a.nz * a.nm * a.nk * 6 + 2 * NSPEC * 8.0 * a.nz * a.nk
+    wl_bytes = 8.0 * a.nz * a.nm * a.nk * (4 if tsz_tables else 6) + 2 * NSPEC * 8.0 * a.nz * a.nk + 2.0 * ytab_bytes * world
     roof["workload"] = {"alg_bytes_per_step": wl_bytes, "achieved": wl_bytes / (ms_total / a.steps * 1e-3) / 1e9 / world,
                         "peak": hbm_peak, "unit": "GB/s per GPU",
                         "frac": wl_bytes / (ms_total / a.steps * 1e-3) / 1e9 / world / hbm_peak,
-                        "note": "SURVEY 8(d) algorithmic traffic of the whole step incl. the tSZ leg (3 cubes written + "
+                        "note": ("table mode: the Compton-y profile stays in its bin tables, 2 cubes written + read once; " if tsz_tables else "") +
+                                "SURVEY 8(d) algorithmic traffic of the whole step incl. the tSZ leg (3 cubes written + "
                                 "read once, 14 spectra) over the step time"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -459,7 +478,9 @@ def run_b200(a):
             "config": {"workload": workload_name(a), "parallelism": "z-sharded x%d" % world,
                        "nfw": "evaluated inside the mass reduction (spectra-only fusion)" if fused_nfw else
                               "cube materialised in HBM",
-                       "l2": "inputs exceed L2 (three %.1f GB cubes per rank)" % (8e-9 * nzl * nm * ldk)},
+                       "tsz": "Compton-y profile kept as bin tables, P_yy reduced from them (no third cube)" if tsz_tables else
+                              "Compton-y cube materialised",
+                       "l2": "inputs exceed L2 (%s %.1f GB cubes per rank)" % ("two" if tsz_tables else "three", 8e-9 * nzl * nm * ldk)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_api * world / a.steps),
                     "d2h_bytes_per_step": int(d2h_api * world / a.steps), "ms_per_step": ms_api / a.steps,
                     "path": "drop-in API: HaloModel -> add_battaglia_profile -> add_battaglia_pres_profile -> "
@@ -499,6 +520,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--transform-mode", type=int, default=0, choices=[0, 1],
                     help="K1 launch plan: 0 = persistent kernel (default), 1 = bin-count-class kernels")
+    ap.add_argument("--tsz-cube", action="store_true",
+                    help="materialise the Compton-y cube (hmv_profile_transform + hmv_power) instead of the table path")
     ap.add_argument("--fused-nfw", action="store_true",
                     help="evaluate the NFW profile inside the mass reduction (hmv_power_six_nfw) instead of writing "
                          "its cube to HBM and reading it back (hmv_uk_nfw + hmv_power_six, the faster default)")

@@ -60,6 +60,7 @@ _SIGS = {
     "hmv_profile_table_doubles": (_ll, [_i, _i, _i]),
     "hmv_profile_tables": (_i, [_i, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p, _p, _p, _d, _d, _i, _i, _p, _p, _p]),
     "hmv_profile_expand": (_i, [_i, _i, _i, _i, _p, _p, _d, _p, _d, _i, _p, _p, _p, _p]),
+    "hmv_power_tab": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _d, _d, _i, _p, _i, _p, _p, _p, _p]),
     "hmv_power_six_tab_ws_doubles": (_ll, [_i, _i, _i]),
     "hmv_power_six_tab": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _d, _d, _p, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _p, _p]),
     "hmv_set_nfw_mode": (_i, [_i]),

@@ -607,6 +607,135 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Auto spectrum of ONE profile given as bin tables (hmv_profile_tables) -- the tSZ case: P_yy needs the Compton-y
+// profile only under the mass integral, so its 32 GB cube is neither written nor read.  Nothing is streamed: a CTA
+// (z, 512-wide k tile) keeps the redshift's per-halo parameters in shared memory, sorts the halos into those whose
+// whole tile lies below the first bin (u = u_1: their contribution does not depend on k and is summed once per CTA),
+// above the last bin (u = 0: nothing) and the rest, and loops over the rest only, each thread interpolating its two
+// wavenumbers from the halo's table row in L2 exactly as the transform's expansion does (fft.py:102-107).
+// Work is proportional to the interpolated elements (37 % on the LARGE grid).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OT_K = 512, OT_T = 256;
+
+struct OneTabArgs {
+  int nm, nk, nmp, JS, J;
+  const double *coef, *zoff, *ks, *Pzk, *tab, *tmeta;
+  double kstar;
+  double *p1h, *p2h;
+};
+
+__global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs a) {
+  extern __shared__ __align__(16) unsigned char ot_smem[];
+  double4* prm = reinterpret_cast<double4*>(ot_smem);              // per interpolated halo: {inv, u_1, a, b} (t = a + b u)
+  double2* prm2 = reinterpret_cast<double2*>(prm + a.nm);          //                        {c4, w2}
+  int* rowid = reinterpret_cast<int*>(prm2 + a.nm);
+  __shared__ double red[3][OT_T / 32];
+  __shared__ int nlist, wcnt[OT_T / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int z = blockIdx.y, k0 = blockIdx.x * OT_K;
+  const long long zrow = (long long)z * a.nm, zrowp = (long long)z * a.nmp;
+  const double tJ = (double)a.J;
+  // wavenumber range of the tile (any order of ks)
+  double kmn = 1.0e300, kmx = 0.0;
+  for (int k = k0 + tid; k < min(a.nk, k0 + OT_K); k += OT_T) { const double v = a.ks[k]; kmn = fmin(kmn, v); kmx = fmax(kmx, v); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmn = fmin(kmn, __shfl_xor_sync(0xffffffffu, kmn, o));
+    kmx = fmax(kmx, __shfl_xor_sync(0xffffffffu, kmx, o));
+  }
+  if (lane == 0) { red[0][warp] = kmn; red[1][warp] = kmx; }
+  if (tid == 0) nlist = 0;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < OT_T / 32; ++w) { kmn = fmin(kmn, red[0][w]); kmx = fmax(kmx, red[1][w]); }
+  __syncthreads();
+  // classify the halos; hold-u_1 halos are summed here, interpolated ones are appended to the list
+  double h1 = 0.0, hA = 0.0;
+  for (int m0 = 0; m0 < a.nm; m0 += OT_T) {
+    const int m = m0 + tid;
+    bool gen = false;
+    double4 mt = make_double4(0.0, 0.0, 0.0, 0.0);
+    double aA = 0, bA = 0, c4 = 0, w2 = 0;
+    if (m < a.nm) {
+      mt = *reinterpret_cast<const double4*>(a.tmeta + (zrowp + m) * 4);
+      const double2* c = reinterpret_cast<const double2*>(a.coef + (zrow + m) * 8);
+      const double2 c01 = c[0], c45 = c[2];
+      aA = c01.x; bA = c01.y; c4 = c45.x; w2 = c45.y;         // both legs are the same tracer
+      const double tlo = kmn * mt.x, thi = kmx * mt.x;
+      if (thi < 1.0 || tlo > tJ) {
+        const double u = (thi < 1.0) ? mt.y : 0.0;              // the whole tile holds u_1, or is zero
+        const double tA = fma(bA, u, aA);
+        h1 = fma(c4 * tA, tA, h1); hA = fma(w2, tA, hA);
+      } else {
+        gen = true;
+      }
+    }
+    // append in halo order (a fixed order of the list keeps the sums bit-reproducible from run to run)
+    const unsigned bal = __ballot_sync(0xffffffffu, gen);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = nlist, tot = 0;
+#pragma unroll
+    for (int w = 0; w < OT_T / 32; ++w) { base += (w < warp) ? wcnt[w] : 0; tot += wcnt[w]; }
+    __syncthreads();                                       // everyone has read nlist and the counts
+    if (tid == 0) nlist += tot;
+    if (gen) {
+      const int slot = base + __popc(bal & ((1u << lane) - 1u));
+      prm[slot] = make_double4(mt.x, mt.y, aA, bA);
+      prm2[slot] = make_double2(c4, w2);
+      rowid[slot] = (m << 12) | min(a.J - 1, (int)mt.z);         // halo index and bin cap (J - 1 < 4096 checked on the host)
+    }
+  }
+  h1 = warp_sum(h1); hA = warp_sum(hA);
+  if (lane == 0) { red[0][warp] = h1; red[1][warp] = hA; }
+  __syncthreads();
+  h1 = hA = 0.0;
+#pragma unroll
+  for (int w = 0; w < OT_T / 32; ++w) { h1 += red[0][w]; hA += red[1][w]; }
+  const int n = nlist;
+
+  const int kc = min(k0 + 2 * tid, a.nk - 1), kc1 = min(k0 + 2 * tid + 1, a.nk - 1);
+  const double kx = a.ks[kc], ky = a.ks[kc1];
+  double p1x = 0, p1y = 0, iAx = 0, iAy = 0;
+#pragma unroll 4
+  for (int i = 0; i < n; ++i) {
+    const double4 q = prm[i];
+    const double2 q2 = prm2[i];
+    const int id = rowid[i];
+    const int jcap = id & 4095;
+    const double* row = a.tab + (zrowp + (id >> 12)) * (long long)a.JS;
+    const double inv = q.x, u1 = q.y;
+    double ue[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const double t = (e ? ky : kx) * inv;
+      const int jj = min(max(__double2int_rz(fmin(t, tJ)), 1), jcap);
+      const double ua = __ldg(row + jj), ub = __ldg(row + jj + 1);
+      double v = fma(t - (double)jj, ub - ua, ua);
+      v = (t > tJ) ? 0.0 : v;
+      ue[e] = (t >= 1.0) ? v : u1;
+    }
+    const double tAx = fma(q.w, ue[0], q.z), tAy = fma(q.w, ue[1], q.z);
+    p1x = fma(q2.x * tAx, tAx, p1x); p1y = fma(q2.x * tAy, tAy, p1y);
+    iAx = fma(q2.y, tAx, iAx); iAy = fma(q2.y, tAy, iAy);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = k0 + 2 * tid + e;
+    if (k >= a.nk) break;
+    const long long o = (long long)z * a.nk + k;
+    if (a.p1h) {
+      const double r = a.ks[k] / a.kstar;
+      a.p1h[o] = ((e ? p1y : p1x) + h1) * (1.0 - exp(-r * r));                                               // hmvec.py:526
+    }
+    if (a.p2h) {
+      const double I = (e ? iAy : iAx) + hA + a.zoff[2 * z];
+      a.p2h[o] = a.Pzk[o] * I * I;                                                                           // hmvec.py:572
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Spectra-only fusion: the six spectra with the NFW matter profile evaluated IN the reduction instead of being read
 // from a cube.  u_NFW(k|M,z) depends on the halo only through (c, a = r_s (1+z)) and a 42-coefficient series, so a
 // 384-byte per-halo record replaces an 8*nk-byte cube row: the kernel streams only the electron cube (half the
@@ -922,6 +1051,38 @@ extern "C" int hmv_power_six_tab(int nz, int nm, int nk, int ldk, const double* 
   dim3 grid(cdiv(ldk, SIX_K), nz);
   power_six_tab_kernel<<<grid, TAB_CT + 32, TAB_SMEM, st>>>(a);
   return check_launch("power_six_tab_kernel");
+}
+
+extern "C" int hmv_power_tab(int nz, int nm, int nk, const double* ms_d, const double* ks_d, const double* nzm_d,
+                             const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, int kind,
+                             const double* tab_d, int nxs, double* ws_d, double* p1h_d, double* p2h_d, void* stream) {
+  HMV_REQUIRE(nz > 0 && nm >= 2 && nk > 0 && nxs >= 4, "hmv_power_tab: bad sizes");
+  HMV_REQUIRE(nz <= 65535, "hmv_power_tab: nz=%d exceeds grid.y limit 65535", nz);
+  HMV_REQUIRE(kind == 0 || kind == 2, "hmv_power_tab: kind must be 0 (matter profile) or 2 (pressure profile)");
+  HMV_REQUIRE(ms_d && ks_d && nzm_d && bh_d && tab_d && ws_d, "hmv_power_tab: null pointer");
+  HMV_REQUIRE(p2h_d == nullptr || Pzk_d != nullptr, "hmv_power_tab: P2h requested without Pzk");
+  HMV_REQUIRE((((unsigned long long)tab_d | (unsigned long long)ws_d) & 15ull) == 0, "hmv_power_tab: tables and workspace must be 16-byte aligned");
+  HMV_REQUIRE(nxs / 2 <= 4096 && nm < (1 << 19), "hmv_power_tab: nxs <= 8192 and nm < 2^19 (packed row ids)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cs = (long long)nz * nm;
+  double* coef = ws_d;
+  double* zoff = ws_d + 8 * cs;
+  TracerArgs t;
+  t.kind = kind; t.Nc = t.Ns = t.NcNs = t.NsNsm1 = t.ngal = t.bias = nullptr;
+  power_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, t, t, 0, coef, zoff);
+  int rc = check_launch("power_prep_kernel");
+  if (rc) return rc;
+  OneTabArgs a;
+  a.nm = nm; a.nk = nk; a.coef = coef; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar; a.p1h = p1h_d; a.p2h = p2h_d;
+  a.JS = (int)hmv_profile_table_stride(nxs); a.J = nxs / 2; a.nmp = cdiv(nm, 16) * 16;
+  a.tab = tab_d; a.tmeta = tab_d + (size_t)nz * a.nmp * (size_t)a.JS;
+  const size_t smem = (size_t)nm * (sizeof(double4) + sizeof(double2) + sizeof(int)) + 16;
+  if (smem > 200 * 1024) return fail(HMV_E_LIMIT, "hmv_power_tab: nm=%d needs %zu B of shared memory", nm, smem);
+  cudaError_t e = cudaFuncSetAttribute(power_one_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_one_tab_kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+  dim3 grid(cdiv(nk, OT_K), nz);
+  power_one_tab_kernel<<<grid, OT_T, smem, st>>>(a);
+  return check_launch("power_one_tab_kernel");
 }
 
 extern "C" long long hmv_power_six_nfw_ws_doubles(int nz, int nm) {

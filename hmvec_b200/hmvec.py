@@ -49,6 +49,29 @@ def pressure_constants(omb, omm):
     return eFrac * (omb / omm) * 200 * G_newt, 4 * np.pi * (sigmaT / (mElect * constants.c ** 2))
 
 
+class TableProfile(object):
+    """A profile kept as the transform's bin tables (hmv_profile_tables) instead of a [nz,nm,nk] cube: ~1 GB instead of
+    32 GB on the LARGE grid.  Consumers that only integrate over M (the auto spectrum: hmv_power_tab) read the tables;
+    anything that needs u(k|M,z) itself gets the cube, expanded on first use (hmv_profile_expand) and kept."""
+
+    def __init__(self, owner, tab, rs_d, xmax, nxs):
+        self._owner = weakref.proxy(owner)
+        self.tab, self.rs_d, self.xmax, self.nxs = tab, rs_d, float(xmax), int(nxs)
+        self.cube = None
+
+    def materialize(self):
+        if self.cube is None:
+            o = self._owner
+            out = o._cube()
+            ws = o._workspace('transform', capi.lib.hmv_profile_transform_ws_doubles(o._nz, o._nm, self.nxs))
+            capi.check(capi.lib.hmv_profile_expand(o._nz, o._nm, o._nk, o._ldk, capi.ptr(o._zs_d), capi.ptr(o._ks_d),
+                                                   o._kmax, capi.ptr(self.rs_d), self.xmax, self.nxs, capi.ptr(ws),
+                                                   capi.ptr(self.tab), capi.ptr(out), capi.stream()),
+                       "hmv_profile_expand")
+            self.cube = out
+        return self.cube
+
+
 class DeviceCubes(MutableMapping):
     """name -> u(z,M,k) cube resident in HBM ([nz][nm][ldk] float64).  Reading an item returns a numpy
     [nz,nm,nk] copy (what reference callers index); assigning a numpy/torch [nz,nm,nk] array uploads it."""
@@ -58,10 +81,16 @@ class DeviceCubes(MutableMapping):
         self._t = {}
 
     def device(self, name):
-        return self._t[name]
+        t = self._t[name]
+        return t.materialize() if isinstance(t, TableProfile) else t
+
+    def tables(self, name):
+        """The TableProfile behind `name`, or None when the profile is held as a cube."""
+        t = self._t.get(name)
+        return t if isinstance(t, TableProfile) else None
 
     def __getitem__(self, name):
-        t = self._t[name]
+        t = self.device(name)
         o = self._owner
         if o._ldk == o._nk:
             return o._host(t)
@@ -70,6 +99,9 @@ class DeviceCubes(MutableMapping):
     def __setitem__(self, name, value):
         o = self._owner
         o._invalidate_spectra()
+        if isinstance(value, TableProfile):
+            self._t[name] = value
+            return
         if isinstance(value, torch.Tensor) and value.is_cuda:
             # zero-copy only for exactly the layout the kernels read: float64, contiguous [nz][nm][ldk], this device,
             # 16-byte aligned (cp.async.bulk sources); anything else is converted and copied into a fresh cube
@@ -434,9 +466,19 @@ class HaloModel(Cosmology):
                    "hmv_mdelta")
         return m200_d, self._dev(rhoc)
 
-    def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm):
-        out = self._cube()
+    def _transform(self, rs_d, cmax_d, xc_d, alpha_d, expo_d, amp_d, oscale_d, gamma, xmax, nxs, mass_norm,
+                   tables=False):
         ws = self._workspace('transform', capi.lib.hmv_profile_transform_ws_doubles(self._nz, self._nm, int(nxs)))
+        if tables and int(nxs) // 2 <= 4096 and self._nm * 28 + 16 <= 200 * 1024:
+            # keep the bin tables only (see TableProfile); limits are those of hmv_power_tab
+            tab = self._empty(int(capi.lib.hmv_profile_table_doubles(self._nz, self._nm, int(nxs))))
+            capi.check(capi.lib.hmv_profile_tables(
+                self._nz, self._nm, self._nk, capi.ptr(self._zs_d), capi.ptr(self._ks_d), self._kmax, capi.ptr(rs_d),
+                capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d), capi.ptr(expo_d), capi.ptr(amp_d),
+                capi.ptr(oscale_d), float(gamma), float(xmax), int(nxs), int(bool(mass_norm)), capi.ptr(ws),
+                capi.ptr(tab), capi.stream()), "hmv_profile_tables")
+            return TableProfile(self, tab, rs_d, xmax, nxs)
+        out = self._cube()
         capi.check(capi.lib.hmv_profile_transform(
             self._nz, self._nm, self._nk, self._ldk, capi.ptr(self._zs_d), capi.ptr(self._ks_d),
             self._kmax, capi.ptr(rs_d), capi.ptr(cmax_d), capi.ptr(xc_d), capi.ptr(alpha_d),
@@ -444,7 +486,7 @@ class HaloModel(Cosmology):
             int(bool(mass_norm)), capi.ptr(ws), capi.ptr(out), capi.stream()), "hmv_profile_transform")
         return out
 
-    def _gnfw(self, kind, fit9, gamma, pres_alpha, amp_const, pref, xmax, nxs):
+    def _gnfw(self, kind, fit9, gamma, pres_alpha, amp_const, pref, xmax, nxs, tables=False):
         m200_d, rhoc_d = self._m200c_device()
         hofz_d = self._dev(self.h_of_z(self.zs))
         outs = [self._empty(self._nz, self._nm) for _ in range(7)]
@@ -454,7 +496,8 @@ class HaloModel(Cosmology):
                                             float(pref), *[capi.ptr(o) for o in outs], capi.stream()),
                    "hmv_gnfw_params")
         rs, cmax, xc, alpha, expo, amp, oscale = outs
-        return self._transform(rs, cmax, xc, alpha, expo, amp, oscale, gamma, xmax, nxs, mass_norm=(kind == 0))
+        return self._transform(rs, cmax, xc, alpha, expo, amp, oscale, gamma, xmax, nxs, mass_norm=(kind == 0),
+                               tables=tables)
 
     def add_battaglia_profile(self, name, family=None, param_override=None, nxs=None, xmax=None,
                               ignore_existing=False):
@@ -499,8 +542,10 @@ class HaloModel(Cosmology):
                     pparams[key] = param_override[key]
         fit9 = [pparams[q + s] for q in ('P0', 'xc', 'beta') for s in ('_A0', '_alpham', '_alphaz')]
         amp_const, pref = pressure_constants(self.p['ombh2'] / self.h ** 2., self.omm0)
+        # kept as bin tables: the tSZ auto spectrum -- what a Compton-y profile is for (hmvec.py:512-514, C_yy) -- is
+        # reduced straight from them; pk_profiles[name] and cross spectra expand the cube on first use
         self.pk_profiles[name] = self._gnfw(1, fit9, pparams['battaglia_pres_gamma'],
-                                            pparams['battaglia_pres_alpha'], amp_const, pref, xmax, nxs)
+                                            pparams['battaglia_pres_alpha'], amp_const, pref, xmax, nxs, tables=True)
 
     def add_nfw_profile(self, name, numeric=False, nxs=None, xmax=None, ignore_existing=False):
         """Truncated-NFW u(k|M,z): analytic Si/Ci kernel, or the numerical transform (hmvec.py:318-355)."""
@@ -687,6 +732,19 @@ class HaloModel(Cosmology):
 
     def _power_pair(self, name, kA, bA, name2, kB, bB, want1=True, want2=True):
         """One generic tracer pair: hmv_power on the resident cubes; returns device [nz,nk] tensors."""
+        if name == name2 and kA == kB and bA is None and bB is None and kA in (_KIND_MATTER, _KIND_PRESSURE):
+            tp = (self.uk_profiles if kA == _KIND_MATTER else self.pk_profiles).tables(name)
+            if tp is not None and tp.cube is None:
+                # auto spectrum of a table-backed profile: no cube is built
+                ws = self._workspace('power', capi.lib.hmv_power_ws_doubles(self._nz, self._nm))
+                p1 = self._empty(self._nz, self._nk) if want1 else None
+                p2 = self._empty(self._nz, self._nk) if want2 else None
+                capi.check(capi.lib.hmv_power_tab(self._nz, self._nm, self._nk, capi.ptr(self._ms_d), capi.ptr(self._ks_d),
+                                                  capi.ptr(self._nzm_d), capi.ptr(self._bh_d), capi.ptr(self._Pzk_d),
+                                                  self._rho_m0, float(self.p['kstar_damping']), kA, capi.ptr(tp.tab),
+                                                  tp.nxs, capi.ptr(ws), capi.ptr(p1), capi.ptr(p2), capi.stream()),
+                           "hmv_power_tab")
+                return p1, p2
         A, keepA = self._tracer(name, kA, bA)
         B, keepB = self._tracer(name2, kB, bB)
         ws = self._workspace('power', capi.lib.hmv_power_ws_doubles(self._nz, self._nm))

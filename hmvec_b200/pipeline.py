@@ -82,13 +82,16 @@ class GridSix(object):
     STAGES = ("sigma2", "massfn", "uk_nfw", "uk_electron", "uk_pressure", "hod", "power_six", "power_yy", "limber")
 
     def __init__(self, inp, device=None, zcomm=None, family="AGN", xmax=None, nxs=None, nz_total_zs=None,
-                 fused_nfw=False, tsz=True):
+                 fused_nfw=False, tsz=True, tsz_tables=True):
         """inp: this rank's slab of `make_inputs` (see slab_inputs).  zcomm: zshard.ZComm for a sharded z axis;
         nz_total_zs: the full redshift vector (needed for Limber after the all-gather).  fused_nfw: spectra-only
         variant -- the NFW profile is evaluated inside the mass reduction (hmv_power_six_nfw), its cube is never
         written and 32 GB of HBM stay free; the default materialises it first (hmv_uk_nfw + hmv_power_six), which
         measured FASTER on B200 (10.9 + 8.9 ms vs 21.5 ms: the fused kernel trades HBM traffic for issue slots --
-        one k per thread instead of eight k per lane sharing each coefficient load -- see DESIGN.md)."""
+        one k per thread instead of eight k per lane sharing each coefficient load -- see DESIGN.md).
+        tsz_tables (default): the Compton-y profile stays in the transform's bin tables (hmv_profile_tables) and P_yy is
+        reduced straight from them (hmv_power_tab) -- its 32 GB cube is never written or read (measured 3.0 vs 4.6 ms on
+        a 64-z slab); False materialises the cube (hmv_profile_transform + hmv_power) as every other consumer needs."""
         if not torch.cuda.is_available():
             raise RuntimeError("hmvec_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback.")
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -108,6 +111,7 @@ class GridSix(object):
         self.fit9 = capi.darr([fam[q + s] for q in ('rho0', 'alpha', 'beta') for s in ('_A0', '_alpham', '_alphaz')])
         # tSZ leg (BASELINE.json configs[4]): Battaglia-2012 pressure profile -> P_yy -> C_yy
         self.tsz = bool(tsz)
+        self.tsz_tables = bool(tsz_tables) and self.tsz
         pf = battaglia_defaults[p['battaglia_pres_family']]
         self.pfit9 = capi.darr([pf[q + s] for q in ('P0', 'xc', 'beta') for s in ('_A0', '_alpham', '_alphaz')])
         from .hmvec import pressure_constants
@@ -155,15 +159,19 @@ class GridSix(object):
         self.h_p1 = torch.empty((self.nsp, nz, nk), dtype=torch.float64).pin_memory()
         self.h_p2 = torch.empty((self.nsp, nz, nk), dtype=torch.float64).pin_memory()
         if self.tsz:
-            self.uy = torch.empty((nz, nm, self.ldk), **f64)
-            if self.ldk > nk:
-                self.uy[..., nk:] = 0.0
+            if self.tsz_tables:
+                self.uy = None
+                self.ytab = E(int(capi.lib.hmv_profile_table_doubles(nz, nm, self.p_nxs)))
+            else:
+                self.uy = torch.empty((nz, nm, self.ldk), **f64)
+                if self.ldk > nk:
+                    self.uy[..., nk:] = 0.0
             for k in ("y_rs", "y_cmax", "y_xc", "y_alpha", "y_expo", "y_amp", "y_oscale"):
                 self.d[k] = E(nz, nm)
             self.d["pair_ws"] = E(int(capi.lib.hmv_power_ws_doubles(nz, nm)))
             self.ty = capi.Tracer()
             self.ty.kind = _KIND_PRESSURE
-            self.ty.us_d = self.uy.data_ptr()
+            self.ty.us_d = self.uy.data_ptr() if self.uy is not None else None
         # Limber (replicated on every rank after the all-gather)
         self.has_limber = "ells" in inp
         if self.has_limber:
@@ -288,11 +296,18 @@ class GridSix(object):
                                          float(p['battaglia_pres_alpha']), self.p_amp, self.p_pref, ptr(d["y_rs"]),
                                          ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
                                          ptr(d["y_amp"]), ptr(d["y_oscale"]), st), "hmv_gnfw_params(pressure)")
-            capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
-                                               ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
-                                               ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
-                                               self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.uy), st),
-                       "hmv_profile_transform(pressure)")
+            if self.tsz_tables:
+                capi.check(L.hmv_profile_tables(nz, nm, nk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
+                                                ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                                ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
+                                                self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.ytab), st),
+                           "hmv_profile_tables(pressure)")
+            else:
+                capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
+                                                   ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                                   ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
+                                                   self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.uy), st),
+                           "hmv_profile_transform(pressure)")
             n += 4 if self.transform_mode == 0 else 7
         self._mark(5)
         if not self.hod_overlap:
@@ -339,10 +354,16 @@ class GridSix(object):
         self._mark(7)
         if self.tsz:
             # P_yy 1h+2h (hmvec.py:512-514, 541-545: pressure tracers, b = 0, no consistency terms)
-            capi.check(L.hmv_power(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
-                                   ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), C.byref(self.ty),
-                                   C.byref(self.ty), ptr(d["pair_ws"]), ptr(self.p1[6]), ptr(self.p2[6]), st),
-                       "hmv_power(yy)")
+            if self.tsz_tables:
+                capi.check(L.hmv_power_tab(nz, nm, nk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                           ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), _KIND_PRESSURE,
+                                           ptr(self.ytab), self.p_nxs, ptr(d["pair_ws"]), ptr(self.p1[6]),
+                                           ptr(self.p2[6]), st), "hmv_power_tab(yy)")
+            else:
+                capi.check(L.hmv_power(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                       ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), C.byref(self.ty),
+                                       C.byref(self.ty), ptr(d["pair_ws"]), ptr(self.p1[6]), ptr(self.p2[6]), st),
+                           "hmv_power(yy)")
             n += 2
             if overlap_d2h:
                 self.ev_yy.record()

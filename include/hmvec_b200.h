@@ -197,6 +197,11 @@ int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d, const dou
 
 /* hmv_power_six with the electron profile given as bin tables (hmv_profile_tables, same nxs) instead of a cube:
  * reference hmvec.py:504-572 for the six pairs, fft.py:97-115 for the interpolation done inside the reduction. */
+/* Auto spectrum (1h + 2h) of ONE matter (kind 0) or pressure (kind 2) profile given as bin tables: nothing of size
+ * nz*nm*nk is read or written (hmvec.py:504-572 with fft.py:97-115 folded in).  ws_d: hmv_power_ws_doubles(nz,nm). */
+int hmv_power_tab(int nz, int nm, int nk, const double* ms_d, const double* ks_d, const double* nzm_d,
+                  const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, int kind, const double* tab_d,
+                  int nxs, double* ws_d, double* p1h_d, double* p2h_d, void* stream);
 long long hmv_power_six_tab_ws_doubles(int nz, int nm, int nk);
 int hmv_power_six_tab(int nz, int nm, int nk, int ldk, const double* ms_d, const double* ks_d, const double* nzm_d,
                       const double* bh_d, const double* Pzk_d, double rho_m0, double kstar, const double* um_d,

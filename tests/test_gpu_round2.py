@@ -186,3 +186,22 @@ def test_eh98_on_the_device(hm):
         d2d, vd = c.P_lin_approx_factors_device(ks_d, zs, type=typ)
         assert_close(d2d, d2h, 1e-14, name="growth")
         assert_close(vd.cpu().numpy(), vh, 1e-11, name="EH98 " + typ)
+
+
+def test_pressure_profile_tables_and_lazy_cube(hm, golden_mini):
+    """add_battaglia_pres_profile keeps bin tables: P_yy comes straight from them (hmv_power_tab), the cube appears
+    when something asks for it (pk_profiles[name], cross spectra) and then gives the same auto spectrum."""
+    g = golden_mini
+    h = hm.HaloModel(g["zs"], g["ks"], ms=g["ms"], accuracy='low')
+    h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+    tp = h.pk_profiles.tables("y")
+    assert tp is not None and tp.cube is None
+    p1, p2 = h.get_power_1halo("y", "y"), h.get_power_2halo("y", "y")
+    assert tp.cube is None                                   # the auto spectrum did not build the cube
+    assert_close(p1, g["P1h_yy"], 1e-6, name="P1h_yy from tables")
+    assert_close(p2, g["P2h_yy"], 1e-6, name="P2h_yy from tables")
+    assert_close(h.pk_profiles["y"], g["pk_y"], 1e-6, OSC, name="pk_y")      # expands the cube
+    assert tp.cube is not None
+    assert_close(h.get_power_1halo("y", "y"), p1, 1e-12, name="P1h_yy cube vs tables")
+    assert_close(h.get_power_2halo("y", "y"), p2, 1e-12, name="P2h_yy cube vs tables")
+    assert_close(h.get_power_1halo("y", "nfw"), g["P1h_ym"], 1e-6, name="P1h_ym")

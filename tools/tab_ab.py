@@ -24,7 +24,7 @@ warnings.filterwarnings("ignore")
 zs_all = np.linspace(0.01, 3., 200)
 pick = np.linspace(0, 199, a.nz).round().astype(int)
 zs = zs_all[pick]; ms = np.geomspace(2e10, 1e17, a.nm); ks = np.geomspace(1e-4, 100, a.nk)
-g = pipeline.GridSix(pipeline.make_inputs(zs, ms, ks, ngal=np.geomspace(1e-3, 1e-5, 200)[pick]))
+g = pipeline.GridSix(pipeline.make_inputs(zs, ms, ks, ngal=np.geomspace(1e-3, 1e-5, 200)[pick]), tsz_tables=False)
 g.upload(); g.run(); torch.cuda.synchronize()
 L, d, ptr, st = capi.lib, g.d, capi.ptr, capi.stream()
 nz, nm, nk, ldk = g.nz, g.nm, g.nk, g.ldk
@@ -95,4 +95,43 @@ out["ms_tables"] = timed(tables)
 out["ms_expand"] = timed(expand)
 out["ms_six"] = timed(lambda: six(p1a, p2a))
 out["ms_six_tab"] = timed(lambda: six_tab(p1b, p2b))
+# ---- tSZ leg: pressure tables + table-only auto spectrum against transform + cube + hmv_power ----
+if g.tsz:
+    import ctypes as C
+    ytab = E(L.hmv_profile_table_doubles(nz, nm, g.p_nxs))
+    wsy = E(L.hmv_power_ws_doubles(nz, nm))
+    pgam = float(g.p['battaglia_pres_gamma'])
+
+    def ytransform():
+        capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), g.kmax, ptr(d["y_rs"]),
+                                           ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                           ptr(d["y_amp"]), ptr(d["y_oscale"]), pgam, g.p_xmax, g.p_nxs, 0,
+                                           ptr(d["tr_ws"]), ptr(g.uy), st), "ytransform")
+
+    def ytables():
+        capi.check(L.hmv_profile_tables(nz, nm, nk, ptr(d["zs"]), ptr(d["ks"]), g.kmax, ptr(d["y_rs"]), ptr(d["y_cmax"]),
+                                        ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]), ptr(d["y_amp"]),
+                                        ptr(d["y_oscale"]), pgam, g.p_xmax, g.p_nxs, 0, ptr(d["tr_ws"]), ptr(ytab), st),
+                   "ytables")
+
+    py1, py2 = torch.zeros(nz, nk, dtype=torch.float64, device=g.ue.device), torch.zeros(nz, nk, dtype=torch.float64, device=g.ue.device)
+    qy1, qy2 = torch.zeros_like(py1), torch.zeros_like(py2)
+
+    def yy_cube():
+        capi.check(L.hmv_power(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]), ptr(d["Pzk"]),
+                               g.rho_m0, float(g.p['kstar_damping']), C.byref(g.ty), C.byref(g.ty), ptr(d["pair_ws"]),
+                               ptr(py1), ptr(py2), st), "yy_cube")
+
+    def yy_tab():
+        capi.check(L.hmv_power_tab(nz, nm, nk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]), ptr(d["Pzk"]),
+                                   g.rho_m0, float(g.p['kstar_damping']), 2, ptr(ytab), g.p_nxs, ptr(wsy), ptr(qy1),
+                                   ptr(qy2), st), "yy_tab")
+
+    ytransform(); ytables(); yy_cube(); yy_tab(); torch.cuda.synchronize()
+    out["yy_tab_vs_cube_rel_p1"] = rel(qy1, py1)
+    out["yy_tab_vs_cube_rel_p2"] = rel(qy2, py2)
+    out["ms_ytransform"] = timed(ytransform)
+    out["ms_ytables"] = timed(ytables)
+    out["ms_yy_cube"] = timed(yy_cube)
+    out["ms_yy_tab"] = timed(yy_tab)
 print("TABAB " + json.dumps(out))
