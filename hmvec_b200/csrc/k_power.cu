@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
   double2* prm2 = reinterpret_cast<double2*>(prm + a.nm);          //                        {c4, w2}
   int* rowid = reinterpret_cast<int*>(prm2 + a.nm);
   __shared__ double red[3][OT_T / 32];
-  __shared__ int nlist, wcnt[OT_T / 32];
+  __shared__ int nlist, nlist2, wcnt[OT_T / 32], wcnt2[OT_T / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int z = blockIdx.y, k0 = blockIdx.x * OT_K;
   const long long zrow = (long long)z * a.nm, zrowp = (long long)z * a.nmp;
@@ -644,16 +644,18 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
     kmx = fmax(kmx, __shfl_xor_sync(0xffffffffu, kmx, o));
   }
   if (lane == 0) { red[0][warp] = kmn; red[1][warp] = kmx; }
-  if (tid == 0) nlist = 0;
+  if (tid == 0) { nlist = 0; nlist2 = 0; }
   __syncthreads();
 #pragma unroll
   for (int w = 0; w < OT_T / 32; ++w) { kmn = fmin(kmn, red[0][w]); kmx = fmax(kmx, red[1][w]); }
   __syncthreads();
-  // classify the halos; hold-u_1 halos are summed here, interpolated ones are appended to the list
+  // classify the halos; hold-u_1 halos are summed here.  Halos whose whole tile lies inside [1, J] and inside the bins
+  // the transform wrote are appended from the front of the list (no classification or clamping per element), the
+  // other interpolated ones from the back -- both in halo order, which keeps the sums bit-reproducible
   double h1 = 0.0, hA = 0.0;
   for (int m0 = 0; m0 < a.nm; m0 += OT_T) {
     const int m = m0 + tid;
-    bool gen = false;
+    int cls = 0;                                               // 1: interior, 2: mixed
     double4 mt = make_double4(0.0, 0.0, 0.0, 0.0);
     double aA = 0, bA = 0, c4 = 0, w2 = 0;
     if (m < a.nm) {
@@ -667,20 +669,24 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
         const double tA = fma(bA, u, aA);
         h1 = fma(c4 * tA, tA, h1); hA = fma(w2, tA, hA);
       } else {
-        gen = true;
+        cls = (tlo >= 1.0 && thi <= tJ && thi < (double)min(a.J - 1, (int)mt.z) + 1.0) ? 1 : 2;
       }
     }
-    // append in halo order (a fixed order of the list keeps the sums bit-reproducible from run to run)
-    const unsigned bal = __ballot_sync(0xffffffffu, gen);
-    if (lane == 0) wcnt[warp] = __popc(bal);
+    const unsigned balI = __ballot_sync(0xffffffffu, cls == 1), balM = __ballot_sync(0xffffffffu, cls == 2);
+    if (lane == 0) { wcnt[warp] = __popc(balI); wcnt2[warp] = __popc(balM); }
     __syncthreads();
-    int base = nlist, tot = 0;
+    int baseI = nlist, baseM = nlist2, totI = 0, totM = 0;
 #pragma unroll
-    for (int w = 0; w < OT_T / 32; ++w) { base += (w < warp) ? wcnt[w] : 0; tot += wcnt[w]; }
-    __syncthreads();                                       // everyone has read nlist and the counts
-    if (tid == 0) nlist += tot;
-    if (gen) {
-      const int slot = base + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < OT_T / 32; ++w) {
+      baseI += (w < warp) ? wcnt[w] : 0; totI += wcnt[w];
+      baseM += (w < warp) ? wcnt2[w] : 0; totM += wcnt2[w];
+    }
+    __syncthreads();                                       // everyone has read the list lengths and the counts
+    if (tid == 0) { nlist += totI; nlist2 += totM; }
+    if (cls) {
+      const unsigned bal = cls == 1 ? balI : balM;
+      const int pos = (cls == 1 ? baseI : baseM) + __popc(bal & ((1u << lane) - 1u));
+      const int slot = cls == 1 ? pos : a.nm - 1 - pos;
       prm[slot] = make_double4(mt.x, mt.y, aA, bA);
       prm2[slot] = make_double2(c4, w2);
       rowid[slot] = (m << 12) | min(a.J - 1, (int)mt.z);         // halo index and bin cap (J - 1 < 4096 checked on the host)
@@ -692,13 +698,28 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
   h1 = hA = 0.0;
 #pragma unroll
   for (int w = 0; w < OT_T / 32; ++w) { h1 += red[0][w]; hA += red[1][w]; }
-  const int n = nlist;
+  const int nI = nlist, nM = nlist2;
 
   const int kc = min(k0 + 2 * tid, a.nk - 1), kc1 = min(k0 + 2 * tid + 1, a.nk - 1);
   const double kx = a.ks[kc], ky = a.ks[kc1];
   double p1x = 0, p1y = 0, iAx = 0, iAy = 0;
+  // interior halos: j = floor(t) needs no clamp, the value no classification
 #pragma unroll 4
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < nI; ++i) {
+    const double4 q = prm[i];
+    const double2 q2 = prm2[i];
+    const double* row = a.tab + (zrowp + (rowid[i] >> 12)) * (long long)a.JS;
+    const double tx = kx * q.x, ty = ky * q.x;
+    const int jx = __double2int_rz(tx), jy = __double2int_rz(ty);
+    const double uax = __ldg(row + jx), ubx = __ldg(row + jx + 1), uay = __ldg(row + jy), uby = __ldg(row + jy + 1);
+    const double ux = fma(tx - (double)jx, ubx - uax, uax), uy = fma(ty - (double)jy, uby - uay, uay);
+    const double tAx = fma(q.w, ux, q.z), tAy = fma(q.w, uy, q.z);
+    p1x = fma(q2.x * tAx, tAx, p1x); p1y = fma(q2.x * tAy, tAy, p1y);
+    iAx = fma(q2.y, tAx, iAx); iAy = fma(q2.y, tAy, iAy);
+  }
+  // halos whose tile crosses the first or the last bin
+#pragma unroll 2
+  for (int i = a.nm - 1; i > a.nm - 1 - nM; --i) {
     const double4 q = prm[i];
     const double2 q2 = prm2[i];
     const int id = rowid[i];
