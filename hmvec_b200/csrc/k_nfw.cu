@@ -14,9 +14,9 @@
 // warp-uniform term count) and writes the row once, coalesced: 8 B/element of algorithmic traffic.
 #include "common.cuh"
 #include "nfw_device.cuh"
+#include "nfw_poly.cuh"
 
 namespace hmv {
-#include "nfw_poly_tables.inc"
 
 constexpr int NFW_T = 256, NFW_E = 8, NFW_CH = 32 * NFW_E;
 
@@ -116,13 +116,6 @@ __global__ void __launch_bounds__(NFW_T, MODE ? 3 : 4) uk_nfw_kernel(int nk, int
 //                            a chunk that straddles interval edges looks the coefficients up per element; elements
 //                            beyond s = 64 (6.8 % on the LARGE grid, all with x > 4) take the closed form's asymptotic
 //                            branch.  No assumption on the order of ks (chunk min/max come from a pre-pass).
-constexpr int NFWP_REC = NFWP_NI * NFWP_STRIDE;          // doubles per halo
-
-__device__ __forceinline__ int nfwp_interval(double s) {
-  const int si = __double2int_rz(fmin(s, 1.0e6));
-  return si < 1 ? 0 : si < 2 ? 1 : si < 16 ? 1 + (si >> 1) : si < 64 ? 5 + (si >> 2) : NFWP_NI;
-}
-
 // per 256-wide chunk: min and max of ks; copies of ks and ks^2 padded to whole chunks (last value repeated), so the
 // cube kernel reads 16-byte pairs without bounds checks
 __global__ void nfw_chunk_kernel(int nk, const double* __restrict__ ks, double* __restrict__ kcmin,
@@ -241,18 +234,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 
-struct NfwpTables {                        // per-CTA copies of the interval tables (lane-divergent lookups)
-  double2 map[NFWP_NI];                    // t = y*map.x + map.y
-  double hi[NFWP_NI + 1];                  // end of the range the interval's polynomial is valid on (a little past its
-                                           // upper edge; last entry: +inf for "beyond")
-  int deg[NFWP_NI];
-  unsigned char idx[72];                   // interval of floor(s) for floor(s) <= 64 (64: beyond)
-};
-
-__device__ __forceinline__ int nfwp_lookup(const NfwpTables& T, double s) {
-  return T.idx[min(__double2int_rz(s), 64)];            // the conversion saturates for huge s
-}
-
 // one element through the general route: the polynomial of its own interval, or the closed form beyond s = 64
 __device__ __noinline__ double nfwp_element(const double* R, const NfwpTables& T, double kk, double ac, double a,
                                             double c, double ln1pc, double inv_mc) {
@@ -297,9 +278,7 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  if (tid < NFWP_NI) { T.map[tid] = g_nfwp_map[tid]; T.deg[tid] = g_nfwp_deg[tid]; }
-  if (tid <= NFWP_NI) T.hi[tid] = tid < NFWP_NI ? g_nfwp_hix[tid] : 1.0e300;
-  if (tid < 72) T.idx[tid] = (unsigned char)(tid < 64 ? nfwp_interval((double)tid + 0.5) : NFWP_NI);
+  nfwp_tables_init(T, tid);
   const int nchunks = (nk + NFW_CH - 1) / NFW_CH;
   const bool cmm_sm = nchunks <= NFWP_MAXCH;
   if (cmm_sm)
@@ -448,6 +427,19 @@ __global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, i
   }
 }
 
+int nfw_poly_records(long long rows, int nm, int nkmax, const double* kmax_d, const double* zs_d, const double* cs_d,
+                     const double* rvir_d, double* rec48, double* prec, cudaStream_t st) {
+  int dev = 0, nsm = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(nfw_poly_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NFWP_GEMM_SMEM);
+  if (e != cudaSuccess) return fail(HMV_E_CUDA, "nfw_poly_records: %s", cudaGetErrorString(e));
+  const long long ngroups = (rows + 15) / 16;
+  const int grid = (int)((ngroups + 7) / 8 < nsm ? (ngroups + 7) / 8 : nsm);
+  nfw_poly_gemm_kernel<<<grid, 256, NFWP_GEMM_SMEM, st>>>(rows, nm, nkmax, kmax_d, zs_d, cs_d, rvir_d, rec48, prec);
+  return check_launch("nfw_poly_gemm_kernel");
+}
+
 __global__ void sici_test_kernel(int n, const double* __restrict__ x, double* __restrict__ si,
                                  double* __restrict__ ci) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,15 +484,7 @@ extern "C" int hmv_uk_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, c
     nfw_chunk_kernel<<<nchunks, 32, 0, st>>>(nk, ks_d, kcmin, kcmx, ksp, k2p);
     rc = check_launch("nfw_chunk_kernel");
     if (rc) return rc;
-    int dev = 0, nsm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nfw_poly_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NFWP_GEMM_SMEM);
-    if (e != cudaSuccess) return fail(HMV_E_CUDA, "hmv_uk_nfw: %s", cudaGetErrorString(e));
-    const long long ngroups = (rows + 15) / 16;
-    const int grid = (int)((ngroups + 7) / 8 < nsm ? (ngroups + 7) / 8 : nsm);
-    nfw_poly_gemm_kernel<<<grid, 256, NFWP_GEMM_SMEM, st>>>(rows, nm, nchunks, kcmx, zs_d, cs_d, rvir_d, ws_d, prec);
-    rc = check_launch("nfw_poly_gemm_kernel");
+    rc = nfw_poly_records(rows, nm, nchunks, kcmx, zs_d, cs_d, rvir_d, ws_d, prec, st);
     if (rc) return rc;
     uk_nfw_poly_kernel<<<cdiv(rows, NFW_T / 32), NFW_T, 0, st>>>(rows, nk, ldk, ksp, k2p, ws_d, prec, kcmin, kcmx, uk_d);
     return check_launch("uk_nfw_poly_kernel");

@@ -12,6 +12,7 @@
 //   power_six_nfw_kernel   the same with the NFW profile evaluated in-kernel (spectra-only fusion)
 #include "common.cuh"
 #include "nfw_device.cuh"
+#include "nfw_poly.cuh"
 
 namespace hmv {
 
@@ -765,26 +766,33 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
 // Same ring/mbarrier structure as power_six_kernel; stage = SIX_R rows x (4 KB of u_e + 64 B coefficients + 384 B
 // NFW record).  k tiles are the slow grid dimension, highest k first: the Si/Ci-heavy tiles are scheduled first.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int NREC = NFW_NREC;
+// {min, max} of ks over [b*tile, (b+1)*tile) for each block b (one warp per block)
+__global__ void tile_range_kernel(int nk, int tile, const double* __restrict__ ks, double* __restrict__ tilek) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  double mn = 1.0e300, mx = 0.0;
+  for (int k = b * tile + lane; k < min(nk, (b + 1) * tile); k += 32) { mn = fmin(mn, ks[k]); mx = fmax(mx, ks[k]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { tilek[2 * b] = mn; tilek[2 * b + 1] = mx; }
+}
 
+constexpr int FREC = NFWP_REC + 6;          // per-halo record of the fused kernel: polynomial coefficients, then
+                                            // {c, a = r_s (1+z), a c, ln(1+c), 1/m_c, 0}
 constexpr int FSX_NST = 6;
-constexpr int FSX_STAGE_DOUBLES = SIX_R * SIX_K + SIX_R * 8 + SIX_R * NREC;
+constexpr int FSX_STAGE_DOUBLES = SIX_R * SIX_K + SIX_R * 8 + SIX_R * FREC;
 constexpr size_t FSX_SMEM = (size_t)FSX_NST * FSX_STAGE_DOUBLES * sizeof(double) + 2 * FSX_NST * sizeof(unsigned long long);
 
 struct FusedArgs {
   int nz, nm, nk, ldk;
   long long spec_stride;
-  const double *ue, *coef, *rec;
+  const double *ue, *coef, *rec48, *prec;
   const double *zoff, *ks, *Pzk;
   double kstar;
   double *p1h, *p2h;
 };
-
-__device__ __forceinline__ double nfw_u(const double* __restrict__ r, double kk) {
-  const double xc = kk * r[44];
-  if (xc <= NFW_XC_MAX) return nfw_horner(r, nfw_terms(xc), xc * xc);
-  return nfw_bracket(kk * r[43], r[42], r[45]) * r[46];
-}
 
 constexpr int FSX_CT = 512;   // consumer threads: one k each (16 warps keep the FP64 pipe fed through the Horner chains)
 
@@ -803,8 +811,41 @@ constexpr int FSX_CT = 512;   // consumer threads: one k each (16 warps keep the
     acc[8] = fma(c67.x, um, acc[8]);                                                  \
   }
 
+// u_NFW of one wavenumber for two halo rows at once (two interleaved Horner chains).  The 32 adjacent wavenumbers of a
+// warp almost always share an interval, so the per-lane coefficient loads are shared-memory broadcasts; the loop runs
+// to the highest degree present in the warp (lower ones are zero padded); beyond s = 64: the closed form.
+__device__ __forceinline__ void nfw_poly_pair(const NfwpTables& T, const double* __restrict__ r0,
+                                              const double* __restrict__ r1, double kk, double& um0, double& um1) {
+  const double s0 = kk * r0[NFWP_REC + 2], s1 = kk * r1[NFWP_REC + 2];
+  const int i0 = nfwp_lookup(T, s0), i1 = nfwp_lookup(T, s1);
+  const int j0 = min(i0, NFWP_NI - 1), j1 = min(i1, NFWP_NI - 1);
+  const double2 m0 = T.map[j0], m1 = T.map[j1];
+  const double t0 = fma(s0 * s0, m0.x, m0.y), t1 = fma(s1 * s1, m1.x, m1.y);
+  const int D = __reduce_max_sync(0xffffffffu, max(T.deg[j0], T.deg[j1]));
+  const double* c0 = r0 + j0 * NFWP_STRIDE;
+  const double* c1 = r1 + j1 * NFWP_STRIDE;
+  double2 a0 = *reinterpret_cast<const double2*>(c0 + D - 1), a1 = *reinterpret_cast<const double2*>(c1 + D - 1);
+  double u0 = fma(a0.y, t0, a0.x), u1 = fma(a1.y, t1, a1.x);
+  for (int j = D - 3; j >= 0; j -= 2) {
+    a0 = *reinterpret_cast<const double2*>(c0 + j);
+    a1 = *reinterpret_cast<const double2*>(c1 + j);
+    u0 = fma(fma(u0, t0, a0.y), t0, a0.x);
+    u1 = fma(fma(u1, t1, a1.y), t1, a1.x);
+  }
+  if (i0 >= NFWP_NI) {
+    const double x = kk * r0[NFWP_REC + 1], c = r0[NFWP_REC];
+    u0 = (x > 4.0 ? nfw_bracket_far(x, c) : nfw_bracket(x, c, r0[NFWP_REC + 3])) * r0[NFWP_REC + 4];
+  }
+  if (i1 >= NFWP_NI) {
+    const double x = kk * r1[NFWP_REC + 1], c = r1[NFWP_REC];
+    u1 = (x > 4.0 ? nfw_bracket_far(x, c) : nfw_bracket(x, c, r1[NFWP_REC + 3])) * r1[NFWP_REC + 4];
+  }
+  um0 = u0; um1 = u1;
+}
+
 __global__ void __launch_bounds__(FSX_CT + 32, 1) power_six_nfw_kernel(const FusedArgs a) {
   extern __shared__ __align__(128) unsigned char six_smem[];
+  __shared__ NfwpTables T;
   double* ring = reinterpret_cast<double*>(six_smem);
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)FSX_NST * FSX_STAGE_DOUBLES);
   unsigned long long* empty = full + FSX_NST;
@@ -813,13 +854,10 @@ __global__ void __launch_bounds__(FSX_CT + 32, 1) power_six_nfw_kernel(const Fus
   const int segk = min(SIX_K, a.ldk - k0);
   const long long zrow = (long long)z * a.nm;
   const int nit = (a.nm + SIX_R - 1) / SIX_R;
-  // this thread's wavenumber and the largest one of the tile (decides series vs Si/Ci per halo row for the whole CTA)
   const int k = k0 + tid;
   const bool active = tid < FSX_CT && k < a.nk;
-  const double kk = active ? __ldg(a.ks + k) : 0.0;
-  double kmax_tile = kk;                 // per WARP: 32 adjacent k decide series vs Si/Ci and the term count
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) kmax_tile = fmax(kmax_tile, __shfl_xor_sync(0xffffffffu, kmax_tile, o));
+  const double kk = __ldg(a.ks + min(k, a.nk - 1));       // idle lanes evaluate a valid wavenumber and discard it
+  nfwp_tables_init(T, tid);
   if (tid == 0) {
     for (int s = 0; s < FSX_NST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, FSX_CT / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -835,11 +873,14 @@ __global__ void __launch_bounds__(FSX_CT + 32, 1) power_six_nfw_kernel(const Fus
         mbar_wait_sleep(empty + s, ph ^ 1u);
         const int m0 = it * SIX_R, rows = min(SIX_R, a.nm - m0);
         double* st = ring + (size_t)s * FSX_STAGE_DOUBLES;
-        mbar_expect_tx(full + s, (unsigned)rows * (segb + 64u + NREC * 8u));
-        for (int r = 0; r < rows; ++r)
+        mbar_expect_tx(full + s, (unsigned)rows * (segb + 64u + FREC * 8u));
+        for (int r = 0; r < rows; ++r) {
           bulk_g2s(st + r * SIX_K, a.ue + (zrow + m0 + r) * (long long)a.ldk + k0, segb, full + s);
+          double* rr = st + SIX_R * SIX_K + SIX_R * 8 + r * FREC;
+          bulk_g2s(rr, a.prec + (zrow + m0 + r) * NFWP_REC, NFWP_REC * 8u, full + s);
+          bulk_g2s(rr + NFWP_REC, a.rec48 + (zrow + m0 + r) * NFW_NREC + 42, 48u, full + s);
+        }
         bulk_g2s(st + SIX_R * SIX_K, a.coef + (zrow + m0) * 8, (unsigned)rows * 64u, full + s);
-        bulk_g2s(st + SIX_R * SIX_K + SIX_R * 8, a.rec + (zrow + m0) * NREC, (unsigned)rows * NREC * 8u, full + s);
         if (++s == FSX_NST) { s = 0; ph ^= 1u; }
       }
     }
@@ -860,32 +901,15 @@ __global__ void __launch_bounds__(FSX_CT + 32, 1) power_six_nfw_kernel(const Fus
     mbar_wait(full + s, ph);
 #pragma unroll 1
     for (int r = 0; r < rows; r += 2) {
-      const double* r0 = recs + r * NREC;
+      const double* r0 = recs + r * FREC;
       const bool two = r + 1 < rows;
-      const double* r1 = two ? r0 + NREC : r0;
-      const double ac0 = r0[44], ac1 = r1[44];
+      const double* r1 = two ? r0 + FREC : r0;
       double um0, um1;
-      if (kmax_tile * fmax(ac0, ac1) <= NFW_XC_MAX) {
-        // both rows are in the series regime for every k of the tile: two interleaved Horner chains with a
-        // CTA-uniform term count (set by the tile's largest k)
-        const int nt = nfw_terms(kmax_tile * fmax(ac0, ac1));
-        const double x0 = kk * ac0, x1 = kk * ac1, y0 = x0 * x0, y1 = x1 * x1;
-        um0 = r0[nt - 1]; um1 = r1[nt - 1];
-#pragma unroll 2
-        for (int i = nt - 2; i >= 1; i -= 2) {
-          const double2 a0 = *reinterpret_cast<const double2*>(r0 + i - 1);
-          const double2 a1 = *reinterpret_cast<const double2*>(r1 + i - 1);
-          um0 = fma(um0, y0, a0.y); um1 = fma(um1, y1, a1.y);
-          um0 = fma(um0, y0, a0.x); um1 = fma(um1, y1, a1.x);
-        }
-      } else {
-        um0 = nfw_u(r0, kk);
-        um1 = nfw_u(r1, kk);
-      }
-      const double ue0 = st[r * SIX_K + tid];
+      nfw_poly_pair(T, r0, r1, kk, um0, um1);
+      const double ue0 = st[r * SIX_K + min(tid, segk - 1)];
       HMV_SIX1(um0, ue0, cfs + r * 4)
       if (two) {
-        const double ue1 = st[(r + 1) * SIX_K + tid];
+        const double ue1 = st[(r + 1) * SIX_K + min(tid, segk - 1)];
         HMV_SIX1(um1, ue1, cfs + (r + 1) * 4)
       }
     }
@@ -1108,7 +1132,7 @@ extern "C" int hmv_power_tab(int nz, int nm, int nk, const double* ms_d, const d
 
 extern "C" long long hmv_power_six_nfw_ws_doubles(int nz, int nm) {
   if (nz <= 0 || nm <= 0) return 0;
-  return (8LL + NREC) * nz * nm + 2LL * nz;   // coefficient records + NFW records + zoff
+  return (8LL + NFW_NREC + NFWP_REC) * nz * nm + 2LL * nz + 4;   // coefficient records + NFW records + zoff + max(ks)
 }
 
 extern "C" int hmv_power_six_nfw(int nz, int nm, int nk, int ldk, const double* zs_d, const double* ms_d,
@@ -1128,18 +1152,22 @@ extern "C" int hmv_power_six_nfw(int nz, int nm, int nk, int ldk, const double* 
   cudaStream_t st = (cudaStream_t)stream;
   const long long cs = (long long)nz * nm;
   double* coef = ws_d;
-  double* rec = ws_d + 8 * cs;
-  double* zoff = rec + NREC * cs;
+  double* rec48 = ws_d + 8 * cs;
+  double* prec = rec48 + NFW_NREC * cs;
+  double* zoff = prec + NFWP_REC * cs;
+  double* kmax_dev = zoff + 2 * nz + ((2 * nz) & 1);
   power_six_prep_kernel<<<nz, 256, 0, st>>>(nm, ms_d, nzm_d, bh_d, rho_m0, Nc_d, Ns_d, NcNs_d, NsNsm1_d, ngal_d, coef,
                                             zoff);
   int rc = check_launch("power_six_prep_kernel");
   if (rc) return rc;
-  nfw_record_kernel<<<cdiv(cs, 128), 128, 0, st>>>(nz, nm, zs_d, cs_d, rvir_d, rec);
-  rc = check_launch("nfw_record_kernel");
+  tile_range_kernel<<<1, 32, 0, st>>>(nk, nk, ks_d, kmax_dev);          // {min, max} of ks
+  rc = check_launch("tile_range_kernel");
+  if (rc) return rc;
+  rc = nfw_poly_records(cs, nm, 1, kmax_dev + 1, zs_d, cs_d, rvir_d, rec48, prec, st);
   if (rc) return rc;
   FusedArgs a;
   a.nz = nz; a.nm = nm; a.nk = nk; a.ldk = ldk; a.spec_stride = spec_stride ? spec_stride : (long long)nz * nk;
-  a.ue = ue_d; a.coef = coef; a.rec = rec; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar;
+  a.ue = ue_d; a.coef = coef; a.rec48 = rec48; a.prec = prec; a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar;
   a.p1h = p1h_d; a.p2h = p2h_d;
   cudaError_t e = cudaFuncSetAttribute(power_six_nfw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FSX_SMEM);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_six_nfw_kernel smem opt-in (%zu B): %s", FSX_SMEM, cudaGetErrorString(e));
