@@ -779,7 +779,11 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
     if (single && p.ts_Q > 0 && ts_k <= TS_S && ts_r <= TS_RMAX) {
       const long long direct = 2LL * ((nb + 3) >> 2) * ((jn + 7) >> 3);
       const long long staged = (long long)WS_HB * p.ts_QT * (2 * TS_U * ts_k + 4 * TS_U * ts_r);
-      two = 5 * staged < 4 * direct;
+#ifndef HMV_K1_TS_NUM
+#define HMV_K1_TS_NUM 5
+#define HMV_K1_TS_DEN 4
+#endif
+      two = HMV_K1_TS_NUM * staged < HMV_K1_TS_DEN * direct;
     }
 #endif
 
