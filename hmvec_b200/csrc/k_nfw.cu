@@ -256,7 +256,10 @@ __device__ __noinline__ double nfwp_element(const double* R, const NfwpTables& T
 // its row's record into its own shared-memory slice, sweeps the leading chunks that lie entirely below s = 1 (two
 // thirds of the LARGE grid's elements) in a tight loop with the six coefficients in registers, and takes the remaining
 // chunks through the general route.  A lane owns four 16-byte pairs of a 256-wide chunk (coalesced 16-byte stores).
-__global__ void __launch_bounds__(NFW_T, 3) uk_nfw_poly_kernel(long long rows, int nk, int ldk,
+#ifndef HMV_NFWP_MINB
+#define HMV_NFWP_MINB 3     // CTAs per SM the register allocation aims at (4 = 64 registers: measured below)
+#endif
+__global__ void __launch_bounds__(NFW_T, HMV_NFWP_MINB) uk_nfw_poly_kernel(long long rows, int nk, int ldk,
                                                                 const double* __restrict__ ksp,
                                                                 const double* __restrict__ k2p,
                                                                 const double* __restrict__ rec48,
