@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(NFW_T, HMV_NFWP_MINB) uk_nfw_poly_kernel(long 
     for (int q = 0; q < 4; ++q) kn[q] = __ldg(kq2 + lane + 32 * q);
     for (int chunk = 0; chunk < nA; ++chunk) {
       const int pbase = chunk * (NFW_CH / 2) + lane;
+      HMV_DEV_ASSERT(chunk + 1 < nchunks && pbase + 96 < npair);
       double2 t[4], u[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) t[q] = make_double2(fma(kn[q].x, ts, to), fma(kn[q].y, ts, to));
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(NFW_T, HMV_NFWP_MINB) uk_nfw_poly_kernel(long 
         const double2 mp = T.map[ivlo];
         const double ts = mp.x * ac2, to = mp.y;
         const int D = T.deg[ivlo];                        // odd
+        HMV_DEV_ASSERT(ivlo >= 0 && ivlo < NFWP_NI && (D & 1) && D < NFWP_STRIDE);
         const double* m = Rr + ivlo * NFWP_STRIDE;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -395,6 +397,7 @@ __global__ void __launch_bounds__(NFW_T, HMV_NFWP_MINB) uk_nfw_poly_kernel(long 
           const double2 mp = T.map[iv];
           t[q] = make_double2(fma(s0 * s0, mp.x, mp.y), fma(s1 * s1, mp.x, mp.y));
           off[q] = iv * NFWP_STRIDE;
+          HMV_DEV_ASSERT(iv >= 0 && iv < NFWP_NI);
           u[q] = make_double2(0.0, 0.0);
         }
         const int D = T.deg[min(ivhi, NFWP_NI - 1)];      // degrees do not decrease with s; lower ones are zero padded

@@ -465,6 +465,7 @@ struct TabLerp { double ua, ub, fr; };   // fr: t - j inside [1, J]; -1: below t
 __device__ __forceinline__ TabLerp tab_fetch(const double* __restrict__ row, double inv, int jcap, double k, double tJ) {
   const double t = k * inv;
   const int jj = min(max(__double2int_rz(fmin(t, tJ)), 1), jcap);       // always inside the bins the transform wrote
+  HMV_DEV_ASSERT(jj >= 1 && jj + 1 <= (int)tJ + 1);
   TabLerp r;
   r.fr = (t >= 1.0) ? ((t > tJ) ? -2.0 : t - (double)jj) : -1.0;
   r.ua = 0.0; r.ub = 0.0;
@@ -688,6 +689,7 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
       const unsigned bal = cls == 1 ? balI : balM;
       const int pos = (cls == 1 ? baseI : baseM) + __popc(bal & ((1u << lane) - 1u));
       const int slot = cls == 1 ? pos : a.nm - 1 - pos;
+      HMV_DEV_ASSERT(slot >= 0 && slot < a.nm);
       prm[slot] = make_double4(mt.x, mt.y, aA, bA);
       prm2[slot] = make_double2(c4, w2);
       rowid[slot] = (m << 12) | min(a.J - 1, (int)mt.z);         // halo index and bin cap (J - 1 < 4096 checked on the host)
@@ -712,6 +714,7 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
     const double* row = a.tab + (zrowp + (rowid[i] >> 12)) * (long long)a.JS;
     const double tx = kx * q.x, ty = ky * q.x;
     const int jx = __double2int_rz(tx), jy = __double2int_rz(ty);
+    HMV_DEV_ASSERT(jx >= 1 && jy >= 1 && jx + 1 < a.JS && jy + 1 < a.JS && jx <= (rowid[i] & 4095) && jy <= (rowid[i] & 4095));
     const double uax = __ldg(row + jx), ubx = __ldg(row + jx + 1), uay = __ldg(row + jy), uby = __ldg(row + jy + 1);
     const double ux = fma(tx - (double)jx, ubx - uax, uax), uy = fma(ty - (double)jy, uby - uay, uay);
     const double tAx = fma(q.w, ux, q.z), tAy = fma(q.w, uy, q.z);
