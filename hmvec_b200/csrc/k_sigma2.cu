@@ -6,7 +6,7 @@ namespace hmv {
 
 // ---- W^2 table: W2T[k'][m] = W(ks[k'] R[m])^2, k' major so the contraction reads it coalesced in m ----
 __global__ void w2_table_kernel(int nm, int nks, const double* __restrict__ ks, const double* __restrict__ R,
-                                double taylor_switch, double* __restrict__ W2T) {
+                                const double* __restrict__ kw, double taylor_switch, double* __restrict__ W2T) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nm * nks) return;
   const int k = (int)(idx / nm), m = (int)(idx - (long long)k * nm);
@@ -20,22 +20,101 @@ __global__ void w2_table_kernel(int nm, int nks, const double* __restrict__ ks, 
     sincos(x, &s, &c);
     w = 3.0 * (s - x * c) / (x * x * x);  // cosmology.py:36
   }
-  W2T[idx] = w * w;
+  W2T[idx] = w * w * kw[k];     // the integration weight of k' rides on the table (one multiply here, none in the GEMM)
 }
 
 // ---- contraction C[z][m] = sum_k (sPzk[z][k]*kw[k]) * W2T[k][m] : FP64 tensor-core GEMM ---------------------
-// CTA tile 32 (z) x 64 (m), k staged 16 at a time through shared memory; warp w owns the 8 x 32 strip
-// (rows 8 (w&3), columns 32 (w>>2)) as four mma.sync m8n8k4 tiles.  Split-k across blockIdx.z.
+// The z extent is small (200 on the LARGE grid, 25 per rank on eight GPUs), so a CTA takes ALL redshifts of a z tile
+// (8 MT rows, MT <= 26) against a 64-wide strip of masses: the 160 MB W^2 table is read once per z tile instead of
+// once per 32 redshifts.  Warp w owns the strip's columns 8w..8w+7 for every row: MT accumulator tiles of
+// mma.sync m8n8k4, fed from a cp.async double-buffered pair of shared-memory tiles (A as [z][k] rows of 16-byte
+// copies, B as [k][m]).  Split-k across blockIdx.z fills the SMs; the partial sums are added in a fixed order.
+constexpr int SG_BN = 64, SG_BK = 16, SG_T = 256, SG_ALD = SG_BK + 4, SG_BLD = SG_BN + 8;
+
+__device__ __forceinline__ void cp_async16_sg(void* dst, const void* src, bool pred) {
+  const int bytes = pred ? 16 : 0;                        // zero-fill when out of range
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+
+template <int MT>
+__global__ void __launch_bounds__(SG_T, MT > 16 ? 1 : 2) sigma2_gemm_kernel(int nz, int nm, int nks, int kchunk,
+                                                                            const double* __restrict__ sPzk,
+                                                                            const double* __restrict__ W2T,
+                                                                            double* __restrict__ out,
+                                                                            long long out_split_stride) {
+  constexpr int BM = 8 * MT;
+  extern __shared__ __align__(16) double sg_smem[];
+  double* As = sg_smem;                                  // [2][BM][SG_ALD]
+  double* Bs = As + 2 * BM * SG_ALD;                     // [2][SG_BK][SG_BLD]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int kq = lane & 3, nq = lane >> 2;
+  const int z0 = blockIdx.y * BM, m0 = blockIdx.x * SG_BN;
+  const int kbeg = blockIdx.z * kchunk, kend = min(nks, kbeg + kchunk);
+  double c[MT][2];
+#pragma unroll
+  for (int t = 0; t < MT; ++t) c[t][0] = c[t][1] = 0.0;
+  // nks and nm are even and the rows 16-byte aligned (checked on the host): every copy is a whole 16-byte word
+  auto load = [&](int k0, int buf) {
+    double* Ab = As + buf * BM * SG_ALD;
+    for (int i = tid; i < BM * (SG_BK / 2); i += SG_T) {            // A: BM rows x 8 words
+      const int r = i / (SG_BK / 2), kw2 = (i - r * (SG_BK / 2)) * 2;
+      const int z = z0 + r, k = k0 + kw2;
+      cp_async16_sg(Ab + r * SG_ALD + kw2, sPzk + (long long)min(z, nz - 1) * nks + min(k, nks - 2), z < nz && k < kend);
+    }
+    double* Bb = Bs + buf * SG_BK * SG_BLD;
+    for (int i = tid; i < SG_BK * (SG_BN / 2); i += SG_T) {         // B: 16 rows x 32 words
+      const int r = i / (SG_BN / 2), mw = (i - r * (SG_BN / 2)) * 2;
+      const int k = k0 + r, m = m0 + mw;
+      cp_async16_sg(Bb + r * SG_BLD + mw, W2T + (long long)min(k, nks - 1) * nm + min(m, nm - 2), k < kend && m < nm);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  load(kbeg, 0);
+  for (int k0 = kbeg; k0 < kend; k0 += SG_BK) {
+    if (k0 + SG_BK < kend) {
+      load(k0 + SG_BK, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const double* Ab = As + buf * BM * SG_ALD;
+    const double* Bb = Bs + buf * SG_BK * SG_BLD;
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; kk += 4) {
+      const double bv = Bb[(kk + kq) * SG_BLD + 8 * w + nq];
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const double av = Ab[(8 * t + nq) * SG_ALD + kk + kq];
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(av), "d"(bv));
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  double* o = out + (long long)blockIdx.z * out_split_stride;
+  const int m = m0 + 8 * w + 2 * kq;
+#pragma unroll
+  for (int t = 0; t < MT; ++t) {
+    const int z = z0 + 8 * t + nq;
+    if (z < nz) {
+      if (m < nm) o[(long long)z * nm + m] = c[t][0];
+      if (m + 1 < nm) o[(long long)z * nm + m + 1] = c[t][1];
+    }
+  }
+}
+
+// fallback for odd nks / nm or unaligned inputs: the scalar-load kernel of round 1
 constexpr int BM = 32, BN = 64, BK = 16, GT = 256;
 #ifndef HMV_SIGMA2_CTAS
 #define HMV_SIGMA2_CTAS (16 * 148)
 #endif
-
-__global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks, int kchunk,
-                                                         const double* __restrict__ sPzk,
-                                                         const double* __restrict__ kw,
-                                                         const double* __restrict__ W2T, double* __restrict__ out,
-                                                         long long out_split_stride) {
+__global__ void __launch_bounds__(GT) sigma2_gemm_plain_kernel(int nz, int nm, int nks, int kchunk,
+                                                               const double* __restrict__ sPzk,
+                                                               const double* __restrict__ W2T, double* __restrict__ out,
+                                                               long long out_split_stride) {
   __shared__ double As[BK][BM + 1];
   __shared__ double Bs[BK][BN + 8];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -44,31 +123,20 @@ __global__ void __launch_bounds__(GT) sigma2_gemm_kernel(int nz, int nm, int nks
   const int z0 = blockIdx.y * BM, m0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * kchunk, kend = min(nks, kbeg + kchunk);
   double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-  // loader indices
   const int az = tid >> 3, ak = (tid & 7) * 2;     // A: 32 z x 16 k, 2 k per thread
   const int bk = tid >> 4, bm = (tid & 15) * 4;    // B: 16 k x 64 m, 4 m per thread
-  // software pipeline: the next k-step's operands are fetched into registers while the current one is multiplied
-  double ra[2], rb[4];
-  auto fetch = [&](int k0) {
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int z = z0 + az, k = k0 + ak + i;
-      ra[i] = (z < nz && k < kend) ? sPzk[(long long)z * nks + k] * kw[k] : 0.0;
+      As[ak + i][az] = (z < nz && k < kend) ? sPzk[(long long)z * nks + k] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + bk, m = m0 + bm + i;
-      rb[i] = (k < kend && m < nm) ? W2T[(long long)k * nm + m] : 0.0;
+      Bs[bk][bm + i] = (k < kend && m < nm) ? W2T[(long long)k * nm + m] : 0.0;
     }
-  };
-  fetch(kbeg);
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) As[ak + i][az] = ra[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Bs[bk][bm + i] = rb[i];
     __syncthreads();
-    if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
       const double a = As[kk + kq][wz + nq];
@@ -102,9 +170,21 @@ __global__ void splitk_reduce_kernel(long long n, int nsplit, const double* __re
   out[i] = s;
 }
 
-static int sigma2_splits(int nz, int nm, int nks) {
-  const long long tiles = (long long)cdiv(nm, BN) * cdiv(nz, BM);
-  long long s = (HMV_SIGMA2_CTAS + tiles - 1) / tiles;   // enough resident CTAs per SM to hide the un-pipelined loads
+// z rows per CTA of the all-z kernel: the smallest of 32 / 64 / 128 / 208 that covers nz (several z tiles beyond 208)
+static int sigma2_mt(int nz) { return nz <= 32 ? 4 : nz <= 64 ? 8 : nz <= 128 ? 16 : 26; }
+
+// split-k factor.  The workspace is sized for the larger of the two plans (all-z kernel / fallback kernel).
+static int sigma2_splits(int nz, int nm, int nks, bool allz) {
+  long long s;
+  if (allz) {
+    const int mt = sigma2_mt(nz);
+    const long long tiles = (long long)cdiv(nm, SG_BN) * cdiv(nz, 8 * mt);
+    const long long slots = 148LL * (mt > 16 ? 1 : 2) * 2;        // at most two full waves of resident CTAs
+    s = slots / tiles;
+  } else {
+    const long long tiles = (long long)cdiv(nm, BN) * cdiv(nz, BM);
+    s = (HMV_SIGMA2_CTAS + tiles - 1) / tiles;   // enough resident CTAs per SM to hide the un-pipelined loads
+  }
   if (s < 1) s = 1;
   if (s > 32) s = 32;
   const long long maxs = (nks + BK - 1) / BK;
@@ -171,8 +251,9 @@ using namespace hmv;
 
 extern "C" long long hmv_sigma2_ws_doubles(int nz, int nm, int nks) {
   if (nz <= 0 || nm <= 0 || nks <= 0) return 0;
-  const int s = sigma2_splits(nz, nm, nks);
-  return (long long)nks * nm + (s > 1 ? (long long)s * nz * nm : 0);
+  const int s0 = sigma2_splits(nz, nm, nks, true), s1 = sigma2_splits(nz, nm, nks, false);
+  const int s = s0 > s1 ? s0 : s1;
+  return (long long)nks * nm + (long long)s * nz * nm;
 }
 
 extern "C" int hmv_sigma2(int nz, int nm, int nks, const double* sPzk_d, const double* kw_d, const double* ks_sig_d,
@@ -181,22 +262,36 @@ extern "C" int hmv_sigma2(int nz, int nm, int nks, const double* sPzk_d, const d
   HMV_REQUIRE(sPzk_d && kw_d && ks_sig_d && R_d && w2_ws_d && sigma2_d, "hmv_sigma2: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const long long nw = (long long)nm * nks;
-  w2_table_kernel<<<cdiv(nw, 256), 256, 0, st>>>(nm, nks, ks_sig_d, R_d, taylor_switch, w2_ws_d);
+  w2_table_kernel<<<cdiv(nw, 256), 256, 0, st>>>(nm, nks, ks_sig_d, R_d, kw_d, taylor_switch, w2_ws_d);
   int rc = check_launch("w2_table_kernel");
   if (rc) return rc;
-  const int splits = sigma2_splits(nz, nm, nks);
+  const bool allz = (nks & 1) == 0 && (nm & 1) == 0 && (((size_t)sPzk_d | (size_t)w2_ws_d) & 15) == 0;
+  const int splits = sigma2_splits(nz, nm, nks, allz);
   int kchunk = cdiv(nks, splits);
   kchunk = cdiv(kchunk, BK) * BK;
-  dim3 grid(cdiv(nm, BN), cdiv(nz, BM), splits);
-  if (splits == 1) {
-    sigma2_gemm_kernel<<<grid, GT, 0, st>>>(nz, nm, nks, kchunk, sPzk_d, kw_d, w2_ws_d, sigma2_d, 0);
-    return check_launch("sigma2_gemm_kernel");
-  }
   double* part = w2_ws_d + nw;
   const long long n = (long long)nz * nm;
-  sigma2_gemm_kernel<<<grid, GT, 0, st>>>(nz, nm, nks, kchunk, sPzk_d, kw_d, w2_ws_d, part, n);
-  rc = check_launch("sigma2_gemm_kernel");
-  if (rc) return rc;
+  double* dst = splits == 1 ? sigma2_d : part;
+  if (allz) {
+    const int mt = sigma2_mt(nz);
+    dim3 grid(cdiv(nm, SG_BN), cdiv(nz, 8 * mt), splits);
+    const size_t smem = (size_t)(2 * 8 * mt * SG_ALD + 2 * SG_BK * SG_BLD) * sizeof(double);
+    cudaError_t e = cudaSuccess;
+#define HMV_SG(MTV)                                                                                                  \
+    case MTV:                                                                                                        \
+      e = cudaFuncSetAttribute(sigma2_gemm_kernel<MTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      if (e == cudaSuccess) sigma2_gemm_kernel<MTV><<<grid, SG_T, smem, st>>>(nz, nm, nks, kchunk, sPzk_d, w2_ws_d, dst, n); \
+      break;
+    switch (mt) { HMV_SG(4) HMV_SG(8) HMV_SG(16) default: HMV_SG(26) }
+#undef HMV_SG
+    if (e != cudaSuccess) return fail(HMV_E_CUDA, "sigma2_gemm_kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+    rc = check_launch("sigma2_gemm_kernel");
+  } else {
+    dim3 grid(cdiv(nm, BN), cdiv(nz, BM), splits);
+    sigma2_gemm_plain_kernel<<<grid, GT, 0, st>>>(nz, nm, nks, kchunk, sPzk_d, w2_ws_d, dst, n);
+    rc = check_launch("sigma2_gemm_plain_kernel");
+  }
+  if (rc || splits == 1) return rc;
   splitk_reduce_kernel<<<cdiv(n, 256), 256, 0, st>>>(n, splits, part, sigma2_d);
   return check_launch("splitk_reduce_kernel");
 }
