@@ -2,16 +2,17 @@
 //
 // The reference evaluates  u = [sin x (Si X - Si x) - sin(cx)/X + cos x (Ci X - Ci x)]/m_c,  X=(1+c)x, x = k r_s (1+z),
 // with two scipy.special.sici calls per (z,M,k).  That closed form is the integral
-//        u(x; c) = (1/m_c) int_0^c  t/(1+t)^2  sinc(x t) dt ,
-// so for x c <= 16 (60-95% of every halo's k-range) this kernel sums its Maclaurin series in y = (x c)^2,
-//        u = sum_n A_n y^n ,   A_n = (-1)^n c^2 Itilde_n / ((2n+1)! m_c) ,  Itilde_n = int_0^1 s^(2n+1)/(1+cs)^2 ds ,
-// whose per-halo coefficients come from a small pre-pass (three-term recurrence in the moment order for c >= 1.5,
-// 64-point Gauss-Legendre below) -- 5 to 39 FMAs per element instead of two Si/Ci pairs, three sincos and a log.
-// Truncation + cancellation error of the series is < 1e-11 relative (worst at x c = 16).  Beyond x c = 16 the
-// Si/Ci form is evaluated directly with the device routines in sici.cuh.
-//
-// One CTA per halo row (z,M); each warp walks 256-wide k chunks (8 elements per lane sharing every coefficient load,
-// warp-uniform term count) and writes the row once, coalesced: 8 B/element of algorithmic traffic.
+//        u(x; c) = (1/m_c) int_0^c  t/(1+t)^2  sinc(x t) dt .
+// Two evaluations are built on it (hmv_set_nfw_mode):
+//   0 (default)  per-halo piecewise polynomials in (x c)^2 on 21 fixed intervals up to x c = 64 whose coefficients come
+//                from one FP64 tensor-core contraction (second half of this file), the closed form's asymptotic
+//                branch beyond;
+//   1            the Maclaurin series in y = (x c)^2 for x c <= 16,
+//                    u = sum_n A_n y^n ,  A_n = (-1)^n c^2 Itilde_n / ((2n+1)! m_c) ,  Itilde_n = int_0^1 s^(2n+1)/(1+cs)^2 ds ,
+//                with per-halo coefficients from a small pre-pass (three-term recurrence in the moment order for
+//                c >= 1.5, 64-point Gauss-Legendre below; 5 to 39 FMAs per element, < 1e-11 relative), and the Si/Ci
+//                form with the device routines of sici.cuh beyond -- round 1's path, kept as the cross-check of the
+//                polynomial tables (one CTA per halo row, 256-wide k chunks, 8 elements per lane).
 #include "common.cuh"
 #include "nfw_device.cuh"
 #include "nfw_poly.cuh"

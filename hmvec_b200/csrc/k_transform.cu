@@ -20,9 +20,11 @@
 // fragment) -- ncu evidence in profiles/.
 //
 // Two launch plans (hmv_set_transform_mode):
-//   0 (default)  profile_transform_ws_kernel: ONE persistent, warp-specialised kernel (second half of this file) --
-//                producer warps evaluate + transform 16 halos at a time, consumer warps interpolate + store, the two
-//                overlapped through a ring of bin tables in L2;
+//   0 (default)  profile_transform_ws_kernel: ONE persistent kernel (second half of this file) -- two independent
+//                8-warp groups per SM, each evaluating + transforming 16 halos and then interpolating + storing their
+//                rows, so that one group's tensor-core phase overlaps the other's store phase.  The same kernel also
+//                runs the two phases as separate launches around a resident table array (hmv_profile_tables /
+//                hmv_profile_expand: consumers that only integrate over M read the tables and never need the cube);
 //   1            profile_transform_kernel: one CTA owns 8 halos and runs evaluation, sums and interpolation one after
 //                the other with the bin table in shared memory; because the number of bins a halo needs grows like
 //                M^(1/3) (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints
