@@ -79,6 +79,13 @@ _SIGS = {
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
     "hmv_ksz_nvv_integral": (_i, [_i, _i, _p, _p, _ll, _p, _ll, _p, _ll, _p, _p, _p]),
     "hmv_pack_sum": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p]),
+    "hmv_peer_alloc": (_i, [_ll, C.POINTER(_p), C.c_char_p]),
+    "hmv_peer_open": (_i, [C.c_char_p, C.POINTER(_p)]),
+    "hmv_peer_close": (_i, [_p]),
+    "hmv_peer_free": (_i, [_p]),
+    "hmv_peer_scatter": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _i, _i, C.POINTER(_p), C.POINTER(_p), _ll,
+                              C.c_ulonglong, _p, _p]),
+    "hmv_peer_wait": (_i, [_p, _i, C.c_ulonglong, _d, _p, _p]),
     "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "hmv_outer": (_i, [_i, _i, _p, _p, _p, _p]),
     "hmv_sum2": (_i, [_ll, _p, _p, _p, _p]),

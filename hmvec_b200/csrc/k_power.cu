@@ -10,6 +10,7 @@
 //   power_pair_kernel      any tracer pair (matter / HOD / pressure), up to four distinct cubes
 //   power_six_kernel       {mm, ee, me, gg, gm, ge} in one pass over two cubes
 //   power_six_nfw_kernel   the same with the NFW profile evaluated in-kernel (spectra-only fusion)
+#include <cstdlib>
 #include "common.cuh"
 #include "nfw_device.cuh"
 #include "nfw_poly.cuh"
@@ -320,12 +321,44 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
   }
 }
 
+// k-tile width for a grid of nz x ceil(ldk / tile) CTAs on `per_sm` CTA slots per SM.  Measured on B200
+// (gpurun_out/r2_k5_tiles.txt): a FULL wave is HBM-bound, its time proportional to the tile width; a CTA running in a
+// part-filled wave is latency-bound and takes ~0.71 of a full 512-column wave whatever its width (each consumer warp
+// walks the whole mass axis for its 64 columns).  So a narrower tile pays only when it moves CTAs out of a thin last
+// wave: a 25-z slab (one rank of an 8-GPU run) has 500 CTAs = 3 waves + 56 at 512 columns, 575 = 3 waves + 131 at 448
+// columns (1.25 -> 1.15 ms); on 100 or 200 redshifts 512 stays best.  Multiples of 16 doubles keep rows 128-B aligned.
+static int wave_tile(int nz, int ldk, int tile_max, int per_sm) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0)
+      sms = 148;
+  }
+  if (const char* e = getenv("HMV_TILE")) {                 // measurement knob: force a width
+    const int t = atoi(e);
+    if (t >= 16 && t <= tile_max && t % 16 == 0) return t;
+  }
+  const long long slots = (long long)sms * per_sm;
+  const double lone = 0.71 * tile_max;                      // a latency-bound CTA, in units of columns of a full wave
+  int best = tile_max;
+  double best_cost = -1.0;
+  for (int t = tile_max; t >= tile_max * 3 / 4; t -= 16) {
+    const long long ctas = (long long)nz * cdiv(ldk, t);
+    const long long full = ctas / slots, rem = ctas % slots;
+    const double cost = (double)full * t + (rem ? fmax(lone, (double)rem / (double)slots * t) : 0.0);
+    if (best_cost < 0.0 || cost < best_cost - 1e-9) { best_cost = cost; best = t; }
+  }
+  return best;
+}
+
 constexpr int SIX_K = 512, SIX_R = 4, SIX_NST = 6, SIX_CT = 256;   // k per CTA, rows per stage, stages, consumers
 constexpr int SIX_STAGE_DOUBLES = 2 * SIX_R * SIX_K + SIX_R * 8;
 constexpr size_t SIX_SMEM = (size_t)SIX_NST * SIX_STAGE_DOUBLES * sizeof(double) + 2 * SIX_NST * sizeof(unsigned long long);
 
 struct SixArgs {
   int nz, nm, nk, ldk;
+  int tk;                  // k per CTA (multiple of 16, <= SIX_K): chosen per launch so that the grid fills whole waves
   long long spec_stride;   // doubles between consecutive spectra in p1h/p2h
   const double *um, *ue, *coef;
   const double *zoff, *ks, *Pzk;
@@ -339,8 +372,8 @@ __global__ void __launch_bounds__(SIX_CT + 32, 1) power_six_kernel(const SixArgs
   unsigned long long* full = reinterpret_cast<unsigned long long*>(ring + (size_t)SIX_NST * SIX_STAGE_DOUBLES);
   unsigned long long* empty = full + SIX_NST;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int z = blockIdx.y, k0 = blockIdx.x * SIX_K;
-  const int segk = min(SIX_K, a.ldk - k0);                 // doubles per row segment (multiple of 2)
+  const int z = blockIdx.y, k0 = blockIdx.x * a.tk;
+  const int segk = min(a.tk, a.ldk - k0);                  // doubles per row segment (multiple of 2)
   const long long zrow = (long long)z * a.nm;
   const int nit = (a.nm + SIX_R - 1) / SIX_R;
   if (tid == 0) {
@@ -1057,7 +1090,8 @@ extern "C" int hmv_power_six(int nz, int nm, int nk, int ldk, const double* ms_d
   a.zoff = zoff; a.ks = ks_d; a.Pzk = Pzk_d; a.kstar = kstar; a.p1h = p1h_d; a.p2h = p2h_d;
   cudaError_t e = cudaFuncSetAttribute(power_six_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SIX_SMEM);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_six_kernel smem opt-in (%zu B): %s", SIX_SMEM, cudaGetErrorString(e));
-  dim3 grid(cdiv(ldk, SIX_K), nz);
+  a.tk = wave_tile(nz, ldk, SIX_K, 1);
+  dim3 grid(cdiv(ldk, a.tk), nz);
   power_six_kernel<<<grid, SIX_CT + 32, SIX_SMEM, st>>>(a);
   return check_launch("power_six_kernel");
 }

@@ -30,6 +30,7 @@
 //                M^(1/3) (10 ... N/2), CTAs are launched in four bin-count classes whose shared-memory footprints
 //                (33 / 49 / 82 / 176 KB) let the many small halos run several CTAs per SM.  N too large for 8 halos'
 //                bin tables in shared memory (> ~6400) falls back to a DFMA rotation recurrence.
+#include <cstdlib>
 #include "common.cuh"
 #include "gnfw_eval.cuh"
 
@@ -344,8 +345,8 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // tiles runs 8 independent accumulator chains (DMMA dependent-issue latency ~49 cycles, 16 cycles of pipe each).
 // Items are issued in an order that strides through the mass axis (golden-ratio step), so light (store-bound) and heavy
 // (DMMA-bound) groups alternate in every SM's queue instead of arriving as one heavy and one light phase; the last
-// redshift runs heavy-first so the queue drains on light items.  The parameters of the next item are fetched into
-// registers while the current one is being transformed.
+// three quarters of the redshifts (see ws_item, launch_transform_ws) run jointly heavy-first so the queue drains on light items.
+// The parameters of the next item are fetched into registers while the current one is being transformed.
 #ifndef HMV_K1_ABL
 #define HMV_K1_ABL 0       // measurement builds only, bit mask: 1 skip the sample evaluation, 2 skip the sine sums,
 #endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill
@@ -485,10 +486,20 @@ __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned 
 }
 
 // queue position -> (z, mass-group index counted from the heavy end)
-__device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int& z, int& q) {
-  z = item / nmg;
-  const int r = item - z * nmg;
-  q = (z == nz - 1) ? r : (int)(((long long)r * stride) % nmg);
+// The last `ntail` redshifts are issued jointly heavy-first -- mass group by mass group across those redshifts -- so
+// that the queue drains on the lightest items of the launch whatever the slab size; the redshifts in front of them
+// stride through the mass axis (a mixed head that desynchronises the groups' phases).
+__device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int ntail, int& z, int& q) {
+  const int nhead = (nz - ntail) * nmg;
+  if (item < nhead) {
+    z = item / nmg;
+    const int r = item - z * nmg;
+    q = (int)(((long long)r * stride) % nmg);
+  } else {
+    const int r = item - nhead;
+    q = r / ntail;
+    z = nz - ntail + (r - q * ntail);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -689,7 +700,7 @@ struct WsGroupShared {                        // per group
 };
 
 __global__ void __launch_bounds__(WS_NG * WS_GT, 1)
-profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride) {
+profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, int nitems, int stride, int ntail) {
   extern __shared__ double smem[];            // [WS_NG] sample buffers, each [NCH_MMA/4][8][4][2]
   __shared__ WsGroupShared gsh[WS_NG];
   __shared__ GnfwTables tabs;
@@ -725,7 +736,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   auto fetch = [&](int item) {
     if (item >= nitems) return;
     int z, q;
-    ws_item(item, p.nz, p.nmg, stride, z, q);
+    ws_item(item, p.nz, p.nmg, stride, ntail, z, q);
     f_jn = p.jn_cta[z * p.nmg + q];
     if (gt < WS_HB) {
       const int m = (p.nmg - 1 - q) * WS_HB + gt;
@@ -755,7 +766,7 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
   while (item < nitems) {
     if (gt == 0) G.nxt_item = atomicAdd(work_counter, 1);
     int z, q;
-    ws_item(item, p.nz, p.nmg, stride, z, q);
+    ws_item(item, p.nz, p.nmg, stride, ntail, z, q);
     const int jn = f_jn;
     const int m0 = (p.nmg - 1 - q) * WS_HB;
     HMV_DEV_ASSERT(jn >= 2 && jn <= p.J && m0 >= 0 && m0 < p.nm && z >= 0 && z < p.nz);
@@ -1105,7 +1116,14 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   if (q.ts_Q > 0) smem += (size_t)(TS_A2_DOUBLES + WS_NG * TS_SLICE) * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride);
+  // Measured (gpurun_out/r2_k1_tail*.txt, electron profile): heavy-first over the last three quarters of the
+  // redshifts behind a mixed head beats both the all-mixed order with a short heavy-first tail (25 z: 1.33 -> 1.20 ms,
+  // 200 z: 9.18 -> 8.92 ms) and heavy-first from the start (1.26 / 2.99 ms on 25 / 64 z)
+  int ntail = (3 * q.nz + 2) / 4;
+  if (ntail < cdiv(2LL * grid * WS_NG, q.nmg)) ntail = cdiv(2LL * grid * WS_NG, q.nmg);
+  if (const char* ev = getenv("HMV_K1_TAIL")) ntail = atoi(ev);          // measurement knob
+  ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
+  profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride, ntail);
   return check_launch("profile_transform_ws_kernel");
 }
 

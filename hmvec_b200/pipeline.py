@@ -188,6 +188,7 @@ class GridSix(object):
         self._ev = None
         self._Pfull = None
         self._Ppack = None
+        self._peer = None
         # the download (224 MB on the full grid) takes about as long as the reduction: start it early, end it small.
         # >= 12 redshifts per reduction launch: a 25-z slab (8 GPUs) still runs as two launches of ~1.7 waves each --
         # the same four wave-times as one launch of 3.4 -- and the first half's copy hides behind the second half
@@ -241,6 +242,8 @@ class GridSix(object):
         self.copy_stream.synchronize()
         torch.cuda.current_stream().synchronize()
         self._check_converged()
+        if self._peer is not None:
+            self._peer.check()
 
     # ------------------------------------------------------------------ the launch sequence
     def _mark(self, i):
@@ -409,19 +412,27 @@ class GridSix(object):
         L, d, ptr = capi.lib, self.d, capi.ptr
         nk, nq = self.nk, self.ncl
         rows = (0, 4, 6)[:nq]                                # mm, gm, yy in self.p1 / self.p2
-        if self._Ppack is None:
-            self._Ppack = torch.empty((self.nz, nq, nk), dtype=torch.float64, device=self.device)
-            self._pa = (C.c_void_p * nq)(*[self.p1[r].data_ptr() for r in rows])
-            self._pb = (C.c_void_p * nq)(*[self.p2[r].data_ptr() for r in rows])
-        capi.check(L.hmv_pack_sum(self.nz, nk, nq, self._pa, self._pb, ptr(self._Ppack), st), "hmv_pack_sum")
-        full = self._Ppack
-        if self.zcomm is not None:
-            # rank order is z order, so the gathered buffer is [nz_total][nq][nk]: each spectrum is a table with row
-            # stride nq*nk (hmv_limber's ldp)
-            if self._Pfull is None:
-                self._Pfull = torch.empty((self.zs_all.numel(), nq, nk), dtype=torch.float64, device=self.device)
-            self.zcomm.all_gather_rows(self._Ppack.view(self.nz, nq * nk), self._Pfull.view(-1, nq * nk))
-            full = self._Pfull
+        pg = self.zcomm.peer_gather(nq * nk) if hasattr(self.zcomm, "peer_gather") else None
+        if pg is not None:
+            # fused pack + all-gather: the summing kernel stores this slab's rows into every rank's table over NVLink
+            full = pg.gather([self.p1[r] for r in rows], [self.p2[r] for r in rows])
+            self._peer = pg
+            nl0 = 2
+        else:
+            if self._Ppack is None:
+                self._Ppack = torch.empty((self.nz, nq, nk), dtype=torch.float64, device=self.device)
+                self._pa = (C.c_void_p * nq)(*[self.p1[r].data_ptr() for r in rows])
+                self._pb = (C.c_void_p * nq)(*[self.p2[r].data_ptr() for r in rows])
+            capi.check(L.hmv_pack_sum(self.nz, nk, nq, self._pa, self._pb, ptr(self._Ppack), st), "hmv_pack_sum")
+            full = self._Ppack
+            nl0 = 1
+            if self.zcomm is not None:
+                # rank order is z order, so the gathered buffer is [nz_total][nq][nk]: each spectrum is a table with
+                # row stride nq*nk (hmv_limber's ldp)
+                if self._Pfull is None:
+                    self._Pfull = torch.empty((self.zs_all.numel(), nq, nk), dtype=torch.float64, device=self.device)
+                self.zcomm.all_gather_rows(self._Ppack.view(self.nz, nq * nk), self._Pfull.view(-1, nq * nk))
+                full = self._Pfull
         base, ldp, nzt = full.data_ptr(), nq * nk, full.shape[0]
         tab = [C.c_void_p(base + 8 * q * nk) for q in range(nq)]
         capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
@@ -434,7 +445,7 @@ class GridSix(object):
             capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
                                     tab[2], None, nzt, ptr(self.zs_all), ptr(d["pref_yy"]), ptr(d["chis"]),
                                     ptr(self.cl[2]), st), "hmv_limber(yy)")
-        return 1 + nq
+        return nl0 + nq
 
     def spectra(self):
         """Download and return ({tag: P1h}, {tag: P2h}, C_kk, C_kg) as numpy (synchronises); with the tSZ leg the

@@ -5,9 +5,15 @@ per z, mass integrals reduce over M), so each rank owns a contiguous z-slab and 
 no data-path collective.  The two places where redshifts couple:
   * the mthresh<->ngal bisection stops when EVERY z has converged (utils.py:26) -> one 8-byte AND all-reduce of the
     per-iteration pass masks (`ZComm.all_reduce_and`);
-  * the Limber integral runs along z (cosmology.py:903) -> one all-gather of each P(k,z) slab (`ZComm.all_gather_z`),
-    NCCL over NVLink on the GPUs (gloo on CPU tensors in the host-logic tests).
+  * the Limber integral runs along z (cosmology.py:903) -> one all-gather of the P(k,z) slabs.  On the GPUs of one
+    box this is `PeerGather`: the kernel that forms the tables stores them straight into every rank's gathered table
+    over NVLink (peer memory through CUDA IPC) and raises a step flag -- no collective launch.  NCCL
+    (`ZComm.all_gather_rows` / `all_gather_z`) is the fallback (HMV_PEER_GATHER=0, or no peer access); gloo on CPU
+    tensors in the host-logic tests.
 """
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -39,6 +45,14 @@ class ZComm(object):
         self.slab = slice(int(self.bounds[self.rank]), int(self.bounds[self.rank + 1]))
         self.nz_local = self.slab.stop - self.slab.start
         self._shifts = {}
+        self._peer = {}
+
+    def peer_gather(self, ncols):
+        """The `PeerGather` for gathered tables of `ncols` doubles per redshift (created collectively on first use --
+        every rank must ask for it at the same point), or None when peer access is unavailable or switched off."""
+        if ncols not in self._peer:
+            self._peer[ncols] = PeerGather.create(self, ncols)
+        return self._peer[ncols]
 
     def all_reduce_and(self, mask):
         """In-place bitwise AND of a 1-element int64 tensor over the ranks (the global bisection stop condition).
@@ -54,7 +68,10 @@ class ZComm(object):
     def all_gather_rows(self, local, out):
         """local: contiguous [nz_local, n] slab -> out: preallocated contiguous [nz_total, n], in place, no staging
         copies when every rank owns the same number of redshifts (the usual case); otherwise via all_gather_z."""
-        if self.nz_total == self.world * self.nz_local and local.is_contiguous() and out.is_contiguous():
+        pg = self.peer_gather(int(local.shape[1])) if local.is_cuda and local.is_contiguous() else None
+        if pg is not None:
+            out.copy_(pg.gather([local], None).view(self.nz_total, -1))
+        elif self.nz_total == self.world * self.nz_local and local.is_contiguous() and out.is_contiguous():
             dist.all_gather_into_tensor(out, local, group=self.group)
         else:
             out.copy_(self.all_gather_z(local))
@@ -98,3 +115,109 @@ class ZComm(object):
             parts = [recv[r * nmax: r * nmax + int(self.bounds[r + 1] - self.bounds[r])] for r in range(self.world)]
             full = torch.cat(parts, dim=0)
         return full.movedim(0, -2).contiguous()
+
+
+class _DevView(object):
+    """A raw device allocation seen by torch (zero-copy, through the CUDA array interface)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGather(object):
+    """All-gather of z-slab tables by peer stores (hmv_peer_scatter / hmv_peer_wait, csrc/k_peer.cu).
+
+    Each rank owns two [nz_total][ncols] tables (used alternately) and a flag array in one cudaMalloc'ed block that
+    every other rank of the box maps through CUDA IPC.  `gather(a, b)` queues, on the current stream, one kernel that
+    writes a (+ b) for this rank's rows into all tables and one that waits until every rank's rows of this step have
+    arrived; it returns the local table of this step as a CUDA tensor, valid until the gather after next."""
+
+    TIMEOUT_S = 20.0
+
+    def __init__(self):
+        self.base = None
+
+    @classmethod
+    def create(cls, zc, ncols):
+        from . import _capi as capi
+        if os.environ.get("HMV_PEER_GATHER", "1") == "0" or zc.world > 16 or not torch.cuda.is_available():
+            return None
+        if dist.get_backend(zc.group) != "nccl":
+            return None
+        self = cls()
+        self.zc, self.ncols = zc, int(ncols)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.table_doubles = zc.nz_total * self.ncols
+        self.flag_off = ((2 * self.table_doubles * 8 + 255) // 256) * 256
+        nbytes = self.flag_off + 256
+        base, handle = C.c_void_p(), C.create_string_buffer(64)
+        ok = capi.lib.hmv_peer_alloc(nbytes, C.byref(base), handle) == 0
+        handles = [None] * zc.world
+        dist.all_gather_object(handles, handle.raw if ok else None, group=zc.group)
+        ptrs = [None] * zc.world
+        if ok and all(h is not None for h in handles):
+            for r, h in enumerate(handles):
+                if r == zc.rank:
+                    ptrs[r] = base.value
+                    continue
+                q = C.c_void_p()
+                if capi.lib.hmv_peer_open(h, C.byref(q)) != 0:
+                    ok = False
+                    break
+                ptrs[r] = q.value
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=zc.group)        # all or nothing (also the start barrier)
+        self.base, self.ptrs = base.value, ptrs
+        if int(flag.item()) == 0:
+            self.close()
+            return None
+        self.step = 0
+        self.done = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._flags = (C.c_void_p * zc.world)(*[p + self.flag_off for p in ptrs])
+        self._bufs = [(C.c_void_p * zc.world)(*[p + 8 * half * self.table_doubles for p in ptrs]) for half in (0, 1)]
+        self._views = [torch.as_tensor(_DevView(self.base + 8 * half * self.table_doubles, self.table_doubles),
+                                       device=self.device) for half in (0, 1)]
+        return self
+
+    def gather(self, a, b=None):
+        """a, b: lists of nsp contiguous float64 CUDA tensors [nz_local, ncols // nsp] (b or its entries may be None).
+        Returns the gathered [nz_total, nsp, ncols // nsp] table (row r of spectrum s = a[s][r] + b[s][r])."""
+        from . import _capi as capi
+        nsp, zc = len(a), self.zc
+        n = int(a[0].shape[1])
+        if nsp * n != self.ncols or any(t.shape != (zc.nz_local, n) for t in a):
+            raise ValueError("PeerGather: tables must be %d x [%d, %d]" % (nsp, zc.nz_local, self.ncols // max(nsp, 1)))
+        self.step += 1
+        half = self.step & 1
+        pa = (C.c_void_p * nsp)(*[capi.ptr(t).value for t in a])
+        pb = (C.c_void_p * nsp)(*[capi.ptr(t).value if t is not None else None for t in b]) if b is not None else None
+        st = capi.stream()
+        capi.check(capi.lib.hmv_peer_scatter(zc.nz_local, n, nsp, pa, pb, zc.world, zc.rank, self._bufs[half],
+                                             self._flags, int(zc.bounds[zc.rank]), self.step,
+                                             C.c_void_p(self.done.data_ptr()), st), "hmv_peer_scatter")
+        capi.check(capi.lib.hmv_peer_wait(C.c_void_p(self.base + self.flag_off), zc.world, self.step, self.TIMEOUT_S,
+                                          C.c_void_p(self.status.data_ptr()), st), "hmv_peer_wait")
+        return self._views[half].view(zc.nz_total, nsp, n)
+
+    def check(self):
+        """Synchronising: raise if a wait gave up (a rank never delivered its rows)."""
+        s = int(self.status.item())
+        if s:
+            raise RuntimeError("PeerGather: rank %d's rows did not arrive within %.0f s" % (s - 1, self.TIMEOUT_S))
+
+    def close(self):
+        from . import _capi as capi
+        if self.base is None:
+            return
+        try:
+            torch.cuda.synchronize()
+            for r, p in enumerate(self.ptrs):
+                if p is not None and r != self.zc.rank:
+                    capi.lib.hmv_peer_close(C.c_void_p(p))
+            capi.lib.hmv_peer_free(C.c_void_p(self.base))
+        except Exception:
+            pass
+        self.base = None

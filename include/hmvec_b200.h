@@ -235,6 +235,27 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
 int hmv_pack_sum(int nz, int nk, int nsp, const double* const* a_h, const double* const* b_h, double* out_d,
                  void* stream);
 
+/* ---- (e) multi-GPU: the z-sharded run's one exchange, fused into the kernel that forms the tables -----------------
+ * (cosmology.py:867-904 integrates P(k,z) over ALL redshifts; zshard.py shards z over the GPUs of one box.)
+ * hmv_peer_scatter is hmv_pack_sum whose stores go over NVLink into the gathered [nrow_total][nsp][ncol] table of
+ * EVERY rank: peer_buf_h[p] / peer_flag_h[p] are this process's mappings of rank p's table and of its flag array
+ * (HMV_MAX_PEERS x uint64, zero-initialised), obtained with hmv_peer_alloc on the owner and hmv_peer_open (CUDA IPC,
+ * one box) on the others; entry `rank` is the local allocation.  The last CTA stores `step` (> 0, increasing) to
+ * flag[rank] on every peer; hmv_peer_wait queues a one-CTA kernel that returns once all npeers flags have reached
+ * `step` (or sets *status_d = 1 + the missing rank after timeout_s; it never hangs).  Alternate two tables by step
+ * parity; scatter, wait and the consumers of one rank must be queued on one stream.  done_d: one zeroed uint32.
+ * These are the only entry points that allocate: peer buffers must come from cudaMalloc to be exportable. */
+#define HMV_MAX_PEERS 16
+int hmv_peer_alloc(long long bytes, void** ptr_out, unsigned char* handle64_out);
+int hmv_peer_open(const unsigned char* handle64, void** ptr_out);
+int hmv_peer_close(void* ptr);
+int hmv_peer_free(void* ptr);
+int hmv_peer_scatter(int nrow, int ncol, int nsp, const double* const* a_h, const double* const* b_h, int npeers,
+                     int rank, void* const* peer_buf_h, void* const* peer_flag_h, long long row0,
+                     unsigned long long step, unsigned int* done_d, void* stream);
+int hmv_peer_wait(const void* flags_d, int npeers, unsigned long long step, double timeout_s, int* status_d,
+                  void* stream);
+
 /* ---- f2: kSZ consumer -- the short-wavelength integral of the velocity-reconstruction noise
  * (ksz.py:299-336, Nvv_core_integral):  out[b] = trapz_kS( kS Pge[b,kS]^2 / (Pgg_tot[b,kS] C_tot(chi* kS)) ) with
  * non-finite integrand values set to zero (ksz.py:98-100).  b = 0..nb-1 runs over the (mu,kL) plane when the spectra

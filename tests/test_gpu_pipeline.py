@@ -122,10 +122,11 @@ def test_z_sharding_emulated_on_one_gpu(setup):
     assert_close(ga2.last_cyy, g["C_yy"], 1e-6, name="sharded C_yy")
 
 
-def _nccl_worker(rank, world, port, q):
+def _nccl_worker(rank, world, port, q, peer):
     import torch
     import torch.distributed as dist
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      HMV_PEER_GATHER=str(peer))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
     try:
@@ -135,14 +136,30 @@ def _nccl_worker(rank, world, port, q):
         inp = pipeline.make_inputs(g["zs"], g["ms"], g["ks"], ngal=g["g2_ngal_target"], ells=g["ells"])
         zc = zshard.ZComm(g["zs"].size)
         gs = pipeline.GridSix(pipeline.slab_inputs(inp, zc.slab), zcomm=zc, nz_total_zs=g["zs"])
-        gs.upload(); gs.run()
+        gs.upload()
+        for _ in range(3):                       # three steps: both halves of the peer tables are reused
+            gs.run()
         p1, p2, ckk, ckg = gs.spectra()
-        q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg, gs.last_cyy))
+        # the row gather on its own, odd row length (scalar stores), against NCCL's all_gather
+        gen = torch.Generator(device="cuda").manual_seed(7 + rank)
+        loc = torch.rand((zc.nz_local, 37), dtype=torch.float64, device="cuda", generator=gen)
+        outp = torch.empty((zc.nz_total, 37), dtype=torch.float64, device="cuda")
+        zc.all_gather_rows(loc, outp)
+        parts = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        rows_ok = bool(torch.equal(outp, torch.cat(parts, dim=0)))
+        if gs._peer is not None:
+            gs._peer.check()
+        q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg, gs.last_cyy,
+               gs._peer is not None, rows_ok))
     finally:
         dist.destroy_process_group()
 
 
-def test_z_sharding_nccl_two_gpus(setup):
+@pytest.mark.parametrize("peer", [1, 0], ids=["peer-stores", "nccl-gather"])
+def test_z_sharding_nccl_two_gpus(setup, peer):
+    """Two ranks over NCCL: the all-z bisection stop and the gathered Limber step reproduce the one-GPU answer, with
+    the gather done by peer stores over NVLink (hmv_peer_scatter / hmv_peer_wait) and by NCCL's all-gather."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (covered on one GPU by test_z_sharding_emulated_on_one_gpu)")
@@ -152,7 +169,7 @@ def test_z_sharding_nccl_two_gpus(setup):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port + peer, q, peer)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted((q.get(timeout=300) for _ in procs), key=lambda o: o[0])
@@ -165,6 +182,8 @@ def test_z_sharding_nccl_two_gpus(setup):
         assert_close(o[5], fkk, 1e-12)
         assert_close(o[6], fkg, 1e-12)
         assert_close(o[7], g["C_yy"], 1e-6)
+        assert o[8] == bool(peer), "peer-store gather %s" % ("was not used" if peer else "ran although switched off")
+        assert o[9], "all_gather_rows differs from NCCL's all_gather"
 
 
 def test_large_grid_properties():
