@@ -289,19 +289,29 @@ def run_b200(a):
         g.run()
     barrier()
 
-    # ---- device-resident timing, stage boundaries marked with events on the launching stream -------------------
-    nst = len(g.STAGES) + 1
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(nst)] for _ in range(a.steps)]
+    # ---- device-resident timing: the launch sequence as it ships (independent legs on their own streams) ---------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0.record()
+    for s in range(a.steps):
+        g.run()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- per-stage times: the same steps again with the stages strictly one after the other on one stream and an
+    # event at every stage boundary (a kernel's own duration, for the roofline entries; their sum is `serial_ms`) ----
+    nst = len(g.STAGES) + 1
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(nst)] for _ in range(a.steps)]
     barrier()
     e0.record()
     for s in range(a.steps):
         g.run(events=evs[s])
     e1.record()
     barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if sampler is not None else None
+    ms_serial = max_over_ranks(e0.elapsed_time(e1))
     stage_ms = np.array([[evs[s][i].elapsed_time(evs[s][i + 1]) for i in range(nst - 1)] for s in range(a.steps)])
     stage_ms = stage_ms.mean(axis=0)
 
@@ -345,6 +355,7 @@ def run_b200(a):
     k1_flop = k1_flops(g.d["rs"], g.d["cmax"], g.xmax, g.nxs)
     k1p_flop = k1_flops(g.d["y_rs"], g.d["y_cmax"], g.p_xmax, g.p_nxs) if g.tsz else 0.0
     fused_nfw, ldk, mode = g.fused_nfw, g.ldk, g.transform_mode
+    overlap_level = int(g.overlap)
     tsz_tables = g.tsz_tables
     ytab_bytes = 0.0
     if tsz_tables:      # bins the Compton-y tables actually hold: sum over halos of (bin count + 2) doubles
@@ -473,13 +484,17 @@ def run_b200(a):
                                 "SURVEY 8(d) algorithmic traffic of the whole step incl. the tSZ leg (3 cubes written + "
                                 "read once, 14 spectra) over the step time"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_total / a.steps, "serial_ms_per_step": ms_serial / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "parallelism": "z-sharded x%d" % world,
                        "nfw": "evaluated inside the mass reduction (spectra-only fusion)" if fused_nfw else
                               "cube materialised in HBM",
                        "tsz": "Compton-y profile kept as bin tables, P_yy reduced from them (no third cube)" if tsz_tables else
                               "Compton-y cube materialised",
+                       "streams": ("overlap level %d (0: one stream + HOD side stream; 1: sigma^2/n(M)/HOD leg beside the NFW "
+                                   "cube; 2: + electron transform and tSZ leg on their own streams), chosen from the slab "
+                                   "size; kernels{} and roofline from a second pass with the stages serialised "
+                                   "(serial_ms_per_step)") % overlap_level,
                        "l2": "inputs exceed L2 (%s %.1f GB cubes per rank)" % ("two" if tsz_tables else "three", 8e-9 * nzl * nm * ldk)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_api * world / a.steps),
                     "d2h_bytes_per_step": int(d2h_api * world / a.steps), "ms_per_step": ms_api / a.steps,

@@ -39,6 +39,11 @@ class Tracer(C.Structure):
                 ("NsNsm1_d", _p), ("ngal_d", _p), ("bias_d", _p)]
 
 
+class LimberJob(C.Structure):
+    """struct hmv_limber_job (include/hmvec_b200.h)"""
+    _fields_ = [("P_d", _p), ("P2_d", _p), ("ngz", _i), ("gzs_d", _p), ("pref_d", _p), ("chis_d", _p), ("cl_d", _p)]
+
+
 _SIGS = {
     "hmv_abi_version": (_i, []),
     "hmv_last_error": (C.c_char_p, []),
@@ -77,6 +82,7 @@ _SIGS = {
     "hmv_power_six_nfw": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _d, _d, _p, _p, _p, _p, _p, _p, _p, _p, _p, _ll,
                                _p, _p, _p]),
     "hmv_limber": (_i, [_i, _p, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "hmv_limber_multi": (_i, [_i, C.POINTER(LimberJob), _i, _p, _i, _i, _i, _p, _p, _p]),
     "hmv_ksz_nvv_integral": (_i, [_i, _i, _p, _p, _ll, _p, _ll, _p, _ll, _p, _p, _p]),
     "hmv_pack_sum": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p, _p]),
     "hmv_peer_alloc": (_i, [_ll, C.POINTER(_p), C.c_char_p]),

@@ -16,12 +16,12 @@ __device__ __forceinline__ int interval(const double* __restrict__ x, int n, dou
   return lo;
 }
 
-__global__ void limber_kernel(int nl, const double* __restrict__ ells, int nzp, int nk, int ldp,
-                              const double* __restrict__ zs, const double* __restrict__ ks,
-                              const double* __restrict__ P, const double* __restrict__ P2, int ngz,
-                              const double* __restrict__ gzs,
-                              const double* __restrict__ pref, const double* __restrict__ chis,
-                              double* __restrict__ cl) {
+__device__ __forceinline__ void limber_warp(int nl, const double* __restrict__ ells, int nzp, int nk, int ldp,
+                                            const double* __restrict__ zs, const double* __restrict__ ks,
+                                            const double* __restrict__ P, const double* __restrict__ P2, int ngz,
+                                            const double* __restrict__ gzs,
+                                            const double* __restrict__ pref, const double* __restrict__ chis,
+                                            double* __restrict__ cl) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= nl) return;
   const double ell = ells[warp];
@@ -52,6 +52,24 @@ __global__ void limber_kernel(int nl, const double* __restrict__ ells, int nzp, 
   }
   acc = warp_sum(acc);
   if (lane == 0) cl[warp] = acc;
+}
+
+__global__ void limber_kernel(int nl, const double* __restrict__ ells, int nzp, int nk, int ldp,
+                              const double* __restrict__ zs, const double* __restrict__ ks,
+                              const double* __restrict__ P, const double* __restrict__ P2, int ngz,
+                              const double* __restrict__ gzs,
+                              const double* __restrict__ pref, const double* __restrict__ chis,
+                              double* __restrict__ cl) {
+  limber_warp(nl, ells, nzp, nk, ldp, zs, ks, P, P2, ngz, gzs, pref, chis, cl);
+}
+
+// several projections of tables on one (z, k) grid in ONE launch (blockIdx.y = job): each is latency-bound (two
+// binary searches and a bilinear lookup per redshift), so C_kk, C_kg and C_yy take the time of one
+struct LimberJobs { hmv_limber_job j[HMV_LIMBER_MAXJOBS]; };
+__global__ void limber_multi_kernel(int nl, const double* __restrict__ ells, int nzp, int nk, int ldp,
+                                    const double* __restrict__ zs, const double* __restrict__ ks, const LimberJobs q) {
+  const hmv_limber_job& j = q.j[blockIdx.y];
+  limber_warp(nl, ells, nzp, nk, ldp, zs, ks, j.P_d, j.P2_d, j.ngz, j.gzs_d, j.pref_d, j.chis_d, j.cl_d);
 }
 
 // ---- measurement helpers -----------------------------------------------------------------------------
@@ -140,6 +158,23 @@ extern "C" int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp
   limber_kernel<<<cdiv(nl, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, P_d, P2_d,
                                                                       ngz, gzs_d, pref_d, chis_d, cl_d);
   return check_launch("limber_kernel");
+}
+
+extern "C" int hmv_limber_multi(int njobs, const hmv_limber_job* jobs_h, int nl, const double* ells_d, int nzp, int nk,
+                                int ldp, const double* zs_d, const double* ks_d, void* stream) {
+  HMV_REQUIRE(njobs >= 1 && njobs <= HMV_LIMBER_MAXJOBS && jobs_h, "hmv_limber_multi: 1..%d jobs", HMV_LIMBER_MAXJOBS);
+  HMV_REQUIRE(nl > 0 && nzp > 0 && nk >= 2 && ldp >= nk && ells_d && zs_d && ks_d, "hmv_limber_multi: bad sizes");
+  LimberJobs q;
+  memset(&q, 0, sizeof(q));
+  for (int i = 0; i < njobs; ++i) {
+    q.j[i] = jobs_h[i];
+    HMV_REQUIRE(q.j[i].P_d && q.j[i].gzs_d && q.j[i].pref_d && q.j[i].chis_d && q.j[i].cl_d && q.j[i].ngz > 0,
+                "hmv_limber_multi: job %d: null pointer or ngz <= 0", i);
+  }
+  const int wpb = 4;
+  dim3 grid(cdiv(nl, wpb), njobs);
+  limber_multi_kernel<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(nl, ells_d, nzp, nk, ldp, zs_d, ks_d, q);
+  return check_launch("limber_multi_kernel");
 }
 
 extern "C" int hmv_ksz_nvv_integral(int nb, int nk, const double* ks_d, const double* pge_d, long long pge_stride,

@@ -322,11 +322,12 @@ __global__ void __launch_bounds__(256) power_six_prep_kernel(int nm, const doubl
 }
 
 // k-tile width for a grid of nz x ceil(ldk / tile) CTAs on `per_sm` CTA slots per SM.  Measured on B200
-// (gpurun_out/r2_k5_tiles.txt): a FULL wave is HBM-bound, its time proportional to the tile width; a CTA running in a
-// part-filled wave is latency-bound and takes ~0.71 of a full 512-column wave whatever its width (each consumer warp
-// walks the whole mass axis for its 64 columns).  So a narrower tile pays only when it moves CTAs out of a thin last
-// wave: a 25-z slab (one rank of an 8-GPU run) has 500 CTAs = 3 waves + 56 at 512 columns, 575 = 3 waves + 131 at 448
-// columns (1.25 -> 1.15 ms); on 100 or 200 redshifts 512 stays best.  Multiples of 16 doubles keep rows 128-B aligned.
+// (gpurun_out/r2_k5_tiles.txt): a wave of 512-column CTAs is HBM-bound (0.33 ms for 2000 masses); narrower CTAs do not
+// get proportionally faster -- below ~440 columns a wave takes 0.285 ms whatever its width, because every consumer warp
+// still walks the whole mass axis for its 64 columns -- and a CTA in a thin last wave takes ~0.24 ms.  So a narrower
+// tile pays only when it moves CTAs out of a thin last wave of a grid that is a few waves deep: a 25-z slab (one rank
+// of an 8-GPU run) has 500 CTAs = 3 waves + 56 at 512 columns, 575 = 3 waves + 131 at 448 (1.25 -> 1.15 ms); 100 or
+// 200 redshifts stay at 512 (a predicted gain below 3 % is not taken).  Multiples of 16 doubles keep rows 128-B aligned.
 static int wave_tile(int nz, int ldk, int tile_max, int per_sm) {
   static int sms = 0;
   if (sms == 0) {
@@ -340,14 +341,19 @@ static int wave_tile(int nz, int ldk, int tile_max, int per_sm) {
     if (t >= 16 && t <= tile_max && t % 16 == 0) return t;
   }
   const long long slots = (long long)sms * per_sm;
-  const double lone = 0.71 * tile_max;                      // a latency-bound CTA, in units of columns of a full wave
-  int best = tile_max;
-  double best_cost = -1.0;
-  for (int t = tile_max; t >= tile_max * 3 / 4; t -= 16) {
+  const double unit = tile_max / 0.33;                      // columns of a full-width wave per millisecond
+  const double floor_w = 0.285 * unit, lone = 0.24 * unit;
+  auto cost = [&](int t) {
     const long long ctas = (long long)nz * cdiv(ldk, t);
     const long long full = ctas / slots, rem = ctas % slots;
-    const double cost = (double)full * t + (rem ? fmax(lone, (double)rem / (double)slots * t) : 0.0);
-    if (best_cost < 0.0 || cost < best_cost - 1e-9) { best_cost = cost; best = t; }
+    return (double)full * fmax((double)t, floor_w) + (rem ? fmax(lone, (double)rem / (double)slots * t) : 0.0);
+  };
+  int best = tile_max;
+  double best_cost = cost(tile_max);
+  const double need = 0.97 * best_cost;
+  for (int t = tile_max - 16; t >= tile_max * 7 / 8; t -= 16) {
+    const double c = cost(t);
+    if (c < need && c < best_cost) { best_cost = c; best = t; }
   }
   return best;
 }

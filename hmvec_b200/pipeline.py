@@ -200,6 +200,21 @@ class GridSix(object):
         self.hod_stream = torch.cuda.Stream(device=self.device)
         self.ev_mf, self.ev_hod = torch.cuda.Event(), torch.cuda.Event()
         self.hod_overlap = True
+        # `overlap` (used when run() is not asked for per-stage events): 1 = the whole sigma^2 -> n(M), b(M) -> HOD leg runs
+        # on the side stream next to the NFW cube (which needs only the halo geometry) and rejoins in front of the mass
+        # integrals; 2 = also the electron transform and the tSZ leg (pressure tables -> P_yy) on streams of their own.
+        # The big kernels still run one after the other (each fills every SM), but a kernel's drain -- SMs idle while
+        # its last CTAs finish -- is taken by the next leg's first CTAs and the small kernels disappear behind the cubes.
+        # That pays on small slabs only (tools/slab_skew.py, medians of interleaved runs, levels 0 / 1 / 2:
+        # 25 z 4.80 / 4.73 / 4.54 ms, 50 z 9.13 / 9.09 / 8.92, 100 z 17.69 / 17.61 / 17.79, 200 z 35.02 / 35.27 / 35.18 --
+        # on long slabs P_yy's table gathers and the six-spectra stream evict each other from L2).
+        self.overlap = 2 if nz <= 64 else (1 if nz <= 128 else 0)
+        self.ev_geo = torch.cuda.Event()
+        self.e_stream = torch.cuda.Stream(device=self.device)
+        self.y_stream = torch.cuda.Stream(device=self.device)
+        self.ev_geo2, self.ev_m200, self.ev_e, self.ev_ydone = (torch.cuda.Event() for _ in range(4))
+        if self.tsz:
+            self.d["tr_ws_y"] = E(int(capi.lib.hmv_profile_transform_ws_doubles(nz, nm, self.p_nxs)))
         self.h_iters = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     # ------------------------------------------------------------------ host <-> device
@@ -251,76 +266,159 @@ class GridSix(object):
             self._ev[i].record()
 
     def run(self, events=None, overlap_d2h=False):
-        """Issue the whole path on the current stream.  `events`: optional list of len(STAGES)+1 CUDA events
-        recorded at the stage boundaries (per-kernel timing for the roofline report).  overlap_d2h: end-to-end mode --
-        the spectra leave for the pinned host buffers chunk by chunk on a copy stream while later chunks compute;
-        finish with `finish_e2e()`."""
-        L, d, ptr, st = capi.lib, self.d, capi.ptr, capi.stream()
-        nz, nm, nk, ldk = self.nz, self.nm, self.nk, self.ldk
-        p = self.p
+        """Issue the whole path.  `events`: optional list of len(STAGES)+1 CUDA events recorded at the stage boundaries
+        (per-kernel timing for the roofline report) -- the stages then run strictly one after the other on the current
+        stream; without them the sigma^2 -> n(M), b(M) -> HOD leg runs on a side stream next to the NFW cube (see
+        `overlap` in __init__) and rejoins in front of the mass integrals.  overlap_d2h: end-to-end mode -- the spectra
+        leave for the pinned host buffers chunk by chunk on a copy stream while later chunks compute; finish with
+        `finish_e2e()`."""
         self._ev = events
-        n = 0
+        self._n = 0
+        main = torch.cuda.current_stream()
+        level = self.overlap if (self.hod_overlap and events is None) else 0
+        side, legs = level >= 1, level >= 2 and not self.fused_nfw
         self._mark(0)
-        capi.check(L.hmv_sigma2(nz, nm, self.nks, ptr(d["sPzk"]), ptr(d["kw"]), ptr(d["ks_sig"]), ptr(d["R"]),
-                                float(p['Wkr_taylor_switch']), ptr(d["sig_ws"]), ptr(d["sigma2"]), st), "hmv_sigma2")
-        n += 3
-        self._mark(1)
-        capi.check(L.hmv_mass_function(nz, nm, ptr(d["sigma2"]), ptr(d["ms"]), self.rho_m0, p['st_A'], p['st_a'],
-                                       p['st_p'], p['st_deltac'], ptr(d["nzm"]), ptr(d["bh"]), st), "hmv_mass_function")
-        capi.check(L.hmv_halo_geometry(nz, nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["drho1"]), self.duffy[0], self.duffy[1],
-                                       self.duffy[2], self.h, ptr(d["cs"]), ptr(d["rvir"]), st), "hmv_halo_geometry")
-        n += 2
+        if side:
+            self.ev_geo.record(main)               # this step's inputs are queued on `main`
+            with torch.cuda.stream(self.hod_stream):
+                self.hod_stream.wait_event(self.ev_geo)
+                self._st_sigma2()
+                self._st_massfn()
+                self._hod_stage(self.hod_stream)
+        else:
+            self._st_sigma2()
+            self._mark(1)
+            self._st_massfn()
+        self._st_geometry()
         self._mark(2)
-        if self.hod_overlap:
-            self._hod_stage(torch.cuda.current_stream())      # side stream, concurrent with the cube kernels
+        if self.hod_overlap and not side:
+            self._hod_stage(main)                  # side stream, concurrent with the cube kernels
+        if legs:
+            self.ev_geo2.record(main)
         if not self.fused_nfw:
-            capi.check(L.hmv_uk_nfw(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["cs"]),
-                                    ptr(d["rvir"]), ptr(d["nfw_ws"]), ptr(self.um), st), "hmv_uk_nfw")
-            n += 3
+            self._st_nfw()
         self._mark(3)
-        capi.check(L.hmv_mdelta(nz, nm, ptr(d["ms"]), ptr(d["cs"]), ptr(d["drho1"]), ptr(d["drho2"]), ptr(d["m200c"]),
-                                st), "hmv_mdelta")
+        if legs:
+            with torch.cuda.stream(self.e_stream):
+                self.e_stream.wait_event(self.ev_geo2)
+                self._st_m200c()
+                self.ev_m200.record(self.e_stream)
+                self._st_electron()
+                self.ev_e.record(self.e_stream)
+        else:
+            self._st_m200c()
+            self._st_electron()
+        self._mark(4)
+        if self.tsz:
+            if legs:
+                with torch.cuda.stream(self.y_stream):
+                    self.y_stream.wait_event(self.ev_m200)
+                    self._st_pressure(self.d["tr_ws_y"])
+                    self.y_stream.wait_event(self.ev_mf)      # n(M), b(M): recorded by _hod_stage on the side stream
+                    self.y_stream.wait_event(self.ev_pzk)
+                    self._st_yy(overlap_d2h)
+                    self.ev_ydone.record(self.y_stream)
+            else:
+                self._st_pressure(self.d["tr_ws"])
+        self._mark(5)
+        if not self.hod_overlap:
+            self._hod_stage(main)
+        self._n += 6
+        self._mark(6)
+        main.wait_event(self.ev_pzk)                 # Pzk of this step has arrived (see upload)
+        if self.hod_overlap:
+            main.wait_event(self.ev_hod)             # n(M), b(M), occupations, ngal, bg are in place
+        if legs:
+            main.wait_event(self.ev_e)
+        self._st_six(overlap_d2h)
+        self._mark(7)
+        if self.tsz:
+            if legs:
+                main.wait_event(self.ev_ydone)
+            else:
+                self._st_yy(overlap_d2h)
+        self._mark(8)
+        if self.has_limber:
+            self._n += self._limber(capi.stream())
+        self._mark(9)
+        self.launches_per_run = self._n
+        self._ev = None
+
+    # ---- the stages (each issues on the CURRENT stream) ----
+    def _st_sigma2(self):
+        L, d, ptr, p = capi.lib, self.d, capi.ptr, self.p
+        capi.check(L.hmv_sigma2(self.nz, self.nm, self.nks, ptr(d["sPzk"]), ptr(d["kw"]), ptr(d["ks_sig"]), ptr(d["R"]),
+                                float(p['Wkr_taylor_switch']), ptr(d["sig_ws"]), ptr(d["sigma2"]), capi.stream()),
+                   "hmv_sigma2")
+        self._n += 3
+
+    def _st_massfn(self):
+        L, d, ptr, p, st = capi.lib, self.d, capi.ptr, self.p, capi.stream()
+        capi.check(L.hmv_mass_function(self.nz, self.nm, ptr(d["sigma2"]), ptr(d["ms"]), self.rho_m0, p['st_A'], p['st_a'],
+                                       p['st_p'], p['st_deltac'], ptr(d["nzm"]), ptr(d["bh"]), st), "hmv_mass_function")
+        self._n += 1
+
+    def _st_geometry(self):
+        L, d, ptr, st = capi.lib, self.d, capi.ptr, capi.stream()
+        capi.check(L.hmv_halo_geometry(self.nz, self.nm, ptr(d["zs"]), ptr(d["ms"]), ptr(d["drho1"]), self.duffy[0],
+                                       self.duffy[1], self.duffy[2], self.h, ptr(d["cs"]), ptr(d["rvir"]), st),
+                   "hmv_halo_geometry")
+        self._n += 1
+
+    def _st_nfw(self):
+        L, d, ptr = capi.lib, self.d, capi.ptr
+        capi.check(L.hmv_uk_nfw(self.nz, self.nm, self.nk, self.ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["cs"]),
+                                ptr(d["rvir"]), ptr(d["nfw_ws"]), ptr(self.um), capi.stream()), "hmv_uk_nfw")
+        self._n += 3
+
+    def _st_m200c(self):
+        L, d, ptr = capi.lib, self.d, capi.ptr
+        capi.check(L.hmv_mdelta(self.nz, self.nm, ptr(d["ms"]), ptr(d["cs"]), ptr(d["drho1"]), ptr(d["drho2"]),
+                                ptr(d["m200c"]), capi.stream()), "hmv_mdelta")
+        self._n += 1
+
+    def _st_electron(self):
+        L, d, ptr, st = capi.lib, self.d, capi.ptr, capi.stream()
+        nz, nm = self.nz, self.nm
         capi.check(L.hmv_gnfw_params(0, nz, nm, ptr(d["zs"]), ptr(d["m200c"]), ptr(d["rvir"]), ptr(d["rhocrit"]),
                                      ptr(d["hofz"]), self.fit9, self.gamma, 1.0, 1.0, 1.0, ptr(d["rs"]), ptr(d["cmax"]),
                                      ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]), ptr(d["oscale"]),
                                      st), "hmv_gnfw_params")
-        capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["rs"]),
+        capi.check(L.hmv_profile_transform(nz, nm, self.nk, self.ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["rs"]),
                                            ptr(d["cmax"]), ptr(d["xc"]), ptr(d["alpha"]), ptr(d["expo"]), ptr(d["amp"]),
                                            ptr(d["oscale"]), self.gamma, self.xmax, self.nxs, 1, ptr(d["tr_ws"]),
                                            ptr(self.ue), st), "hmv_profile_transform")
-        # mdelta, gnfw_params, sine_table, bin_count + one persistent kernel (or the four bin-count classes)
-        n += 5 if self.transform_mode == 0 else 8
-        self._mark(4)
-        if self.tsz:
-            # Compton-y profile (hmvec.py:252-316): pressure GNFW, no mass norm, scaled by 4 pi sigma_T/(m_e c^2)
-            # r200c^3 (1+z)^2/H -- the second invocation of the transform kernel
-            capi.check(L.hmv_gnfw_params(1, nz, nm, ptr(d["zs"]), ptr(d["m200c"]), ptr(d["rvir"]), ptr(d["rhocrit"]),
-                                         ptr(d["hofz"]), self.pfit9, float(p['battaglia_pres_gamma']),
-                                         float(p['battaglia_pres_alpha']), self.p_amp, self.p_pref, ptr(d["y_rs"]),
-                                         ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
-                                         ptr(d["y_amp"]), ptr(d["y_oscale"]), st), "hmv_gnfw_params(pressure)")
-            if self.tsz_tables:
-                capi.check(L.hmv_profile_tables(nz, nm, nk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
-                                                ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
-                                                ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
-                                                self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.ytab), st),
-                           "hmv_profile_tables(pressure)")
-            else:
-                capi.check(L.hmv_profile_transform(nz, nm, nk, ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
-                                                   ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
-                                                   ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
-                                                   self.p_xmax, self.p_nxs, 0, ptr(d["tr_ws"]), ptr(self.uy), st),
-                           "hmv_profile_transform(pressure)")
-            n += 4 if self.transform_mode == 0 else 7
-        self._mark(5)
-        if not self.hod_overlap:
-            self._hod_stage(torch.cuda.current_stream())
-        n += 6
-        self._mark(6)
+        # gnfw_params, sine_table, bin_count + one persistent kernel (or the four bin-count classes)
+        self._n += 4 if self.transform_mode == 0 else 7
+
+    def _st_pressure(self, ws):
+        # Compton-y profile (hmvec.py:252-316): pressure GNFW, no mass norm, scaled by 4 pi sigma_T/(m_e c^2)
+        # r200c^3 (1+z)^2/H -- the second invocation of the transform kernel
+        L, d, ptr, p, st = capi.lib, self.d, capi.ptr, self.p, capi.stream()
+        nz, nm, nk = self.nz, self.nm, self.nk
+        capi.check(L.hmv_gnfw_params(1, nz, nm, ptr(d["zs"]), ptr(d["m200c"]), ptr(d["rvir"]), ptr(d["rhocrit"]),
+                                     ptr(d["hofz"]), self.pfit9, float(p['battaglia_pres_gamma']),
+                                     float(p['battaglia_pres_alpha']), self.p_amp, self.p_pref, ptr(d["y_rs"]),
+                                     ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                     ptr(d["y_amp"]), ptr(d["y_oscale"]), st), "hmv_gnfw_params(pressure)")
+        if self.tsz_tables:
+            capi.check(L.hmv_profile_tables(nz, nm, nk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
+                                            ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                            ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
+                                            self.p_xmax, self.p_nxs, 0, ptr(ws), ptr(self.ytab), st),
+                       "hmv_profile_tables(pressure)")
+        else:
+            capi.check(L.hmv_profile_transform(nz, nm, nk, self.ldk, ptr(d["zs"]), ptr(d["ks"]), self.kmax, ptr(d["y_rs"]),
+                                               ptr(d["y_cmax"]), ptr(d["y_xc"]), ptr(d["y_alpha"]), ptr(d["y_expo"]),
+                                               ptr(d["y_amp"]), ptr(d["y_oscale"]), float(p['battaglia_pres_gamma']),
+                                               self.p_xmax, self.p_nxs, 0, ptr(ws), ptr(self.uy), st),
+                       "hmv_profile_transform(pressure)")
+        self._n += 4 if self.transform_mode == 0 else 7
+
+    def _st_six(self, overlap_d2h):
         # z-chunked so that (in e2e mode) the device->host copy of a finished chunk overlaps the next chunk's kernel
-        torch.cuda.current_stream().wait_event(self.ev_pzk)            # Pzk of this step has arrived (see upload)
-        if self.hod_overlap:
-            torch.cuda.current_stream().wait_event(self.ev_hod)        # occupations, ngal, bg are in place
+        L, d, ptr, p, st = capi.lib, self.d, capi.ptr, self.p, capi.stream()
+        nz, nm, nk, ldk = self.nz, self.nm, self.nk, self.ldk
         nchunk = self.d2h_chunks if overlap_d2h else 1
         zb = np.linspace(0, nz, nchunk + 1).round().astype(int)
         S = nz * nk
@@ -337,7 +435,7 @@ class GridSix(object):
                                                off(d["Nc"], z0, nm), off(d["Ns"], z0, nm), off(d["NcNs"], z0, nm),
                                                off(d["NsNsm1"], z0, nm), off(d["ngal"], z0, 1), ptr(d["pow_ws"]), S,
                                                off(self.p1, z0, nk), off(self.p2, z0, nk), st), "hmv_power_six_nfw")
-                n += 3
+                self._n += 3
             else:
                 capi.check(L.hmv_power_six(z1 - z0, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), off(d["nzm"], z0, nm),
                                            off(d["bh"], z0, nm), off(d["Pzk"], z0, nk), self.rho_m0,
@@ -346,7 +444,7 @@ class GridSix(object):
                                            off(d["NcNs"], z0, nm), off(d["NsNsm1"], z0, nm), off(d["ngal"], z0, 1),
                                            ptr(d["pow_ws"]), S, off(self.p1, z0, nk), off(self.p2, z0, nk), st),
                            "hmv_power_six")
-            n += 2
+            self._n += 2
             if overlap_d2h:
                 self.ev_chunk[ci].record()
                 self.copy_stream.wait_event(self.ev_chunk[ci])
@@ -354,32 +452,28 @@ class GridSix(object):
                     for q in range(6):       # one contiguous [z1-z0, nk] block per spectrum: plain async memcpys
                         self.h_p1[q, z0:z1].copy_(self.p1[q, z0:z1], non_blocking=True)
                         self.h_p2[q, z0:z1].copy_(self.p2[q, z0:z1], non_blocking=True)
-        self._mark(7)
-        if self.tsz:
-            # P_yy 1h+2h (hmvec.py:512-514, 541-545: pressure tracers, b = 0, no consistency terms)
-            if self.tsz_tables:
-                capi.check(L.hmv_power_tab(nz, nm, nk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
-                                           ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), _KIND_PRESSURE,
-                                           ptr(self.ytab), self.p_nxs, ptr(d["pair_ws"]), ptr(self.p1[6]),
-                                           ptr(self.p2[6]), st), "hmv_power_tab(yy)")
-            else:
-                capi.check(L.hmv_power(nz, nm, nk, ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
-                                       ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), C.byref(self.ty),
-                                       C.byref(self.ty), ptr(d["pair_ws"]), ptr(self.p1[6]), ptr(self.p2[6]), st),
-                           "hmv_power(yy)")
-            n += 2
-            if overlap_d2h:
-                self.ev_yy.record()
-                self.copy_stream.wait_event(self.ev_yy)
-                with torch.cuda.stream(self.copy_stream):
-                    self.h_p1[6].copy_(self.p1[6], non_blocking=True)
-                    self.h_p2[6].copy_(self.p2[6], non_blocking=True)
-        self._mark(8)
-        if self.has_limber:
-            n += self._limber(st)
-        self._mark(9)
-        self.launches_per_run = n
-        self._ev = None
+
+    def _st_yy(self, overlap_d2h):
+        # P_yy 1h+2h (hmvec.py:512-514, 541-545: pressure tracers, b = 0, no consistency terms)
+        L, d, ptr, p, st = capi.lib, self.d, capi.ptr, self.p, capi.stream()
+        nz, nm, nk = self.nz, self.nm, self.nk
+        if self.tsz_tables:
+            capi.check(L.hmv_power_tab(nz, nm, nk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                       ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), _KIND_PRESSURE,
+                                       ptr(self.ytab), self.p_nxs, ptr(d["pair_ws"]), ptr(self.p1[6]),
+                                       ptr(self.p2[6]), st), "hmv_power_tab(yy)")
+        else:
+            capi.check(L.hmv_power(nz, nm, nk, self.ldk, ptr(d["ms"]), ptr(d["ks"]), ptr(d["nzm"]), ptr(d["bh"]),
+                                   ptr(d["Pzk"]), self.rho_m0, float(p['kstar_damping']), C.byref(self.ty),
+                                   C.byref(self.ty), ptr(d["pair_ws"]), ptr(self.p1[6]), ptr(self.p2[6]), st),
+                       "hmv_power(yy)")
+        self._n += 2
+        if overlap_d2h:
+            self.ev_yy.record()
+            self.copy_stream.wait_event(self.ev_yy)
+            with torch.cuda.stream(self.copy_stream):
+                self.h_p1[6].copy_(self.p1[6], non_blocking=True)
+                self.h_p2[6].copy_(self.p2[6], non_blocking=True)
 
     def _hod_stage(self, main):
         # The HOD solve needs only n(M,z) and b(M,z), is latency-bound (one CTA per redshift, 24 + 40 bisection
@@ -434,18 +528,18 @@ class GridSix(object):
                 self.zcomm.all_gather_rows(self._Ppack.view(self.nz, nq * nk), self._Pfull.view(-1, nq * nk))
                 full = self._Pfull
         base, ldp, nzt = full.data_ptr(), nq * nk, full.shape[0]
-        tab = [C.c_void_p(base + 8 * q * nk) for q in range(nq)]
-        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
-                                tab[0], None, nzt, ptr(self.zs_all), ptr(d["pref_kk"]), ptr(d["chis"]),
-                                ptr(self.cl[0]), st), "hmv_limber(kk)")
-        capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
-                                tab[1], None, 1, ptr(d["gz"]), ptr(d["pref_kg"]), ptr(d["chig"]), ptr(self.cl[1]),
-                                st), "hmv_limber(kg)")
-        if nq > 2:
-            capi.check(L.hmv_limber(self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]),
-                                    tab[2], None, nzt, ptr(self.zs_all), ptr(d["pref_yy"]), ptr(d["chis"]),
-                                    ptr(self.cl[2]), st), "hmv_limber(yy)")
-        return nl0 + nq
+        # C_kk, C_kg (and C_yy) in one launch: each projection is latency-bound, so three cost the time of one
+        dp = lambda t: t.data_ptr()
+        jobs = (capi.LimberJob * nq)()
+        specs = [(nzt, self.zs_all, d["pref_kk"], d["chis"]), (1, d["gz"], d["pref_kg"], d["chig"]),
+                 (nzt, self.zs_all, d["pref_yy"], d["chis"])][:nq]
+        for q, (ngz, gzs, pref, chis) in enumerate(specs):
+            jobs[q].P_d, jobs[q].P2_d, jobs[q].ngz = base + 8 * q * nk, None, ngz
+            jobs[q].gzs_d, jobs[q].pref_d, jobs[q].chis_d, jobs[q].cl_d = dp(gzs), dp(pref), dp(chis), dp(self.cl[q])
+        capi.check(L.hmv_limber_multi(nq, jobs, self.nl, ptr(d["ells"]), nzt, nk, ldp, ptr(self.zs_all), ptr(d["ks"]), st),
+                   "hmv_limber_multi")
+        return nl0 + 1
+
 
     def spectra(self):
         """Download and return ({tag: P1h}, {tag: P2h}, C_kk, C_kg) as numpy (synchronises); with the tSZ leg the

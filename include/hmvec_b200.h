@@ -228,6 +228,21 @@ int hmv_limber(int nl, const double* ells_d, int nzp, int nk, int ldp, const dou
                const double* P_d, const double* P2_d, int ngz, const double* gzs_d, const double* pref_d,
                const double* chis_d, double* cl_d, void* stream);
 
+/* The same for up to HMV_LIMBER_MAXJOBS projections of tables that share the (zs, ks) grid and the multipoles, in one
+ * launch (C_kk, C_kg, C_yy of one step: cosmology.py:536-597).  jobs_h: HOST array; fields as in hmv_limber. */
+#define HMV_LIMBER_MAXJOBS 4
+typedef struct hmv_limber_job {
+  const double* P_d;     /* [nzp][ldp] table */
+  const double* P2_d;    /* optional second table added at lookup, or NULL */
+  int ngz;               /* window redshifts (1: no z integral) */
+  const double* gzs_d;   /* [ngz] */
+  const double* pref_d;  /* [ngz] H W1 W2 / chi^2 */
+  const double* chis_d;  /* [ngz] */
+  double* cl_d;          /* [nl] result */
+} hmv_limber_job;
+int hmv_limber_multi(int njobs, const hmv_limber_job* jobs_h, int nl, const double* ells_d, int nzp, int nk, int ldp,
+                     const double* zs_d, const double* ks_d, void* stream);
+
 /* Sum-and-pack in front of the one all-gather of a z-sharded run: out_d[z][s][k] = a_s[z][k] + b_s[z][k] for up to
  * four spectra (P1h + P2h of C_kk's P_mm, C_kg's P_gm, C_yy's P_yy, cosmology.py:536-597).  a_h / b_h: HOST arrays of
  * nsp device pointers to [nz][nk] tables (b_h or any b_h[s] may be NULL).  After all_gather the table of spectrum s is

@@ -21,6 +21,8 @@ def main():
     ap.add_argument("--world", type=int, default=8)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--nz", type=int, default=200)
+    ap.add_argument("--ranks", default="", help="comma-separated ranks to time (default: all)")
+    ap.add_argument("--partitions", default="contiguous,round_robin")
     a = ap.parse_args()
     import warnings
     warnings.filterwarnings("ignore")
@@ -33,9 +35,10 @@ def main():
     inp = pipeline.make_inputs(zs, ms, ks, ngal=ngal)
     b = zshard.slab_bounds(a.nz, a.world)
     out = {}
-    for name in ("contiguous", "round_robin"):
+    ranks = [int(x) for x in a.ranks.split(",") if x] or list(range(a.world))
+    for name in a.partitions.split(","):
         rows = []
-        for r in range(a.world):
+        for r in ranks:
             idx = np.arange(b[r], b[r + 1]) if name == "contiguous" else np.arange(r, a.nz, a.world)
             g = pipeline.GridSix(pipeline.slab_inputs(inp, idx))
             g.upload()
@@ -49,7 +52,24 @@ def main():
             torch.cuda.synchronize()
             st = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(nst - 1)] for e in evs]).mean(axis=0)
             tot = float(np.mean([e[0].elapsed_time(e[-1]) for e in evs]))
-            rows.append({"rank": r, "ms": tot, **{n: round(float(v), 3) for n, v in zip(g.STAGES, st)}})
+            # the launch sequence with the side streams: level 1 = sigma^2/n(M)/HOD leg, 2 = + electron and tSZ legs;
+            # interleaved repetitions so that clock / power drift hits every level alike
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            lv = {0: [], 1: [], 2: []}
+            for rep in range(3):
+                for level in (0, 1, 2):
+                    g.overlap = level
+                    for _ in range(2):
+                        g.run()
+                    torch.cuda.synchronize()
+                    e0.record()
+                    for s in range(a.steps):
+                        g.run()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    lv[level].append(e0.elapsed_time(e1) / a.steps)
+            rows.append({"rank": r, "ms": tot, **{"ms_level%d" % k: round(float(np.median(v)), 4) for k, v in lv.items()},
+                         **{n: round(float(v), 3) for n, v in zip(g.STAGES, st)}})
             print(name, json.dumps(rows[-1]), flush=True)
             del g
             torch.cuda.empty_cache()
