@@ -225,9 +225,13 @@ def api_step(hm, zc, zs, ms, ks, ells, ngal):
         h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
         h.add_hod("g", ngal=ngal[sl])
         P = {p: h.get_power(*p) for p in PAIRS}
-    # sharded: the gathered tables stay on the device (C_kk & co. accept CUDA tensors), no round trip through the host
-    full = (lambda x: zc.all_gather_host(x, to_host=False)) if zc is not None else (lambda x: x)
-    Pmm, Pgm, Pyy = full(P[("nfw", "nfw")]), full(P[("g", "nfw")]), full(P[("y", "y")])
+        if zc is not None:
+            # sharded: the three tables Limber integrates are gathered from their device copies and stay on the
+            # device (C_kk & co. accept CUDA tensors) -- no round trip through the host
+            Pmm, Pgm, Pyy = zc.all_gather_tables([h.get_power_device(*p)
+                                                  for p in (("nfw", "nfw"), ("g", "nfw"), ("y", "y"))])
+        else:
+            Pmm, Pgm, Pyy = P[("nfw", "nfw")], P[("g", "nfw")], P[("y", "y")]
     ckk = h.C_kk(ells, zs, ks, Pmm, lzs1=2.5, lzs2=2.5)
     ckg = h.C_kg(ells, zs, ks, Pgm, gzs=0.8, lzs=2.5)
     cyy = h.C_yy(ells, zs, ks, Pyy)

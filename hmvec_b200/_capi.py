@@ -164,3 +164,4 @@ def reset_copy_counters():
 
 def copy_counters():
     return tuple(_copied)
+

@@ -870,6 +870,17 @@ class HaloModel(Cosmology):
             return self._power(name, name2, True, True, b1, b2, kinds=k1, add=True)
         return self.get_power_1halo(name, name2) + self.get_power_2halo(name, name2, verbose, b1, b2)
 
+    def get_power_device(self, name, name2=None):
+        """get_power without the download: P1h + P2h as a CUDA tensor [nz,nk] (an extension of the reference's API for
+        device-side consumers -- the gather over the z-shards, C_kk & co., which accept CUDA tensors).  After
+        get_power on the standard pairs this is a lookup of the resident spectra."""
+        name2 = name if name2 is None else name2
+        k1, k2 = self._kinds_1h(name, name2), self._kinds_2h(name, name2)
+        if k1 != k2:
+            raise ValueError("get_power_device: %r x %r resolve to different tracers for the 1-halo and 2-halo terms"
+                             % (name, name2))
+        return self._power(name, name2, True, True, kinds=k1, to_host=False, add=True)
+
     def get_power_six(self, matter="nfw", electron="electron", hod="g", to_host=True, stacked=False):
         """{mm, ee, me, gg, gm, ge} 1h and 2h spectra in ONE pass over the two cubes (hmv_power_six).
 

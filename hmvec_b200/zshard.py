@@ -78,18 +78,24 @@ class ZComm(object):
         return out
 
     def all_gather_host(self, local, to_host=True):
-        """numpy [nz_local, n] slab -> [nz_total, n] on every rank (what a user of the drop-in API does with the per-rank
-        get_power results before the Limber integral): upload, one all-gather over NVLink, download.  to_host=False
-        skips the download and returns the CUDA tensor, which C_kk / C_kg / C_yy accept in place of a numpy table."""
+        """[nz_local, n] slab -> [nz_total, n] on every rank (what a user of the drop-in API does with the per-rank
+        get_power results before the Limber integral).  `local` is a numpy array (upload, gather over NVLink, download)
+        or the CUDA tensor HaloModel.get_power_device returns (no upload).  to_host=False skips the download and
+        returns the CUDA tensor, which C_kk / C_kg / C_yy accept in place of a numpy table."""
         from . import _capi as capi
-        h = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
-        t = h.to(dev, non_blocking=h.is_pinned()) if dev.type == "cuda" else h
+        if isinstance(local, torch.Tensor) and local.is_cuda:
+            # already on the device (HaloModel.get_power_device): nothing to upload
+            t, dev, h = local.to(torch.float64).contiguous(), local.device, None
+        else:
+            h = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64))
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+            t = h.to(dev, non_blocking=h.is_pinned()) if dev.type == "cuda" else h
         out = torch.empty((self.nz_total, t.shape[1]), dtype=torch.float64, device=dev)
         self.all_gather_rows(t, out)
         if dev.type != "cuda":
             return out.numpy()
-        capi.count_h2d(h.numel() * 8)
+        if h is not None:
+            capi.count_h2d(h.numel() * 8)
         if not to_host:
             return out
         capi.count_d2h(out.numel() * 8)
@@ -97,6 +103,18 @@ class ZComm(object):
         res.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return res.numpy()
+
+    def all_gather_tables(self, tables):
+        """Several CUDA [nz_local, n] slabs (HaloModel.get_power_device) -> their [nz_total, n] tables on every rank in
+        ONE exchange (one hmv_peer_scatter + hmv_peer_wait for all of them); one gather per table without peer access."""
+        tables = [t.to(torch.float64).contiguous() for t in tables]
+        n = int(tables[0].shape[1])
+        pg = self.peer_gather(len(tables) * n) if (len(tables) <= 4 and all(t.is_cuda and t.shape == tables[0].shape
+                                                                             for t in tables)) else None
+        if pg is None:
+            return [self.all_gather_host(t, to_host=False) for t in tables]
+        full = pg.gather(tables, None)                       # [nz_total, nsp, n], valid until the gather after next
+        return [full[:, s, :].contiguous() for s in range(len(tables))]
 
     def all_gather_z(self, local):
         """local: [..., nz_local, n] slab (z is dim -2) -> [..., nz_total, n] on every rank."""

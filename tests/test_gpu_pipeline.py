@@ -150,8 +150,24 @@ def _nccl_worker(rank, world, port, q, peer):
         rows_ok = bool(torch.equal(outp, torch.cat(parts, dim=0)))
         if gs._peer is not None:
             gs._peer.check()
+        # the drop-in API on this rank's slab: device-side gather of the three Limber tables in one exchange
+        import contextlib
+        import io
+        import hmvec_b200 as hm
+        with contextlib.redirect_stdout(io.StringIO()):
+            h = hm.HaloModel(g["zs"][zc.slab], g["ks"], ms=g["ms"], accuracy='low', zcomm=zc)
+            h.add_battaglia_profile("electron", family="AGN", xmax=20, nxs=5000)
+            h.add_battaglia_pres_profile("y", family="pres", xmax=20, nxs=5000)
+            h.add_hod("g2", ngal=g["g2_ngal_target"][zc.slab])
+            pairs = (("nfw", "nfw"), ("g2", "nfw"), ("y", "y"))
+            Ph = [h.get_power(*pr) for pr in pairs]
+            Pd = [h.get_power_device(*pr) for pr in pairs]
+        dev_ok = all(np.array_equal(a, b.cpu().numpy()) for a, b in zip(Ph, Pd))
+        Pmm, Pgm, Pyy = zc.all_gather_tables(Pd)
+        akk = h.C_kk(g["ells"], g["zs"], g["ks"], Pmm, lzs1=2.5, lzs2=2.5)
+        ayy = h.C_yy(g["ells"], g["zs"], g["ks"], Pyy)
         q.put((rank, zc.slab.start, zc.slab.stop, p1["ge"], p2["gg"], ckk, ckg, gs.last_cyy,
-               gs._peer is not None, rows_ok))
+               gs._peer is not None, rows_ok, dev_ok, akk, ayy))
     finally:
         dist.destroy_process_group()
 
@@ -184,6 +200,9 @@ def test_z_sharding_nccl_two_gpus(setup, peer):
         assert_close(o[7], g["C_yy"], 1e-6)
         assert o[8] == bool(peer), "peer-store gather %s" % ("was not used" if peer else "ran although switched off")
         assert o[9], "all_gather_rows differs from NCCL's all_gather"
+        assert o[10], "get_power_device differs from get_power"
+        assert_close(o[11], fkk, 1e-12, name="API C_kk over gathered device tables")
+        assert_close(o[12], g["C_yy"], 1e-6, name="API C_yy over gathered device tables")
 
 
 def test_large_grid_properties():
