@@ -656,7 +656,15 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 // wavenumbers from the halo's table row in L2 exactly as the transform's expansion does (fft.py:102-107).
 // Work is proportional to the interpolated elements (37 % on the LARGE grid).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int OT_K = 512, OT_T = 256;
+#ifndef HMV_OT_T
+#define HMV_OT_T 256          // threads per CTA (a thread owns two adjacent wavenumbers)
+#define HMV_OT_MINB 2         // CTAs per SM the register allocation aims at
+#define HMV_OT_UNROLL 6       // halos in flight per thread in the interior loop
+#endif
+// Measured on a 67-z slab (gpurun_out/r2_ot_variants.txt): 6 halos in flight 1.02 ms against 1.10 with 4 (8 spills);
+// prefetch instructions (L1 or L2) for the table line of the halo 4 / 8 / 16 positions ahead: 1.20-1.25 ms -- slower,
+// the extra address arithmetic costs more than the earlier arrival saves.
+constexpr int OT_T = HMV_OT_T, OT_K = 2 * OT_T, OT_UNROLL = HMV_OT_UNROLL;
 
 struct OneTabArgs {
   int nm, nk, nmp, JS, J;
@@ -665,7 +673,7 @@ struct OneTabArgs {
   double *p1h, *p2h;
 };
 
-__global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs a) {
+__global__ void __launch_bounds__(OT_T, HMV_OT_MINB) power_one_tab_kernel(const OneTabArgs a) {
   extern __shared__ __align__(16) unsigned char ot_smem[];
   double4* prm = reinterpret_cast<double4*>(ot_smem);              // per interpolated halo: {inv, u_1, a, b} (t = a + b u)
   double2* prm2 = reinterpret_cast<double2*>(prm + a.nm);          //                        {c4, w2}
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(OT_T, 2) power_one_tab_kernel(const OneTabArgs
   const double kx = a.ks[kc], ky = a.ks[kc1];
   double p1x = 0, p1y = 0, iAx = 0, iAy = 0;
   // interior halos: j = floor(t) needs no clamp, the value no classification
-#pragma unroll 4
+#pragma unroll OT_UNROLL
   for (int i = 0; i < nI; ++i) {
     const double4 q = prm[i];
     const double2 q2 = prm2[i];
