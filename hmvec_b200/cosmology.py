@@ -411,10 +411,13 @@ class Cosmology(object):
         return limber_integral(ells, zs, ks, Pgg, gzs, Wz1s, Wz2s, hzs, chis, device=self.device)
 
     def C_kk(self, ells, zs, ks, Pmm, lzs1=None, ldndz1=None, lzs2=None, ldndz2=None, lwindow1=None, lwindow2=None):
-        if lwindow1 is None:
+        own1 = lwindow1 is None
+        if own1:
             lwindow1 = self.lensing_window(zs, lzs1, ldndz1)
         if lwindow2 is None:
-            lwindow2 = self.lensing_window(zs, lzs2, ldndz2)
+            same = (own1 and ldndz1 is None and ldndz2 is None and lzs1 is not None and np.ndim(lzs1) == 0
+                    and np.ndim(lzs2) == 0 and lzs1 == lzs2)
+            lwindow2 = lwindow1 if same else self.lensing_window(zs, lzs2, ldndz2)     # the auto spectrum: one window
         chis = self.comoving_radial_distance(zs)
         hzs = self.h_of_z(zs)
         return limber_integral(ells, zs, ks, Pmm, zs, lwindow1, lwindow2, hzs, chis, device=self.device)
