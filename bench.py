@@ -388,6 +388,8 @@ def run_b200(a):
                            float(np.max(np.abs(ayy / gyy - 1.0))) if gyy is not None else 0.0)
     summ = summary_for_shard_check(aP, (akk, akg, ayy), world, dist, dev)
 
+    if zc is not None:
+        zc.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // The parameters of the next item are fetched into registers while the current one is being transformed.
 #ifndef HMV_K1_ABL
 #define HMV_K1_ABL 0       // measurement builds only, bit mask: 1 skip the sample evaluation, 2 skip the sine sums,
-#endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill
+#endif                     // 4 consumers skip the rows, 8 consumers store every block as a fill, 64 constant blocks are not stored
 constexpr int WS_HB = 16, WS_NG = 2, WS_GT = 256, WS_MAXCTA = 192;
 constexpr int WS_GS_DOUBLES = (NCH_MMA / 4) * 64;      // one sample buffer: 16 halos x NCH_MMA samples
 // sum over the lanes of the caller's parity (even lanes hold halos 0-7, odd lanes halos 8-15)
@@ -490,6 +490,12 @@ __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned 
 // that the queue drains on the lightest items of the launch whatever the slab size; the redshifts in front of them
 // stride through the mass axis (a mixed head that desynchronises the groups' phases).
 __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int ntail, int& z, int& q) {
+  if (ntail < 0) {                       // measurement variant: heaviest and lightest items of the launch alternate
+    const int n = nz * nmg, idx = (item & 1) ? n - 1 - (item >> 1) : (item >> 1);
+    q = idx / nz;
+    z = idx - q * nz;
+    return;
+  }
   const int nhead = (nz - ntail) * nmg;
   if (item < nhead) {
     z = item / nmg;
@@ -1027,11 +1033,13 @@ profile_transform_ws_kernel(const TParams p, double* ring, int* work_counter, in
           double2* orow = reinterpret_cast<double2*>(out0 + (long long)row * p.ldk) + base + lane;
           const double* Uh = tabbase + (size_t)(row - r0) * tabstride;
           if (c < 2) {
+#if !(HMV_K1_ABL & 64)                       // ablation 64: constant blocks are not stored (timing only)
             const double fv = c ? 0.0 : G.u1[row];
             const double2 v = make_double2(fv, fv);
 #pragma unroll
             for (int u = 0; u < WS_NU; ++u)
               if (whole || base + lane + 32 * u < npair) ws_store(orow + 32 * u, v);
+#endif
           } else if (c == 2) {
             const double inv = G.h_inv[row];
             unsigned jc[8], jo[8];
@@ -1122,7 +1130,7 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   int ntail = (3 * q.nz + 2) / 4;
   if (ntail < cdiv(2LL * grid * WS_NG, q.nmg)) ntail = cdiv(2LL * grid * WS_NG, q.nmg);
   if (const char* ev = getenv("HMV_K1_TAIL")) ntail = atoi(ev);          // measurement knob
-  ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
+  if (ntail >= 0) ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
   profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride, ntail);
   return check_launch("profile_transform_ws_kernel");
 }

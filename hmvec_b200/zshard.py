@@ -54,6 +54,16 @@ class ZComm(object):
             self._peer[ncols] = PeerGather.create(self, ncols)
         return self._peer[ncols]
 
+    def close(self):
+        """Collective: unmap and free the peer tables (after a barrier, so that no rank is still storing into them)."""
+        if any(pg is not None for pg in self._peer.values()):
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        for pg in self._peer.values():
+            if pg is not None:
+                pg.close()
+        self._peer = {}
+
     def all_reduce_and(self, mask):
         """In-place bitwise AND of a 1-element int64 tensor over the ranks (the global bisection stop condition).
         NCCL has no bitwise reductions, so the 64 bits travel as 64 int32 flags reduced with MIN."""
