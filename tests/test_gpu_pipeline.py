@@ -70,6 +70,34 @@ def test_gridsix_matches_golden_and_halomodel(setup, fused):
         gb.spectra()
 
 
+def test_side_stream_levels_are_bit_identical(setup):
+    """GridSix.overlap 0 / 1 / 2 (one stream; sigma^2 -> n(M) -> HOD leg beside the NFW cube; + electron and tSZ legs on
+    their own streams) and the serialised, event-marked pass bench.py takes its per-stage times from launch the same
+    kernels on the same data: every output must agree bit for bit, also over repeated steps (cross-step hazards)."""
+    import torch
+    g, inp, pipeline = setup
+    ref = None
+    for level in (0, 1, 2, "events"):
+        gs = pipeline.GridSix(inp)
+        gs.upload()
+        evs = None
+        if level == "events":
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(gs.STAGES) + 1)]
+        else:
+            gs.overlap = level
+        for _ in range(3):
+            gs.run(events=evs)
+        for _ in range(2):
+            gs.upload(); gs.run(overlap_d2h=True); gs.finish_e2e()
+        p1, p2, ckk, ckg = gs.spectra()
+        cur = [p1[t] for t in sorted(p1)] + [p2[t] for t in sorted(p2)] + [ckk, ckg, gs.last_cyy]
+        if ref is None:
+            ref = cur
+        else:
+            for a, b in zip(ref, cur):
+                assert np.array_equal(a, b), "overlap level %r changes the results" % (level,)
+
+
 class _StandInComm(object):
     """Plays the other rank of a 2-way z split on a single GPU: AND with the other slab's pass mask, all-gather by
     concatenating the other slab's stored spectra (slab order given by `first`)."""
