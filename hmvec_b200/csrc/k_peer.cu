@@ -70,6 +70,7 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int npeers, un
                                  long long timeout_cycles, int* status) {
   const int r = threadIdx.x;
   if (r >= npeers) return;
+  if (*reinterpret_cast<volatile int*>(status) != 0) return;     // an earlier wait gave up: fail fast, the host raises
   const long long t0 = clock64();
   while (ld_acquire_sys(flags + r) < step) {
     if (clock64() - t0 > timeout_cycles) { atomicExch(status, 1 + r); break; }

@@ -205,3 +205,50 @@ def test_pressure_profile_tables_and_lazy_cube(hm, golden_mini):
     assert_close(h.get_power_1halo("y", "y"), p1, 1e-12, name="P1h_yy cube vs tables")
     assert_close(h.get_power_2halo("y", "y"), p2, 1e-12, name="P2h_yy cube vs tables")
     assert_close(h.get_power_1halo("y", "nfw"), g["P1h_ym"], 1e-6, name="P1h_ym")
+
+
+def test_peer_exchange_on_one_rank_and_wait_timeout():
+    """The peer-store exchange (csrc/k_peer.cu) with a single rank whose 'peer' table is its own: hmv_peer_scatter packs
+    a_s + b_s into [nrow][nsp][ncol] (odd and even row lengths: scalar and 16-byte stores), publishes the step flag,
+    hmv_peer_wait passes; a wait for a flag nobody raises gives up after its timeout with the missing rank in the
+    status word instead of hanging, and every later wait returns at once."""
+    import ctypes as C
+    import time
+    import torch
+    from hmvec_b200 import _capi as capi
+    dev = torch.device("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for ncol in (130, 37):
+        nrow, nsp = 5, 3
+        a = [torch.rand((nrow, ncol), dtype=torch.float64, device=dev, generator=gen) for _ in range(nsp)]
+        b = [torch.rand((nrow, ncol), dtype=torch.float64, device=dev, generator=gen), None, a[0]]
+        out = torch.zeros((nrow + 2, nsp, ncol), dtype=torch.float64, device=dev)          # this rank's rows start at 1
+        flags = torch.zeros(16, dtype=torch.int64, device=dev)
+        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        pa = (C.c_void_p * nsp)(*[t.data_ptr() for t in a])
+        pb = (C.c_void_p * nsp)(*[t.data_ptr() if t is not None else None for t in b])
+        bufs, flg = (C.c_void_p * 1)(out.data_ptr()), (C.c_void_p * 1)(flags.data_ptr())
+        for step in (1, 2):
+            capi.check(capi.lib.hmv_peer_scatter(nrow, ncol, nsp, pa, pb, 1, 0, bufs, flg, 1, step,
+                                                 C.c_void_p(done.data_ptr()), capi.stream()), "hmv_peer_scatter")
+            capi.check(capi.lib.hmv_peer_wait(C.c_void_p(flags.data_ptr()), 1, step, 5.0,
+                                              C.c_void_p(status.data_ptr()), capi.stream()), "hmv_peer_wait")
+        torch.cuda.synchronize()
+        want = torch.stack([a[0] + b[0], a[1], a[2] + a[0]], dim=1)
+        assert torch.equal(out[1:1 + nrow], want) and float(out[0].abs().sum()) == 0.0 and float(out[-1].abs().sum()) == 0.0
+        assert int(flags[0]) == 2 and int(done[0]) == 0 and int(status[0]) == 0
+    # nobody raises flag 1 of a two-rank set: the wait gives up after 0.05 s
+    t0 = time.perf_counter()
+    capi.check(capi.lib.hmv_peer_wait(C.c_void_p(flags.data_ptr()), 2, 2, 0.05, C.c_void_p(status.data_ptr()),
+                                      capi.stream()), "hmv_peer_wait")
+    torch.cuda.synchronize()
+    assert int(status[0]) == 2 and time.perf_counter() - t0 < 2.0
+    t0 = time.perf_counter()
+    capi.check(capi.lib.hmv_peer_wait(C.c_void_p(flags.data_ptr()), 2, 3, 30.0, C.c_void_p(status.data_ptr()),
+                                      capi.stream()), "hmv_peer_wait")
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 1.0, "a wait behind a failed one must return at once"
+    with pytest.raises(capi.HmvError):
+        capi.check(capi.lib.hmv_peer_scatter(nrow, ncol, 5, pa, pb, 1, 0, bufs, flg, 0, 1,
+                                             C.c_void_p(done.data_ptr()), capi.stream()), "hmv_peer_scatter")
