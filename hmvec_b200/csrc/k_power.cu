@@ -663,7 +663,9 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 #endif
 // Measured on a 67-z slab (gpurun_out/r2_ot_variants.txt): 6 halos in flight 1.02 ms against 1.10 with 4 (8 spills);
 // prefetch instructions (L1 or L2) for the table line of the halo 4 / 8 / 16 positions ahead: 1.20-1.25 ms -- slower,
-// the extra address arithmetic costs more than the earlier arrival saves.
+// the extra address arithmetic costs more than the earlier arrival saves.  A ninth warp that walks the halo lists ahead
+// of the others and asks L2 for every halo's whole table segment with coalesced prefetches (32 / 96 / 256 halos
+// ahead): 1.60 ms against 1.03 (gpurun_out/r2_ot_pfw.txt) -- the gathers are not waiting for DRAM alone.
 constexpr int OT_T = HMV_OT_T, OT_K = 2 * OT_T, OT_UNROLL = HMV_OT_UNROLL;
 
 struct OneTabArgs {
