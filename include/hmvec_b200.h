@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - every `*_d` pointer is a DEVICE pointer to float64 (or int32 where typed so); the caller owns
- *     every buffer, including workspaces; the library never allocates device memory;
+ *     every buffer, including workspaces; the library never allocates device memory (exceptions: hmv_peer_alloc,
+ *     whose blocks must come from cudaMalloc to be exportable to the other ranks, and the self-timing hmv_bench_*);
  *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and asynchronous,
  *     no hidden synchronisation (except hmv_bench_* which time themselves with events);
  *   - return value 0 = ok, <0 = error (HMV_E_*); hmv_last_error() gives a thread-local message;
