@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(TT, (TABLE && TT == 256) ? (MAXNJ <= 4 ? 3 : 2
 // tiles runs 8 independent accumulator chains (DMMA dependent-issue latency ~49 cycles, 16 cycles of pipe each).
 // Items are issued in an order that strides through the mass axis (golden-ratio step), so light (store-bound) and heavy
 // (DMMA-bound) groups alternate in every SM's queue instead of arriving as one heavy and one light phase; the last
-// three quarters of the redshifts (see ws_item, launch_transform_ws) run jointly heavy-first so the queue drains on light items.
+// redshifts behind a short mixed head (see ws_item, launch_transform_ws) run jointly heavy-first so the queue drains on light items.
 // The parameters of the next item are fetched into registers while the current one is being transformed.
 #ifndef HMV_K1_ABL
 #define HMV_K1_ABL 0       // measurement builds only, bit mask: 1 skip the sample evaluation, 2 skip the sine sums,
@@ -1124,10 +1124,14 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   if (q.ts_Q > 0) smem += (size_t)(TS_A2_DOUBLES + WS_NG * TS_SLICE) * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  // Measured (gpurun_out/r2_k1_tail*.txt, electron profile): heavy-first over the last three quarters of the
-  // redshifts behind a mixed head beats both the all-mixed order with a short heavy-first tail (25 z: 1.33 -> 1.20 ms,
-  // 200 z: 9.18 -> 8.92 ms) and heavy-first from the start (1.26 / 2.99 ms on 25 / 64 z)
-  int ntail = (3 * q.nz + 2) / 4;
+  // Measured (gpurun_out/r2_k1_tail*.txt, electron profile): heavy-first behind a short mixed head of 4-6 redshifts
+  // beats both the all-mixed order with a one-redshift heavy-first tail (25 z: 1.33 -> 1.19 ms, 64 z: 3.06 -> 2.90,
+  // 200 z: 9.18 -> 8.90) and heavy-first from the start (1.26 / 2.99 ms on 25 / 64 z: every group then begins with
+  // the sine sums of a heaviest item and nothing is stored for the first third of a millisecond); the head's length
+  // matters little beyond that (a quarter of the redshifts: 1.20 / 2.93 / 8.94 ms)
+  int head = q.nz / 8;
+  head = head < 4 ? 4 : (head > 6 ? 6 : head);
+  int ntail = q.nz - head;
   if (ntail < cdiv(2LL * grid * WS_NG, q.nmg)) ntail = cdiv(2LL * grid * WS_NG, q.nmg);
   if (const char* ev = getenv("HMV_K1_TAIL")) ntail = atoi(ev);          // measurement knob
   if (ntail >= 0) ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
