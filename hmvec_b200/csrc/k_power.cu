@@ -656,6 +656,12 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 // wavenumbers from the halo's table row in L2 exactly as the transform's expansion does (fft.py:102-107).
 // Work is proportional to the interpolated elements (37 % on the LARGE grid).
 // ---------------------------------------------------------------------------------------------------------
+#ifndef HMV_OT_ORDER
+#define HMV_OT_ORDER 1        // 1: k tiles slow and descending (expensive tiles of every redshift first), 0: z slow
+#endif
+#ifndef HMV_OT_ZC
+#define HMV_OT_ZC 100         // ... within chunks of this many redshifts
+#endif
 #ifndef HMV_OT_T
 #define HMV_OT_T 256          // threads per CTA (a thread owns two adjacent wavenumbers)
 #define HMV_OT_MINB 2         // CTAs per SM the register allocation aims at
@@ -669,7 +675,7 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 constexpr int OT_T = HMV_OT_T, OT_K = 2 * OT_T, OT_UNROLL = HMV_OT_UNROLL;
 
 struct OneTabArgs {
-  int nm, nk, nmp, JS, J;
+  int nm, nk, nmp, JS, J, nz;
   const double *coef, *zoff, *ks, *Pzk, *tab, *tmeta;
   double kstar;
   double *p1h, *p2h;
@@ -683,7 +689,24 @@ __global__ void __launch_bounds__(OT_T, HMV_OT_MINB) power_one_tab_kernel(const 
   __shared__ double red[3][OT_T / 32];
   __shared__ int nlist, nlist2, wcnt[OT_T / 32], wcnt2[OT_T / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if HMV_OT_ORDER
+  // k tiles are the slow index, highest k first, within chunks of HMV_OT_ZC redshifts: a tile's cost is the number of
+  // halos it has to interpolate (none at low k, where every halo holds u_1), so the expensive tiles of every redshift
+  // go first and the launch drains on the trivial ones.  Measured against redshift-slow order (gpurun_out/
+  // r2_ot_order*.txt): 25 z 0.454 -> 0.385 ms, 67 z 1.013 -> 0.858, 100 z 1.49 -> 1.33, 200 z 2.63 -> 2.52 (chunks of
+  // 100; 2.58 unchunked, 2.74 with chunks of 32 or 64).
+  int z, k0;
+  {
+    const int T = (a.nk + OT_K - 1) / OT_K, per = HMV_OT_ZC * T;
+    const int c = blockIdx.x / per, r = blockIdx.x - c * per;
+    const int nzc = min(HMV_OT_ZC, a.nz - c * HMV_OT_ZC);
+    const int tr = r / nzc;
+    z = c * HMV_OT_ZC + (r - tr * nzc);
+    k0 = (T - 1 - tr) * OT_K;
+  }
+#else
   const int z = blockIdx.y, k0 = blockIdx.x * OT_K;
+#endif
   const long long zrow = (long long)z * a.nm, zrowp = (long long)z * a.nmp;
   const double tJ = (double)a.J;
   // wavenumber range of the tile (any order of ks)
@@ -1178,7 +1201,12 @@ extern "C" int hmv_power_tab(int nz, int nm, int nk, const double* ms_d, const d
   if (smem > 200 * 1024) return fail(HMV_E_LIMIT, "hmv_power_tab: nm=%d needs %zu B of shared memory", nm, smem);
   cudaError_t e = cudaFuncSetAttribute(power_one_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "power_one_tab_kernel smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
+#if HMV_OT_ORDER
+  dim3 grid((unsigned)nz * cdiv(nk, OT_K));
+  a.nz = nz;
+#else
   dim3 grid(cdiv(nk, OT_K), nz);
+#endif
   power_one_tab_kernel<<<grid, OT_T, smem, st>>>(a);
   return check_launch("power_one_tab_kernel");
 }
