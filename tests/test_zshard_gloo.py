@@ -34,6 +34,12 @@ def _worker(rank, world, port, nz, q):
         # the drop-in API's hand-over: per-rank numpy slabs -> the full numpy table on every rank (even and ragged slabs)
         host = zc.all_gather_host(full[2, zc.slab].numpy())
         ok_gather2 = ok_gather2 and isinstance(host, np.ndarray) and bool(np.array_equal(host, full[2].numpy()))
+        # several tables in one call (the API's Limber hand-over); without peer access this is one gather per table,
+        # and ZComm.close() is a no-op
+        tabs = zc.all_gather_tables([full[i, zc.slab].contiguous() for i in (0, 3)])
+        ok_gather2 = ok_gather2 and all(bool(np.array_equal(np.asarray(t), full[i].numpy())) for t, i in zip(tabs, (0, 3)))
+        ok_gather2 = ok_gather2 and zc.peer_gather(6) is None
+        zc.close()
         # rank 0 passes from iteration 3 on, rank 1 from iteration 5 on -> global first pass = iteration 5
         mask = torch.tensor([(~0) << (3 if rank == 0 else 5)], dtype=torch.int64)
         zc.all_reduce_and(mask)
