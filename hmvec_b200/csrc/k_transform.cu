@@ -1133,7 +1133,8 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   head = head < 4 ? 4 : (head > 6 ? 6 : head);
   int ntail = q.nz - head;
   if (ntail < cdiv(2LL * grid * WS_NG, q.nmg)) ntail = cdiv(2LL * grid * WS_NG, q.nmg);
-  if (const char* ev = getenv("HMV_K1_TAIL")) ntail = atoi(ev);          // measurement knob
+  if (const char* ev = getenv("HMV_K1_TAIL"))                            // measurement knob
+    if (*ev) ntail = atoi(ev);
   if (ntail >= 0) ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
   profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride, ntail);
   return check_launch("profile_transform_ws_kernel");
