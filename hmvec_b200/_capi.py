@@ -92,6 +92,9 @@ _SIGS = {
     "hmv_peer_scatter": (_i, [_i, _i, _i, C.POINTER(_p), C.POINTER(_p), _i, _i, C.POINTER(_p), C.POINTER(_p), _ll,
                               C.c_ulonglong, _p, _p]),
     "hmv_peer_wait": (_i, [_p, _i, C.c_ulonglong, _d, _p, _p]),
+    "hmv_debug_k1_order": (_i, [_i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "hmv_debug_wave_tile": (_i, [_i, _i]),
+    "hmv_debug_tab_order": (_i, [_i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "hmv_pk_spline": (_i, [_i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _d, _p, _p]),
     "hmv_outer": (_i, [_i, _i, _p, _p, _p, _p]),
     "hmv_sum2": (_i, [_ll, _p, _p, _p, _p]),

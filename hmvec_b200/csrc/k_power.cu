@@ -674,6 +674,17 @@ __global__ void __launch_bounds__(TAB_CT + 32, 1) power_six_tab_kernel(const Six
 // ahead): 1.60 ms against 1.03 (gpurun_out/r2_ot_pfw.txt) -- the gathers are not waiting for DRAM alone.
 constexpr int OT_T = HMV_OT_T, OT_K = 2 * OT_T, OT_UNROLL = HMV_OT_UNROLL;
 
+// launch position -> (redshift, first wavenumber of the tile) of power_one_tab_kernel's tile-slow order
+__host__ __device__ __forceinline__ void ot_cta(int id, int nz, int nk, int& z, int& k0) {
+  const int T = (nk + OT_K - 1) / OT_K, per = HMV_OT_ZC * T;
+  const int c = id / per, r = id - c * per;
+  const int left = nz - c * HMV_OT_ZC;
+  const int nzc = left < HMV_OT_ZC ? left : HMV_OT_ZC;
+  const int tr = r / nzc;
+  z = c * HMV_OT_ZC + (r - tr * nzc);
+  k0 = (T - 1 - tr) * OT_K;
+}
+
 struct OneTabArgs {
   int nm, nk, nmp, JS, J, nz;
   const double *coef, *zoff, *ks, *Pzk, *tab, *tmeta;
@@ -696,14 +707,7 @@ __global__ void __launch_bounds__(OT_T, HMV_OT_MINB) power_one_tab_kernel(const 
   // r2_ot_order*.txt): 25 z 0.454 -> 0.385 ms, 67 z 1.013 -> 0.858, 100 z 1.49 -> 1.33, 200 z 2.63 -> 2.52 (chunks of
   // 100; 2.58 unchunked, 2.74 with chunks of 32 or 64).
   int z, k0;
-  {
-    const int T = (a.nk + OT_K - 1) / OT_K, per = HMV_OT_ZC * T;
-    const int c = blockIdx.x / per, r = blockIdx.x - c * per;
-    const int nzc = min(HMV_OT_ZC, a.nz - c * HMV_OT_ZC);
-    const int tr = r / nzc;
-    z = c * HMV_OT_ZC + (r - tr * nzc);
-    k0 = (T - 1 - tr) * OT_K;
-  }
+  ot_cta(blockIdx.x, a.nz, a.nk, z, k0);
 #else
   const int z = blockIdx.y, k0 = blockIdx.x * OT_K;
 #endif
@@ -1255,4 +1259,23 @@ extern "C" int hmv_power_six_nfw(int nz, int nm, int nk, int ldk, const double* 
   dim3 grid(nz, cdiv(ldk, SIX_K));
   power_six_nfw_kernel<<<grid, FSX_CT + 32, FSX_SMEM, st>>>(a);
   return check_launch("power_six_nfw_kernel");
+}
+
+// host-side introspection for the CPU tests: the k-tile width hmv_power_six picks for an nz x ldk launch, and the
+// (z, k0) of every CTA of hmv_power_tab's launch order (returns the tile width of that kernel)
+extern "C" int hmv_debug_wave_tile(int nz, int ldk) {
+  HMV_REQUIRE(nz > 0 && ldk > 0, "hmv_debug_wave_tile: bad sizes");
+  return wave_tile(nz, ldk, SIX_K, 1);
+}
+extern "C" int hmv_debug_tab_order(int nz, int nk, int* z_out, int* k0_out) {
+  HMV_REQUIRE(nz > 0 && nk > 0 && z_out && k0_out, "hmv_debug_tab_order: bad arguments");
+  const int T = cdiv(nk, OT_K);
+  for (int i = 0; i < nz * T; ++i) {
+#if HMV_OT_ORDER
+    ot_cta(i, nz, nk, z_out[i], k0_out[i]);
+#else
+    z_out[i] = i / T; k0_out[i] = (i % T) * OT_K;
+#endif
+  }
+  return OT_K;
 }

@@ -489,7 +489,7 @@ __device__ __forceinline__ void ws_lerp_interior(double k, double inv, unsigned 
 // The last `ntail` redshifts are issued jointly heavy-first -- mass group by mass group across those redshifts -- so
 // that the queue drains on the lightest items of the launch whatever the slab size; the redshifts in front of them
 // stride through the mass axis (a mixed head that desynchronises the groups' phases).
-__device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int ntail, int& z, int& q) {
+__host__ __device__ __forceinline__ void ws_item(int item, int nz, int nmg, int stride, int ntail, int& z, int& q) {
   if (ntail < 0) {                       // measurement variant: heaviest and lightest items of the launch alternate
     const int n = nz * nmg, idx = (item & 1) ? n - 1 - (item >> 1) : (item >> 1);
     q = idx / nz;
@@ -1105,6 +1105,32 @@ static bool ws_ring_fits(int nxs) {
 
 static int g_transform_mode = 0;   // 0: warp-specialised persistent kernel; 1: bin-count-class kernels
 
+// stride through the mass groups with a step near nmg/phi^2 that is coprime to nmg (a permutation of 0..nmg-1)
+static int ws_stride(int nmg) {
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  int stride = (int)(0.381966 * nmg);
+  if (stride < 1) stride = 1;
+  while (gcd(stride, nmg) != 1) ++stride;
+  return stride;
+}
+
+// how many redshifts the queue issues jointly heavy-first (see ws_item)
+static int ws_tail(int nz, int nmg, int grid) {
+  // Measured (gpurun_out/r2_k1_tail*.txt, electron profile): heavy-first behind a short mixed head of 4-6 redshifts
+  // beats both the all-mixed order with a one-redshift heavy-first tail (25 z: 1.33 -> 1.19 ms, 64 z: 3.06 -> 2.90,
+  // 200 z: 9.18 -> 8.90) and heavy-first from the start (1.26 / 2.99 ms on 25 / 64 z: every group then begins with
+  // the sine sums of a heaviest item and nothing is stored for the first third of a millisecond); the head's length
+  // matters little beyond that (a quarter of the redshifts: 1.20 / 2.93 / 8.94 ms)
+  int head = nz / 8;
+  head = head < 4 ? 4 : (head > 6 ? 6 : head);
+  int ntail = nz - head;
+  if (ntail < cdiv(2LL * grid * WS_NG, nmg)) ntail = cdiv(2LL * grid * WS_NG, nmg);
+  if (const char* ev = getenv("HMV_K1_TAIL"))                            // measurement knob
+    if (*ev) ntail = atoi(ev);
+  if (ntail >= 0) ntail = ntail < 1 ? 1 : (ntail > nz ? nz : ntail);
+  return ntail;
+}
+
 static int launch_transform_ws(const TParams& p, double* ring, int* counter, cudaStream_t st) {
   int dev = 0, nsm = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -1115,27 +1141,12 @@ static int launch_transform_ws(const TParams& p, double* ring, int* counter, cud
   q.jlo = 0; q.jhi = p.J; q.JS = ws_js(p.N);
   const int nitems = q.nz * q.nmg;
   const int grid = nitems < nsm ? nitems : (nsm < WS_MAXCTA ? nsm : WS_MAXCTA);
-  // stride through the mass groups with a step near nmg/phi^2 that is coprime to nmg (a permutation of 0..nmg-1)
-  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
-  int stride = (int)(0.381966 * q.nmg);
-  if (stride < 1) stride = 1;
-  while (gcd(stride, q.nmg) != 1) ++stride;
+  const int stride = ws_stride(q.nmg);
   size_t smem = (size_t)WS_NG * WS_GS_DOUBLES * sizeof(double);
   if (q.ts_Q > 0) smem += (size_t)(TS_A2_DOUBLES + WS_NG * TS_SLICE) * sizeof(double);
   e = cudaFuncSetAttribute(profile_transform_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(HMV_E_CUDA, "profile_transform smem opt-in (%zu B): %s", smem, cudaGetErrorString(e));
-  // Measured (gpurun_out/r2_k1_tail*.txt, electron profile): heavy-first behind a short mixed head of 4-6 redshifts
-  // beats both the all-mixed order with a one-redshift heavy-first tail (25 z: 1.33 -> 1.19 ms, 64 z: 3.06 -> 2.90,
-  // 200 z: 9.18 -> 8.90) and heavy-first from the start (1.26 / 2.99 ms on 25 / 64 z: every group then begins with
-  // the sine sums of a heaviest item and nothing is stored for the first third of a millisecond); the head's length
-  // matters little beyond that (a quarter of the redshifts: 1.20 / 2.93 / 8.94 ms)
-  int head = q.nz / 8;
-  head = head < 4 ? 4 : (head > 6 ? 6 : head);
-  int ntail = q.nz - head;
-  if (ntail < cdiv(2LL * grid * WS_NG, q.nmg)) ntail = cdiv(2LL * grid * WS_NG, q.nmg);
-  if (const char* ev = getenv("HMV_K1_TAIL"))                            // measurement knob
-    if (*ev) ntail = atoi(ev);
-  if (ntail >= 0) ntail = ntail < 1 ? 1 : (ntail > q.nz ? q.nz : ntail);
+  const int ntail = ws_tail(q.nz, q.nmg, grid);
   profile_transform_ws_kernel<<<grid, WS_NG * WS_GT, smem, st>>>(q, ring, counter, nitems, stride, ntail);
   return check_launch("profile_transform_ws_kernel");
 }
@@ -1333,4 +1344,15 @@ extern "C" int hmv_profile_expand(int nz, int nm, int nk, int ldk, const double*
   HMV_REQUIRE(tab_d, "hmv_profile_expand: null table array");
   return profile_transform_impl(nz, nm, nk, ldk, zs_d, ks_d, kmax, rs_d, nullptr, nullptr, nullptr, nullptr, nullptr,
                                 nullptr, nullptr, 0.0, xmax, nxs, 0, ws_d, uk_d, stream, const_cast<double*>(tab_d), 2);
+}
+
+// host-side introspection for the CPU tests: the (z, mass group) of every queue position of the persistent kernel for
+// an nz x nm grid on `grid` CTAs (0 = 148) -- the order must be a permutation of all items
+extern "C" int hmv_debug_k1_order(int nz, int nm, int grid, int* z_out, int* q_out) {
+  HMV_REQUIRE(nz > 0 && nm > 0 && z_out && q_out, "hmv_debug_k1_order: bad arguments");
+  const int nmg = cdiv(nm, WS_HB);
+  if (grid <= 0) grid = 148;
+  const int stride = ws_stride(nmg), ntail = ws_tail(nz, nmg, grid);
+  for (int i = 0; i < nz * nmg; ++i) ws_item(i, nz, nmg, stride, ntail, z_out[i], q_out[i]);
+  return nmg;
 }

@@ -272,6 +272,16 @@ int hmv_peer_scatter(int nrow, int ncol, int nsp, const double* const* a_h, cons
 int hmv_peer_wait(const void* flags_d, int npeers, unsigned long long step, double timeout_s, int* status_d,
                   void* stream);
 
+/* ---- launch-order introspection (host only, no device work): what the CPU tests check --------------------------
+ * hmv_debug_k1_order: (z, mass group counted from the heavy end) of every position of hmv_profile_transform's work
+ *   queue on an nz x nm grid with `grid` CTAs (0 = 148); z_out/q_out: HOST arrays of nz*ceil(nm/16) ints; returns the
+ *   number of mass groups.  hmv_debug_wave_tile: the k-tile width hmv_power_six picks for nz redshifts of ldk columns.
+ * hmv_debug_tab_order: (z, first wavenumber) of every CTA of hmv_power_tab in launch order; HOST arrays of
+ *   nz*ceil(nk/tile) ints; returns the tile width.  Every (z, group) / (z, tile) must occur exactly once. */
+int hmv_debug_k1_order(int nz, int nm, int grid, int* z_out, int* q_out);
+int hmv_debug_wave_tile(int nz, int ldk);
+int hmv_debug_tab_order(int nz, int nk, int* z_out, int* k0_out);
+
 /* ---- f2: kSZ consumer -- the short-wavelength integral of the velocity-reconstruction noise
  * (ksz.py:299-336, Nvv_core_integral):  out[b] = trapz_kS( kS Pge[b,kS]^2 / (Pgg_tot[b,kS] C_tot(chi* kS)) ) with
  * non-finite integrand values set to zero (ksz.py:98-100).  b = 0..nb-1 runs over the (mu,kL) plane when the spectra

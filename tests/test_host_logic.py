@@ -115,3 +115,44 @@ def test_pk_table_preparation_matches_oracle():
     import pytest
     with pytest.raises(ValueError):
         _table_for_spline(ks, zs, pk * np.cos(2.0 * np.log(ks))[None, :], True, 150.0)
+
+
+def test_launch_orders_are_permutations():
+    """The work orders the kernels pick for load balance (host-side introspection entry points, no device work): the
+    profile transform's queue (a mixed head, then jointly heavy-first) and the tile-slow order of the table reduction
+    must visit every (z, mass group) / (z, k tile) exactly once for any grid, incl. ragged ones and slabs shorter than
+    the head; the six-spectra kernel's tile width stays a multiple of 16 within [448, 512]."""
+    import ctypes as C
+    import os
+    from hmvec_b200 import _capi as capi
+    os.environ.pop("HMV_K1_TAIL", None)
+    os.environ.pop("HMV_TILE", None)
+    for nz, nm, grid in ((1, 16, 0), (3, 48, 0), (6, 200, 0), (25, 2000, 0), (64, 2000, 148), (200, 2000, 148),
+                         (7, 37, 4), (40, 1000, 16)):
+        nmg = -(-nm // 16)
+        z = (C.c_int * (nz * nmg))()
+        q = (C.c_int * (nz * nmg))()
+        assert capi.lib.hmv_debug_k1_order(nz, nm, grid, z, q) == nmg
+        seen = {(z[i], q[i]) for i in range(nz * nmg)}
+        assert len(seen) == nz * nmg and all(0 <= a < nz and 0 <= b < nmg for a, b in seen), (nz, nm, grid)
+        if nz >= 25:
+            # the launch ends on the lightest mass groups (q counts from the heavy end) of the heavy-first redshifts
+            assert q[nz * nmg - 1] == nmg - 1 and q[nz * nmg - 2] == nmg - 1
+    os.environ["HMV_K1_TAIL"] = "-1"          # measurement variant: heaviest and lightest items alternate
+    try:
+        z, q = (C.c_int * (6 * 13))(), (C.c_int * (6 * 13))()
+        capi.lib.hmv_debug_k1_order(6, 200, 0, z, q)
+        assert len({(z[i], q[i]) for i in range(6 * 13)}) == 6 * 13
+    finally:
+        del os.environ["HMV_K1_TAIL"]
+    for nz, nk in ((1, 10), (6, 1001), (25, 10000), (100, 10000), (130, 3000), (200, 10000), (201, 513)):
+        n = nz * (-(-nk // 512))
+        z, k0 = (C.c_int * n)(), (C.c_int * n)()
+        tile = capi.lib.hmv_debug_tab_order(nz, nk, z, k0)
+        assert tile == 512
+        seen = {(z[i], k0[i]) for i in range(n)}
+        assert len(seen) == n and all(0 <= a < nz and 0 <= b < nk and b % tile == 0 for a, b in seen), (nz, nk)
+        assert k0[0] == (-(-nk // 512) - 1) * 512 and k0[n - 1] == 0      # highest wavenumbers first, lowest last
+    tiles = {nz: capi.lib.hmv_debug_wave_tile(nz, 10000) for nz in (12, 13, 25, 50, 100, 200)}
+    assert all(t % 16 == 0 and 448 <= t <= 512 for t in tiles.values()), tiles
+    assert tiles[25] == 448 and tiles[50] == tiles[100] == tiles[200] == 512, tiles
