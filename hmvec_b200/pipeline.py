@@ -275,7 +275,10 @@ class GridSix(object):
         self._ev = events
         self._n = 0
         main = torch.cuda.current_stream()
-        level = self.overlap if (self.hod_overlap and events is None) else 0
+        # with stage events everything, the HOD solve included, runs on the current stream: its stage time is then a
+        # kernel time, not the time it takes to queue work on a side stream
+        hod_side = self.hod_overlap and events is None
+        level = self.overlap if hod_side else 0
         side, legs = level >= 1, level >= 2 and not self.fused_nfw
         self._mark(0)
         if side:
@@ -284,15 +287,15 @@ class GridSix(object):
                 self.hod_stream.wait_event(self.ev_geo)
                 self._st_sigma2()
                 self._st_massfn()
-                self._hod_stage(self.hod_stream)
+                self._hod_stage(self.hod_stream, self.hod_stream)
         else:
             self._st_sigma2()
             self._mark(1)
             self._st_massfn()
         self._st_geometry()
         self._mark(2)
-        if self.hod_overlap and not side:
-            self._hod_stage(main)                  # side stream, concurrent with the cube kernels
+        if hod_side and not side:
+            self._hod_stage(main, self.hod_stream)     # side stream, concurrent with the cube kernels
         if legs:
             self.ev_geo2.record(main)
         if not self.fused_nfw:
@@ -321,12 +324,12 @@ class GridSix(object):
             else:
                 self._st_pressure(self.d["tr_ws"])
         self._mark(5)
-        if not self.hod_overlap:
-            self._hod_stage(main)
+        if not hod_side:
+            self._hod_stage(main, main)
         self._n += 6
         self._mark(6)
         main.wait_event(self.ev_pzk)                 # Pzk of this step has arrived (see upload)
-        if self.hod_overlap:
+        if hod_side:
             main.wait_event(self.ev_hod)             # n(M), b(M), occupations, ngal, bg are in place
         if legs:
             main.wait_event(self.ev_e)
@@ -475,12 +478,11 @@ class GridSix(object):
                 self.h_p1[6].copy_(self.p1[6], non_blocking=True)
                 self.h_p2[6].copy_(self.p2[6], non_blocking=True)
 
-    def _hod_stage(self, main):
+    def _hod_stage(self, main, hs):
         # The HOD solve needs only n(M,z) and b(M,z), is latency-bound (one CTA per redshift, 24 + 40 bisection
         # iterations, two flag all-reduces when z is sharded) and writes only [nz,nm] arrays: it runs on a side stream
         # next to the two cube kernels and rejoins in front of the mass integrals.
         self.ev_mf.record(main)
-        hs = self.hod_stream if self.hod_overlap else main
         L, d, ptr, p, nz, nm = capi.lib, self.d, capi.ptr, self.p, self.nz, self.nm
         with torch.cuda.stream(hs):
             hs.wait_event(self.ev_mf)
